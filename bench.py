@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffMVS / CasDiffMVS inference hot path (ref-views/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+A *step* is one forward of `CasDiffMVS` for one reference view (the region the reference times in
+`/root/reference/test.py:122-127`) on synthetic DTU-shaped inputs (`diffmvs_b200/synth.py`).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ref-views/sec at DTU 1600x1152xD384x7-view; depth L1 vs ref"
+UNIT = "ref-views/s"
+# algorithmic bytes per ref-view at cfg3 with ideal per-operator fusion (fp32)
+ALGO_BYTES_CFG3 = 2.75e9
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def _oracle_forward_cpu(workload: str, threads: int):
+    """One CPU forward of the oracle port on `threads` host threads; returns seconds."""
+    import torch
+    from diffmvs_b200 import synth
+    from oracle import diffmvs_ref as O
+    from oracle import spec
+    torch.set_num_threads(threads)
+    args = synth.workload_args(workload)
+    sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
+    imgs, proj, dv = synth.workload_inputs(workload)
+    gen = torch.Generator().manual_seed(1)
+    randn = lambda like: torch.randn(like.shape, generator=gen, dtype=torch.float32)
+
+    def run():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.casdiffmvs_forward(sd, args, imgs, proj, dv, randn=randn)
+        return time.perf_counter() - t0
+    return run
+
+
+def run_reference(a):
+    """`--impl reference`: the reference algorithm on the host cores (oracle port; the Python reference cannot
+    travel to the GPU box and needs a CUDA device at import)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    run = _oracle_forward_cpu(a.workload, cores)
+    first = run()                                   # warm-up (thread pools, allocator)
+    budget = 200.0
+    n_warm = max(0, min(a.warmup - 1, int(20.0 / max(first, 1e-3))))
+    for _ in range(n_warm):
+        run()
+    n = max(1, min(a.steps, int(budget / max(first, 1e-3))))
+    times = [run() for _ in range(n)]
+    sec = sum(times) / len(times)
+    value = 1.0 / sec
+    sample = f"{n} timed forward(s) of 1 ref-view at {a.workload} (of --steps {a.steps}), {n_warm + 1} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": a.workload, "views": _views(a.workload)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _views(workload):
+    from diffmvs_b200 import synth
+    return synth.WORKLOADS[workload][3]
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from diffmvs_b200 import _cabi, ops, synth
+    from diffmvs_b200.models import CasDiffMVS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+
+    variant, H, W, V, D0 = synth.WORKLOADS[a.workload]
+    args = synth.workload_args(a.workload)
+    model = CasDiffMVS(args, test=True)
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+    model.load_state_dict(synth.synth_state_dict(shapes, 123), strict=False)
+    model.to(dev).eval()
+
+    # each rank owns its own reference views (weak scaling: one ref-view per step per GPU)
+    imgs, proj, dv = synth.workload_inputs(a.workload, seed=rank)
+    h_imgs = [i.pin_memory() for i in imgs]
+    h_proj = {k: v.pin_memory() for k, v in proj.items()}
+    h_dv = dv.pin_memory()
+    d_imgs = [i.to(dev) for i in imgs]
+    d_proj = {k: v.to(dev) for k, v in proj.items()}
+    d_dv = dv.to(dev)
+    h2d = sum(t.numel() * 4 for t in h_imgs) + sum(t.numel() * 4 for t in h_proj.values()) + h_dv.numel() * 4
+    gather_buf = [torch.empty((1, H, W), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def step_resident():
+        out = model(d_imgs, d_proj, d_dv)
+        if world > 1:   # single gather of the per-view result to rank 0
+            dist.gather(out["depth"][-1], gather_buf, dst=0)
+        return out
+
+    h_out = {}
+
+    def step_e2e():
+        di = [t.to(dev, non_blocking=True) for t in h_imgs]
+        dp = {k: t.to(dev, non_blocking=True) for k, t in h_proj.items()}
+        dd = h_dv.to(dev, non_blocking=True)
+        out = model(di, dp, dd)
+        res = [out["depth"][-1]] + list(out["photometric_confidence"])
+        for i, t in enumerate(res):
+            if i not in h_out:
+                h_out[i] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h_out[i].copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the caller holds the result, as test.py:130 does
+        return sum(t.numel() * 4 for t in res)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms[0].item(), ms[1].item()
+
+    with torch.no_grad():
+        for _ in range(max(a.warmup, 3)):
+            step_resident()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = lib.dmvs_launch_count()
+        ms_dev, ms_wall = timed(step_resident, a.steps)
+        launches = lib.dmvs_launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        # end to end through the public API with host buffers
+        d2h = step_e2e()
+        step_e2e()
+        _, e2e_wall = timed(step_e2e, a.steps)
+        # per-kernel-family device time over one more step (CUDA events on the launch stream)
+        prof = ops.Profiler()
+        ops.set_profiler(prof)
+        step_resident()
+        ops.set_profiler(None)
+        summ = prof.summary() if rank == 0 else {}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_dev / a.steps
+    value = world * a.steps / (ms_dev / 1e3)
+    e2e_value = world * a.steps / (e2e_wall / 1e3)
+    peak, peak_src = _peaks()
+    # dominant kernel family by device time
+    fam = {}
+    for (name, tag), r in summ.items():
+        f = fam.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
+        f["ms"] += r["ms"]; f["bytes"] += r["bytes"]; f["calls"] += r["calls"]
+    tot_ms = sum(f["ms"] for f in fam.values()) or 1.0
+    top_name = max(fam, key=lambda k: fam[k]["ms"]) if fam else "n/a"
+    top = fam.get(top_name, {"ms": 1.0, "bytes": 0, "calls": 1})
+    achieved = top["bytes"] / (top["ms"] / 1e3) / 1e9 if top["ms"] > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": f"dmvs_{top_name} (all launches of one step)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "share_of_step": top["ms"] / tot_ms, "launches_per_step": top["calls"],
+        "whole_step": {"algorithmic_bytes": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7),
+                       "achieved": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7) / (ms_step / 1e3) / 1e9,
+                       "frac": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7) / (ms_step / 1e3) / 1e9 / peak},
+        "families_ms": {k: round(v["ms"], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+    }
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        run = _oracle_forward_cpu(a.workload, cores)
+        t = run()
+        if t < 10.0:
+            t = min(t, run())
+        cpu = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 ref-view at {a.workload} (one full step), oracle port on {cores} host threads"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": a.workload, "variant": variant, "image": [W, H], "views": V, "numdepth_initial": D0,
+                   "numdepth": 384, "batch": 1, "l2": "inputs (155 MB at cfg3) and per-step working set exceed L2",
+                   "parallelism": f"ref-views sharded, {world} GPU(s), no data-path collective"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "wall_ms_per_step": ms_wall / a.steps,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,67 @@
+// Shared device helpers for the diffmvs_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "diffmvs_b200.h"
+
+#define DMVS_STR2(x) #x
+#define DMVS_STR(x) DMVS_STR2(x)
+
+namespace dmvs {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+__device__ __forceinline__ float siluf_(float v) { return v / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case DMVS_ACT_RELU: return fmaxf(v, 0.0f);
+    case DMVS_ACT_SIGMOID: return sigmoidf_(v);
+    case DMVS_ACT_TANH: return tanhf(v);
+    case DMVS_ACT_SILU: return siluf_(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// disp_to_depth / depth_to_disp of the reference (module.py:220-235), evaluated from the same
+// `depth_min`, `depth_max` tensors the reference passes around (diffusion.py:140-146).
+struct DepthRange {
+  float min_disp, span;
+  __device__ __forceinline__ DepthRange(float depth_min, float depth_max) {
+    min_disp = 1.0f / depth_max;
+    const float max_disp = 1.0f / depth_min;
+    span = max_disp - min_disp;
+  }
+  __device__ __forceinline__ float to_depth(float n) const {
+    // __fmaf_rn would fuse the rounding; the reference rounds the product first.
+    const float scaled = fmaxf(__fadd_rn(min_disp, __fmul_rn(span, n)), 1e-6f);
+    return 1.0f / scaled;
+  }
+  __device__ __forceinline__ float to_norm(float depth) const {
+    return __fdiv_rn(__fsub_rn(1.0f / depth, min_disp), span);
+  }
+};
+
+// Number of kernels this library has launched in this process (bench.py reports it as gpu_launches).
+extern unsigned long long g_launch_count;
+
+inline int launch_status() {
+  ++g_launch_count;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+}  // namespace dmvs

@@ -1,0 +1,470 @@
+// Direct fp32 convolution (2-D / 3-D, channels-last) with fused prologue/epilogue, and the 3-D
+// transposed convolution of CostRegNet_small.  See include/diffmvs_b200.h for the contract.
+//
+// Design (B200, HBM/L2-bound layers with 3..64 channels):
+//   * one CTA = 256 threads = 8 warps computes a 32-wide output tile; a warp owns PX output rows
+//     (lane = x) and CO_T output channels, accumulating PX*CO_T values in registers;
+//   * the input tile (with halo) and the weight slab of one input-channel chunk are staged in shared
+//     memory; activations are read as 128-bit vectors along channels with a padded pixel pitch
+//     (bank-conflict free), weights as warp-uniform broadcast vectors;
+//   * GroupNorm+SiLU of the producer layer is applied while staging (no extra pass over HBM), and
+//     the GroupNorm statistics of this layer's output are reduced in the epilogue.
+#include "common.cuh"
+
+namespace dmvs {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileW = 32;
+
+struct ConvArgs {
+  dmvs_conv_desc d;
+  int cin_pad;     // (C1 + C2) rounded up to 4
+  int w_cstride;   // total padded Cout of the packed weight tensor
+  int co_base;     // first output channel of this launch
+  int CK;          // input channels staged per chunk (4, 8, 16)
+  int CKP;         // padded pixel pitch of the staged tile in floats
+  int in_rows, in_cols;
+  int vec_x, vec_x2;  // 128-bit loads allowed on x / x2
+  int vec_y;          // 128-bit stores allowed on y
+  int Hs, Ws;         // stored size of x (H/2, W/2 when in_up2)
+};
+
+template <int CO_T, int WC, int PX, int S>
+__global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
+  constexpr int WP = 8 / WC;           // warps along output rows
+  constexpr int TH = WP * PX;          // output rows per CTA
+  constexpr int COUT_S = CO_T * WC;    // output channels per CTA
+  const dmvs_conv_desc& d = a.d;
+
+  extern __shared__ __align__(16) float smem[];
+  float* in_s = smem;
+  float* w_s = in_s + a.in_rows * a.in_cols * a.CKP;
+  float* gn_s = w_s + d.KH * d.KW * a.CK * COUT_S;   // [2][C1] when in_stats
+  __shared__ float stat_s[8];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int wc = warp % WC;
+  const int wp = warp / WC;
+
+  const int n = blockIdx.z / d.Do;
+  const int od = blockIdx.z - n * d.Do;
+  const int ty0 = blockIdx.y * TH;
+  const int tx0 = blockIdx.x * kTileW;
+  const int iy0 = ty0 * S - d.pad_h;
+  const int ix0 = tx0 * S - d.pad_w;
+
+  if (tid < 8) stat_s[tid] = 0.0f;
+  if (d.in_stats != nullptr) {
+    // per-channel affine of the producer's GroupNorm (4 groups) for sample n
+    const int cpg = d.C1 / 4;
+    for (int c = tid; c < d.C1; c += kThreads) {
+      const int g = c / cpg;
+      const double s = d.in_stats[(n * 4 + g) * 2 + 0];
+      const double q = d.in_stats[(n * 4 + g) * 2 + 1];
+      const double mean = s * (double)d.in_inv_count;
+      double var = q * (double)d.in_inv_count - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+      const float g1 = d.in_g1[c] * rstd;
+      gn_s[c] = g1;
+      gn_s[d.C1 + c] = d.in_g0[c] - (float)mean * g1;
+    }
+  }
+
+  float acc[PX][CO_T];
+#pragma unroll
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[p][j] = 0.0f;
+
+  const int ck4 = a.CK >> 2;
+  const int in_units = a.in_rows * a.in_cols * ck4;
+  const int w_rows = d.KH * d.KW * a.CK;
+  const int w_units = w_rows * (COUT_S / 4);
+  const int Ctot = d.C1 + d.C2;
+
+  for (int kd = 0; kd < d.KD; ++kd) {
+    const int id = od * S + kd - d.pad_d;
+    if (id < 0 || id >= d.D) continue;  // zero padding along depth (uniform for the CTA)
+    for (int c0 = 0; c0 < a.cin_pad; c0 += a.CK) {
+      __syncthreads();  // previous chunk fully consumed (also orders gn_s / stat_s init)
+      // ---- stage the input tile -------------------------------------------------------------
+      for (int idx = tid; idx < in_units; idx += kThreads) {
+        const int c4 = idx % ck4;
+        const int t = idx / ck4;
+        const int col = t % a.in_cols;
+        const int row = t / a.in_cols;
+        const int iy = iy0 + row, ix = ix0 + col;
+        const int ch = c0 + c4 * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W && ch < Ctot) {
+          const int sy = d.in_up2 ? (iy >> 1) : iy;
+          const int sx = d.in_up2 ? (ix >> 1) : ix;
+          const int64_t pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws + sx;
+          if (ch + 3 < d.C1 && a.vec_x) {
+            v = ldg4(d.x + pix * d.x_ps + ch);
+          } else if (ch >= d.C1 && ch + 3 < Ctot && a.vec_x2) {
+            v = ldg4(d.x2 + pix * d.x2_ps + (ch - d.C1));
+          } else {
+            float e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = ch + k;
+              e[k] = c < d.C1 ? __ldg(d.x + pix * d.x_ps + c)
+                              : (c < Ctot ? __ldg(d.x2 + pix * d.x2_ps + (c - d.C1)) : 0.0f);
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+          }
+          if (d.in_stats != nullptr) {
+            // GroupNorm affine + SiLU of the producer (only defined for the x part, C2 == 0)
+            float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = ch + k;
+              if (c < d.C1) e[k] = siluf_(fmaf(e[k], gn_s[c], gn_s[d.C1 + c]));
+            }
+            v = make_float4(e[0], e[1], e[2], e[3]);
+          }
+        }
+        *reinterpret_cast<float4*>(in_s + (row * a.in_cols + col) * a.CKP + c4 * 4) = v;
+      }
+      // ---- stage the weight slab [KH*KW][CK][COUT_S] ----------------------------------------
+      for (int idx = tid; idx < w_units; idx += kThreads) {
+        const int j4 = idx % (COUT_S / 4);
+        const int r = idx / (COUT_S / 4);
+        const int ci = r % a.CK;
+        const int tap = r / a.CK;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + ci < a.cin_pad) {
+          const int64_t off = ((int64_t)((kd * d.KH * d.KW + tap) * a.cin_pad + c0 + ci)) * a.w_cstride +
+                              a.co_base + j4 * 4;
+          v = ldg4(d.w + off);
+        }
+        *reinterpret_cast<float4*>(w_s + r * COUT_S + j4 * 4) = v;
+      }
+      __syncthreads();
+      // ---- accumulate -----------------------------------------------------------------------
+      const float* in_base = in_s + ((wp * PX * S) * a.in_cols + lane * S) * a.CKP;
+      const int row_pitch = S * a.in_cols * a.CKP;
+      for (int kh = 0; kh < d.KH; ++kh) {
+        for (int kw = 0; kw < d.KW; ++kw) {
+          const float* ip = in_base + (kh * a.in_cols + kw) * a.CKP;
+          const float* wt = w_s + ((kh * d.KW + kw) * a.CK) * COUT_S + wc * CO_T;
+          for (int c4 = 0; c4 < ck4; ++c4) {
+            float av[PX][4];
+#pragma unroll
+            for (int p = 0; p < PX; ++p) {
+              const float4 t4 = *reinterpret_cast<const float4*>(ip + p * row_pitch + c4 * 4);
+              av[p][0] = t4.x; av[p][1] = t4.y; av[p][2] = t4.z; av[p][3] = t4.w;
+            }
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+              const float* wr = wt + (c4 * 4 + ci) * COUT_S;
+#pragma unroll
+              for (int j4 = 0; j4 < CO_T / 4; ++j4) {
+                const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 4);
+#pragma unroll
+                for (int p = 0; p < PX; ++p) {
+                  acc[p][j4 * 4 + 0] = fmaf(av[p][ci], wv.x, acc[p][j4 * 4 + 0]);
+                  acc[p][j4 * 4 + 1] = fmaf(av[p][ci], wv.y, acc[p][j4 * 4 + 1]);
+                  acc[p][j4 * 4 + 2] = fmaf(av[p][ci], wv.z, acc[p][j4 * 4 + 2]);
+                  acc[p][j4 * 4 + 3] = fmaf(av[p][ci], wv.w, acc[p][j4 * 4 + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- epilogue -----------------------------------------------------------------------------
+  const int ox = tx0 + lane;
+  const int cbase = a.co_base + wc * CO_T;  // first absolute output channel of this thread
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f}, gsq[4] = {0.f, 0.f, 0.f, 0.f};
+  const int cpg_out = d.Cout >= 4 ? d.Cout / 4 : 1;
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    const int oy = ty0 + wp * PX + p;
+    if (ox >= d.Wo || oy >= d.Ho) continue;
+    const int64_t opix = ((int64_t)(n * d.Do + od) * d.Ho + oy) * d.Wo + ox;
+    int64_t rpix = opix;
+    if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+    float out[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) {
+      const int c = cbase + j;
+      float v = acc[p][j];
+      if (c < d.Cout) {
+        if (d.bias != nullptr) v += __ldg(d.bias + c);
+        if (d.epi == DMVS_EPI_STD) {
+          if (d.res_mode == DMVS_RES_PRE_ACT) v += __ldg(d.res + rpix * d.res_ps + c);
+          if (c >= d.act_c0) v = apply_act(v, d.act);
+          if (d.res_mode == DMVS_RES_POST_ACT) v += __ldg(d.res + rpix * d.res_ps + c);
+        } else if (d.epi == DMVS_EPI_GRU_ZR) {
+          v = sigmoidf_(v);
+          if (c >= d.gru_hidden) v *= __ldg(d.aux1 + opix * d.aux1_ps + (c - d.gru_hidden));
+        } else {  // DMVS_EPI_GRU_Q
+          const float z = __ldg(d.aux1 + opix * d.aux1_ps + c);
+          const float h = __ldg(d.aux2 + opix * d.aux2_ps + c);
+          v = (1.0f - z) * h + z * tanhf(v);
+        }
+        if (d.out_stats != nullptr) {
+          const int g = c / cpg_out;
+          gsum[g] += v;
+          gsq[g] += v * v;
+        }
+      }
+      out[j] = v;
+    }
+    float* yp = d.y + opix * d.y_ps + cbase;
+    if (a.vec_y && cbase + CO_T <= d.Cout) {
+#pragma unroll
+      for (int j4 = 0; j4 < CO_T / 4; ++j4)
+        *reinterpret_cast<float4*>(yp + j4 * 4) = make_float4(out[j4 * 4], out[j4 * 4 + 1], out[j4 * 4 + 2], out[j4 * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j)
+        if (cbase + j < d.Cout) yp[j] = out[j];
+    }
+  }
+  if (d.out_stats != nullptr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float s = warp_sum(gsum[g]);
+      const float q = warp_sum(gsq[g]);
+      if (lane == 0) {
+        atomicAdd(&stat_s[g * 2 + 0], s);
+        atomicAdd(&stat_s[g * 2 + 1], q);
+      }
+    }
+    __syncthreads();
+    if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------
+using KernelFn = void (*)(const ConvArgs);
+
+template <int CO_T, int WC, int PX, int S>
+KernelFn get_kernel() {
+  static bool configured = false;
+  KernelFn fn = conv_kernel<CO_T, WC, PX, S>;
+  if (!configured) {
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    configured = true;
+  }
+  return fn;
+}
+
+template <int CO_T, int WC>
+KernelFn pick_px(int px, int s) {
+  constexpr int kMaxPx = (CO_T >= 32) ? 2 : 4;
+  if (px > kMaxPx) px = kMaxPx;
+  if (s == 1) {
+    if (px >= 4) { if constexpr (kMaxPx >= 4) return get_kernel<CO_T, WC, 4, 1>(); }
+    if (px >= 2) return get_kernel<CO_T, WC, 2, 1>();
+    return get_kernel<CO_T, WC, 1, 1>();
+  }
+  if (px >= 4) { if constexpr (kMaxPx >= 4) return get_kernel<CO_T, WC, 4, 2>(); }
+  if (px >= 2) return get_kernel<CO_T, WC, 2, 2>();
+  return get_kernel<CO_T, WC, 1, 2>();
+}
+
+KernelFn pick_kernel(int chunk, int px, int s, int* co_t, int* wc) {
+  switch (chunk) {
+    case 4: *co_t = 4; *wc = 1; return pick_px<4, 1>(px, s);
+    case 8: *co_t = 8; *wc = 1; return pick_px<8, 1>(px, s);
+    case 16: *co_t = 16; *wc = 1; return pick_px<16, 1>(px, s);
+    case 32: *co_t = 32; *wc = 1; return pick_px<32, 1>(px, s);
+    case 64: *co_t = 32; *wc = 2; return pick_px<32, 2>(px, s);
+    default: *co_t = 32; *wc = 4; return pick_px<32, 4>(px, s);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kSmemBudget = 100 * 1024;  // two CTAs per SM
+
+}  // namespace
+}  // namespace dmvs
+
+using namespace dmvs;
+
+extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
+  if (dp == nullptr) return DMVS_ERR_ARG;
+  const dmvs_conv_desc& d = *dp;
+  if (!d.x || !d.w || !d.y) return DMVS_ERR_ARG;
+  if (d.N <= 0 || d.D <= 0 || d.H <= 0 || d.W <= 0 || d.C1 <= 0 || d.C2 < 0 || d.Cout <= 0) return DMVS_ERR_ARG;
+  if (d.C2 > 0 && !d.x2) return DMVS_ERR_ARG;
+  if (d.KD <= 0 || d.KH <= 0 || d.KW <= 0 || (d.stride != 1 && d.stride != 2)) return DMVS_ERR_ARG;
+  if (d.Do <= 0 || d.Ho <= 0 || d.Wo <= 0) return DMVS_ERR_ARG;
+  if (d.res_mode != DMVS_RES_NONE && !d.res) return DMVS_ERR_ARG;
+  if (d.epi != DMVS_EPI_STD && (!d.aux1 || (d.epi == DMVS_EPI_GRU_Q && !d.aux2))) return DMVS_ERR_ARG;
+  if (d.in_stats && (d.C2 != 0 || (d.C1 % 4) != 0 || !d.in_g1 || !d.in_g0)) return DMVS_ERR_ARG;
+  if (d.out_stats && (d.Cout % 4) != 0) return DMVS_ERR_ARG;
+  if ((d.in_up2 || d.res_up2) && (d.D != 1 || d.KD != 1)) return DMVS_ERR_UNSUPPORTED;
+  if (d.in_up2 && ((d.H | d.W) & 1)) return DMVS_ERR_ARG;
+  if (d.res_up2 && ((d.Ho | d.Wo) & 1)) return DMVS_ERR_ARG;
+  // the output size must be what the geometry implies
+  if ((d.H + 2 * d.pad_h - d.KH) / d.stride + 1 != d.Ho || (d.W + 2 * d.pad_w - d.KW) / d.stride + 1 != d.Wo ||
+      (d.D + 2 * d.pad_d - d.KD) / d.stride + 1 != d.Do)
+    return DMVS_ERR_ARG;
+  if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
+
+  ConvArgs a;
+  a.d = d;
+  a.cin_pad = (d.C1 + d.C2 + 3) & ~3;
+  a.w_cstride = (d.Cout + 3) & ~3;
+  a.vec_x = aligned16(d.x) && (d.x_ps % 4 == 0) && (d.C1 % 4 == 0);
+  a.vec_x2 = d.C2 > 0 && aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C1 % 4 == 0) && (d.C2 % 4 == 0);
+  a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
+  a.Hs = d.in_up2 ? d.H / 2 : d.H;
+  a.Ws = d.in_up2 ? d.W / 2 : d.W;
+
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int S = d.stride;
+  int remaining = a.w_cstride;
+  int co_base = 0;
+  while (remaining > 0) {
+    int chunk = 128;
+    while (chunk > remaining) chunk >>= 1;  // largest power of two (>=4) not above what is left
+    int co_t, wc;
+    // choose rows-per-thread and the channel chunk that fit the shared-memory budget
+    const int max_px = chunk >= 32 ? 2 : 4;
+    int px = max_px, ck = 0;
+    size_t smem = 0;
+    const int wcount = chunk == 64 ? 2 : (chunk == 128 ? 4 : 1);
+    for (; px >= 1; px >>= 1) {
+      const int th = (8 / wcount) * px;
+      const int in_rows = (th - 1) * S + d.KH;
+      const int in_cols = (kTileW - 1) * S + d.KW;
+      ck = 0;
+      for (int c = 16; c >= 4; c >>= 1) {
+        if (c > a.cin_pad && c > 4) continue;
+        const int ckp = c == 4 ? 4 : c + 4;
+        const size_t need = ((size_t)in_rows * in_cols * ckp + (size_t)d.KH * d.KW * c * chunk + 2 * (size_t)d.C1) * 4;
+        if (need <= (size_t)kSmemBudget) { ck = c; smem = need; break; }
+      }
+      if (ck) {
+        // keep at least ~2 waves of CTAs when a smaller tile is possible
+        const int th2 = (8 / wcount) * px;
+        const long blocks = (long)ceil_div(d.Wo, kTileW) * ceil_div(d.Ho, th2) * d.N * d.Do;
+        if (blocks >= 2 * kNumSMs || px == 1) break;
+      }
+    }
+    if (!ck) return DMVS_ERR_UNSUPPORTED;
+    if (px < 1) px = 1;
+    KernelFn fn = pick_kernel(chunk, px, S, &co_t, &wc);
+    const int th = (8 / wc) * px;
+    a.co_base = co_base;
+    a.CK = ck;
+    a.CKP = ck == 4 ? 4 : ck + 4;
+    a.in_rows = (th - 1) * S + d.KH;
+    a.in_cols = (kTileW - 1) * S + d.KW;
+    dim3 grid(ceil_div(d.Wo, kTileW), ceil_div(d.Ho, th), d.N * d.Do);
+    if (grid.y > 65535 || grid.z > 65535) return DMVS_ERR_UNSUPPORTED;
+    fn<<<grid, kThreads, smem, st>>>(a);
+    int rc = launch_status();
+    if (rc) return rc;
+    co_base += chunk;
+    remaining -= chunk;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ConvTranspose3d(k3, s2, p1, op1) + bias + ReLU + skip    (module.py:110-144, 436-437, 445-446)
+// out[o] = sum_k in[(o + 1 - k)/2] * w[k] over taps with (o + 1 - k) even and in range.
+// One thread = one output voxel x all Cout (<= 16).  Tiny FLOP share (< 2 GFLOP), so kept simple.
+// ---------------------------------------------------------------------------------------------
+namespace dmvs {
+namespace {
+
+template <int COUT>
+__global__ void __launch_bounds__(128) deconv3d_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, const float* __restrict__ skip,
+                                                       float* __restrict__ y, int N, int D, int H, int W, int Cin) {
+  extern __shared__ __align__(16) float ws[];  // [27][Cin][COUT]
+  const int wtotal = 27 * Cin * COUT;
+  for (int i = threadIdx.x; i < wtotal; i += blockDim.x) ws[i] = __ldg(w + i);
+  __syncthreads();
+  const int Do = 2 * D, Ho = 2 * H, Wo = 2 * W;
+  const int64_t total = (int64_t)N * Do * Ho * Wo;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += (int64_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(o % Wo);
+    int64_t t = o / Wo;
+    const int oy = (int)(t % Ho);
+    t /= Ho;
+    const int oz = (int)(t % Do);
+    const int n = (int)(t / Do);
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int kd = 0; kd < 3; ++kd) {
+      const int tz = oz + 1 - kd;
+      if (tz < 0 || (tz & 1) || (tz >> 1) >= D) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ty = oy + 1 - kh;
+        if (ty < 0 || (ty & 1) || (ty >> 1) >= H) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          const int tx = ox + 1 - kw;
+          if (tx < 0 || (tx & 1) || (tx >> 1) >= W) continue;
+          const float* xp = x + ((((int64_t)n * D + (tz >> 1)) * H + (ty >> 1)) * W + (tx >> 1)) * Cin;
+          const float* wp = ws + ((kd * 3 + kh) * 3 + kw) * Cin * COUT;
+          for (int c4 = 0; c4 < Cin; c4 += 4) {
+            const float4 v = ldg4(xp + c4);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int j = 0; j < COUT; ++j) acc[j] = fmaf(e[k], wp[(c4 + k) * COUT + j], acc[j]);
+            }
+          }
+        }
+      }
+    }
+    float* yp = y + o * COUT;
+    const float* sp = skip + o * COUT;
+#pragma unroll
+    for (int j4 = 0; j4 < COUT / 4; ++j4) {
+      const float4 s = ldg4(sp + j4 * 4);
+      float4 r;
+      r.x = fmaxf(acc[j4 * 4 + 0] + __ldg(bias + j4 * 4 + 0), 0.f) + s.x;
+      r.y = fmaxf(acc[j4 * 4 + 1] + __ldg(bias + j4 * 4 + 1), 0.f) + s.y;
+      r.z = fmaxf(acc[j4 * 4 + 2] + __ldg(bias + j4 * 4 + 2), 0.f) + s.z;
+      r.w = fmaxf(acc[j4 * 4 + 3] + __ldg(bias + j4 * 4 + 3), 0.f) + s.w;
+      *reinterpret_cast<float4*>(yp + j4 * 4) = r;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace dmvs
+
+extern "C" int dmvs_deconv3d_f32(const float* x, const float* w, const float* bias, const float* skip, float* y,
+                                 int32_t N, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream) {
+  if (!x || !w || !bias || !skip || !y) return DMVS_ERR_ARG;
+  if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin % 4) != 0) return DMVS_ERR_ARG;
+  if (Cout != 8 && Cout != 16) return DMVS_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(skip) || !aligned16(y)) return DMVS_ERR_ALIGN;
+  const size_t smem = (size_t)27 * Cin * Cout * 4;
+  const int64_t total = (int64_t)N * 8 * D * H * W;
+  int blocks = (int)(ceil_div64(total, 128) < (int64_t)kNumSMs * 16 ? ceil_div64(total, 128) : (int64_t)kNumSMs * 16);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cout == 8) {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(deconv3d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+    deconv3d_kernel<8><<<blocks, 128, smem, st>>>(x, w, bias, skip, y, N, D, H, W, Cin);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(deconv3d_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+    deconv3d_kernel<16><<<blocks, 128, smem, st>>>(x, w, bias, skip, y, N, D, H, W, Cin);
+  }
+  return launch_status();
+}

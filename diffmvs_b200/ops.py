@@ -1,0 +1,413 @@
+"""Torch-tensor front end of the C-ABI kernels.
+
+Tensors handled here are channels-last in *shape*: maps are ``[N,H,W,C]``, volumes ``[N,D,H,W,C]``,
+possibly channel slices of a wider buffer (``t[..., a:b]``), which the kernels address through a
+pixel stride.  PyTorch only provides device memory, the caching allocator and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
+                    RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
+
+Tensor = torch.Tensor
+
+
+class Profiler:
+    """Optional per-call CUDA-event timing of the kernel entry points (used by bench.py / tools; off by default).
+
+    Each record is (name, tag, algorithmic_bytes, start_event, end_event); `summary()` synchronises and
+    aggregates by (name, tag).  Bytes are the logical sizes of every tensor argument and result - the
+    unique traffic an ideally fused launch would move."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, tag, nbytes, e0, e1 in self.records:
+            k = (name, tag)
+            a = agg.setdefault(k, [0, 0.0, 0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += nbytes
+        return {k: {"calls": v[0], "ms": v[1], "bytes": v[2]} for k, v in agg.items()}
+
+
+_PROFILER: Optional[Profiler] = None
+
+
+def set_profiler(p: Optional[Profiler]) -> None:
+    global _PROFILER
+    _PROFILER = p
+
+
+def _tensor_bytes(obj) -> int:
+    if isinstance(obj, torch.Tensor):
+        return obj.numel() * obj.element_size()
+    if isinstance(obj, (tuple, list)):
+        return sum(_tensor_bytes(o) for o in obj)
+    if isinstance(obj, PackedConv):
+        return _tensor_bytes(obj.w)
+    if isinstance(obj, GroupNormIn):
+        return 0
+    return 0
+
+
+def _profiled(name: str):
+    def deco(fn):
+        def wrapper(*a, **k):
+            prof = _PROFILER
+            if prof is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            nbytes = _tensor_bytes(a) + _tensor_bytes(list(k.values()))
+            if k.get("out") is None and k.get("cost_out") is None:
+                nbytes += _tensor_bytes(out)
+            tag = ""
+            if name == "conv":
+                pc = a[1]
+                tag = f"{pc.cin}->{pc.cout} k{'x'.join(map(str, pc.k))} s{k.get('stride', 1)} {tuple(out.shape[1:-1])}"
+            prof.records.append((name, tag, nbytes, e0, e1))
+            return out
+        wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+        return wrapper
+    return deco
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req_cuda_f32(t: Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name}: the diffmvs_b200 kernels run on CUDA only (got {t.device}); there is no CPU path")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name}: expected float32, got {t.dtype}")
+
+
+def pixel_stride(t: Tensor, name: str = "tensor") -> int:
+    """Pixel stride of a channels-last map/volume view; validates the layout."""
+    _req_cuda_f32(t, name)
+    if t.dim() not in (4, 5) or t.stride(-1) != 1:
+        raise ValueError(f"{name}: expected a channels-last [N,(D,)H,W,C] view, got shape {tuple(t.shape)} "
+                         f"strides {t.stride()}")
+    ps = t.stride(-2)
+    expect = ps
+    for dim in range(t.dim() - 2, 0, -1):  # W, H, (D)
+        if t.shape[dim] > 1 and t.stride(dim) != expect:
+            raise ValueError(f"{name}: not a dense channels-last view (strides {t.stride()})")
+        expect *= t.shape[dim]
+    if t.shape[0] > 1 and t.stride(0) != expect:
+        raise ValueError(f"{name}: batch stride {t.stride(0)} != {expect}")
+    if ps < t.shape[-1]:
+        raise ValueError(f"{name}: pixel stride {ps} < channels {t.shape[-1]}")
+    return ps
+
+
+@dataclass
+class PackedConv:
+    """Host-prepared convolution: weights [KD,KH,KW,cin_pad,cout_pad] (BN folded), optional bias."""
+    w: Tensor
+    bias: Optional[Tensor]
+    cin: int
+    cout: int
+    k: Tuple[int, int, int]
+
+    def to(self, device) -> "PackedConv":
+        return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device), self.cin,
+                          self.cout, self.k)
+
+
+@dataclass
+class GroupNormIn:
+    """GroupNorm(4)+affine+SiLU of the producer, applied while the consumer stages its input."""
+    stats: Tensor   # [N,4,2] float64
+    g1: Tensor      # [C]
+    g0: Tensor      # [C]
+
+
+@_profiled("conv")
+def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int = 1,
+         pad: Optional[Tuple[int, int, int]] = None, act: int = ACT_NONE, act_c0: int = 0,
+         res: Optional[Tensor] = None, res_mode: int = RES_NONE, res_up2: bool = False, in_up2: bool = False,
+         in_gn: Optional[GroupNormIn] = None, out: Optional[Tensor] = None, out_stats: Optional[Tensor] = None,
+         epi: int = EPI_STD, aux1: Optional[Tensor] = None, aux2: Optional[Tensor] = None,
+         gru_hidden: int = 0) -> Tensor:
+    """2-D (x: [N,H,W,C]) or 3-D (x: [N,D,H,W,C]) convolution with fused prologue/epilogue."""
+    three_d = x.dim() == 5
+    x_ps = pixel_stride(x, "conv input")
+    if three_d:
+        N, D, H, W, C1 = x.shape
+    else:
+        N, H, W, C1 = x.shape
+        D = 1
+    if in_up2:
+        H, W = 2 * H, 2 * W
+    C2 = 0
+    x2_ps = 0
+    if x2 is not None:
+        x2_ps = pixel_stride(x2, "conv input 2")
+        if tuple(x2.shape[:-1]) != tuple(x.shape[:-1]):
+            raise ValueError(f"conv: concat inputs disagree: {tuple(x.shape)} vs {tuple(x2.shape)}")
+        C2 = x2.shape[-1]
+    if C1 + C2 != pc.cin:
+        raise ValueError(f"conv: input has {C1}+{C2} channels, weights expect {pc.cin}")
+    KD, KH, KW = pc.k
+    if pad is None:
+        pad = (KD // 2, KH // 2, KW // 2)
+    pd, ph, pw = pad
+    Do = (D + 2 * pd - KD) // stride + 1
+    Ho = (H + 2 * ph - KH) // stride + 1
+    Wo = (W + 2 * pw - KW) // stride + 1
+    oshape = (N, Do, Ho, Wo, pc.cout) if three_d else (N, Ho, Wo, pc.cout)
+    if out is None:
+        out = torch.empty(oshape, device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != oshape:
+        raise ValueError(f"conv: out has shape {tuple(out.shape)}, expected {oshape}")
+    y_ps = pixel_stride(out, "conv output")
+
+    d = ConvDesc()
+    d.x, d.x2 = _ptr(x), _ptr(x2)
+    d.N, d.D, d.H, d.W = N, D, H, W
+    d.C1, d.C2, d.x_ps, d.x2_ps, d.in_up2 = C1, C2, x_ps, x2_ps, int(in_up2)
+    if in_gn is not None:
+        d.in_stats, d.in_g1, d.in_g0 = _ptr(in_gn.stats), _ptr(in_gn.g1), _ptr(in_gn.g0)
+        d.in_inv_count = 1.0 / float(D * H * W * (C1 // 4))
+    d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
+    d.KD, d.KH, d.KW, d.stride = KD, KH, KW, stride
+    d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
+    d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps
+    d.act, d.act_c0, d.res_mode = act, act_c0, res_mode
+    if res is not None:
+        d.res, d.res_ps, d.res_up2 = _ptr(res), pixel_stride(res, "conv residual"), int(res_up2)
+        want = (N, Ho // 2, Wo // 2) if res_up2 else tuple(oshape[:-1])
+        if tuple(res.shape[:-1]) != want or res.shape[-1] < pc.cout:
+            raise ValueError(f"conv: residual shape {tuple(res.shape)} incompatible with output {oshape}")
+    d.epi, d.gru_hidden = epi, gru_hidden
+    if aux1 is not None:
+        d.aux1, d.aux1_ps = _ptr(aux1), pixel_stride(aux1, "conv aux1")
+    if aux2 is not None:
+        d.aux2, d.aux2_ps = _ptr(aux2), pixel_stride(aux2, "conv aux2")
+    d.out_stats = _ptr(out_stats)
+    check(_cabi.lib().dmvs_conv_f32(C.byref(d), _stream()), "dmvs_conv_f32")
+    return out
+
+
+@_profiled("deconv3d")
+def deconv3d(x: Tensor, w: Tensor, bias: Tensor, skip: Tensor) -> Tensor:
+    N, D, H, W, Cin = x.shape
+    Cout = skip.shape[-1]
+    for t, n in ((x, "x"), (skip, "skip")):
+        _req_cuda_f32(t, n)
+        if not t.is_contiguous():
+            raise ValueError("deconv3d: dense channels-last volumes required")
+    y = torch.empty_like(skip)
+    check(_cabi.lib().dmvs_deconv3d_f32(_ptr(x), _ptr(w), _ptr(bias), _ptr(skip), _ptr(y), N, D, H, W, Cin, Cout,
+                                        _stream()), "dmvs_deconv3d_f32")
+    return y
+
+
+@_profiled("compose_homographies")
+def compose_homographies(proj: Tensor) -> Tensor:
+    """proj [B,V,2,4,4] -> [B,V-1,12]."""
+    _req_cuda_f32(proj, "proj_matrices")
+    proj = proj.contiguous()
+    B, V = proj.shape[:2]
+    hom = torch.empty((B, V - 1, 12), device=proj.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_compose_homographies(_ptr(proj), _ptr(hom), B, V, _stream()), "dmvs_compose_homographies")
+    return hom
+
+
+@_profiled("warp_volume")
+def warp_volume(src: Tensor, hom: Tensor, depth: Tensor) -> Tensor:
+    """src [B,Hs,Ws,C], hom [B,12], depth [B,D,H,W] -> [B,D,H,W,C]."""
+    ps = pixel_stride(src, "warp source")
+    B, Hs, Ws, Cc = src.shape
+    _, D, H, W = depth.shape
+    out = torch.empty((B, D, H, W, Cc), device=src.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_warp_volume(_ptr(src), ps, _ptr(hom.contiguous()), _ptr(depth.contiguous()), _ptr(out), B, Cc,
+                                       Hs, Ws, D, H, W, _stream()), "dmvs_warp_volume")
+    return out
+
+
+@_profiled("plane_sweep_corr")
+def plane_sweep_corr(feats: Tensor, hom: Tensor, plane_depth: Tensor, G: int) -> Tensor:
+    """feats [V,B,H,W,C] dense, hom [B,V-1,12], plane_depth [B,D] -> cor [B*(V-1),D,H,W,G]."""
+    _req_cuda_f32(feats, "features")
+    if not feats.is_contiguous():
+        raise ValueError("plane_sweep_corr: dense [V,B,H,W,C] features required")
+    V, B, H, W, Cc = feats.shape
+    D = plane_depth.shape[1]
+    cor = torch.empty((B * (V - 1), D, H, W, G), device=feats.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_plane_sweep_corr(_ptr(feats), _ptr(hom), _ptr(plane_depth.contiguous()), _ptr(cor), B, V, Cc, G,
+                                            D, H, W, _stream()), "dmvs_plane_sweep_corr")
+    return cor
+
+
+@_profiled("view_weight_max")
+def view_weight_max(logit: Tensor) -> Tensor:
+    """logit [N,D,H,W] (dense) -> [N,H,W]."""
+    N, D, H, W = logit.shape
+    w = torch.empty((N, H, W), device=logit.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_view_weight_max(_ptr(logit), _ptr(w), N, D, H * W, _stream()), "dmvs_view_weight_max")
+    return w
+
+
+@_profiled("aggregate_views")
+def aggregate_views(cor: Tensor, w: Tensor, B: int) -> Tensor:
+    """cor [B*V1,D,H,W,G], w [B*V1,H,W] -> [B,D,H,W,G]."""
+    NV, D, H, W, G = cor.shape
+    V1 = NV // B
+    vol = torch.empty((B, D, H, W, G), device=cor.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_aggregate_views(_ptr(cor), _ptr(w), _ptr(vol), B, V1, D, H * W, G, _stream()),
+          "dmvs_aggregate_views")
+    return vol
+
+
+@_profiled("depth_regression")
+def depth_regression(logits: Tensor, depth_min: Tensor, depth_max: Tensor, want_floor: bool = False):
+    """logits [B,D,H,W] dense -> (norm_inv, depth, conf [B,H,W], floor_idx or None)."""
+    B, D, H, W = logits.shape
+    mk = lambda: torch.empty((B, H, W), device=logits.device, dtype=torch.float32)
+    n, dep, conf = mk(), mk(), mk()
+    fl = torch.empty((B, H, W), device=logits.device, dtype=torch.int32) if want_floor else None
+    check(_cabi.lib().dmvs_depth_regression(_ptr(logits), _ptr(depth_min), _ptr(depth_max), _ptr(n), _ptr(dep), _ptr(conf),
+                                            _ptr(fl), B, D, H * W, _stream()), "dmvs_depth_regression")
+    return n, dep, conf, fl
+
+
+@_profiled("get_cost")
+def get_cost(feats: Tensor, hom: Tensor, inv_depth: Tensor, conf: Optional[Tensor], view_w: Tensor, depth_min: Tensor,
+             depth_max: Tensor, G: int, D: int, wshift: int, interval: float, min_radius: float, max_radius: float,
+             cost_out: Optional[Tensor] = None, samples_out: Optional[Tensor] = None):
+    """feats [V,B,H,W,C]; inv_depth/conf [B,H,W]; view_w [B,V-1,H>>s,W>>s] -> cost [B,H,W,G*D], samples [B,H,W,D]."""
+    if not feats.is_contiguous():
+        raise ValueError("get_cost: dense [V,B,H,W,C] features required")
+    V, B, H, W, Cc = feats.shape
+    if cost_out is None:
+        cost_out = torch.empty((B, H, W, G * D), device=feats.device, dtype=torch.float32)
+    if samples_out is None:
+        samples_out = torch.empty((B, H, W, D), device=feats.device, dtype=torch.float32)
+    if tuple(view_w.shape) != (B, V - 1, H >> wshift, W >> wshift) or not view_w.is_contiguous():
+        raise ValueError(f"get_cost: view weights {tuple(view_w.shape)} do not match {(B, V - 1, H >> wshift, W >> wshift)}")
+    conf_ps = 1
+    if conf is not None:
+        if conf.dim() == 4:      # [B,H,W,k] channel slice of the U-Net head
+            conf_ps = pixel_stride(conf, "conf")
+        elif not conf.is_contiguous():
+            raise ValueError("get_cost: conf must be dense [B,H,W] or a channel slice [B,H,W,1]")
+    check(_cabi.lib().dmvs_get_cost(_ptr(feats), _ptr(hom), _ptr(inv_depth), _ptr(conf), conf_ps, _ptr(view_w), _ptr(depth_min),
+                                    _ptr(depth_max), _ptr(cost_out), pixel_stride(cost_out, "cost"), _ptr(samples_out),
+                                    pixel_stride(samples_out, "samples"), B, V, Cc, G, D, H, W, wshift, interval,
+                                    min_radius, max_radius, _stream()), "dmvs_get_cost")
+    return cost_out, samples_out
+
+
+@_profiled("groupnorm_silu_add")
+def groupnorm_silu_add(x: Tensor, gn: GroupNormIn, res: Optional[Tensor], out: Optional[Tensor] = None) -> Tensor:
+    """x [N,H,W,C] dense raw conv output -> silu(GN(x)) + res."""
+    N, H, W, Cc = x.shape
+    if not x.is_contiguous():
+        raise ValueError("groupnorm_silu_add: dense input required")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_cabi.lib().dmvs_groupnorm_silu_add(_ptr(x), _ptr(gn.stats), _ptr(gn.g1), _ptr(gn.g0), _ptr(res),
+                                              0 if res is None else pixel_stride(res, "residual"), _ptr(out),
+                                              pixel_stride(out, "out"), N, H * W, Cc, _stream()),
+          "dmvs_groupnorm_silu_add")
+    return out
+
+
+@_profiled("upsample_depth")
+def upsample_depth(n: Tensor, mask: Tensor, depth_min: Optional[Tensor], depth_max: Optional[Tensor], ratio: int,
+                   want: str = "depth+norm"):
+    """n [B,H,W], mask [B,H,W,9r^2] -> tuple of the requested [B,rH,rW] maps ("raw", "depth", "norm")."""
+    B, H, W = n.shape
+    mk = lambda: torch.empty((B, H * ratio, W * ratio), device=n.device, dtype=torch.float32)
+    keys = want.split("+")
+    outs = {k: mk() for k in keys}
+    check(_cabi.lib().dmvs_upsample_depth(_ptr(n.contiguous()), _ptr(mask), pixel_stride(mask, "mask"), _ptr(depth_min),
+                                          _ptr(depth_max), _ptr(outs.get("raw")), _ptr(outs.get("depth")),
+                                          _ptr(outs.get("norm")), B, H, W, ratio, _stream()), "dmvs_upsample_depth")
+    return tuple(outs[k] for k in keys)
+
+
+@_profiled("refine_update")
+def refine_update(mode: int, inv0: Tensor, src: Optional[Tensor], src_ps: int, scale: float, delta: Tensor, inv: Tensor,
+                  inv_slot: Optional[Tensor], slot_ps: int, depth_min: Optional[Tensor] = None,
+                  depth_max: Optional[Tensor] = None, depth: Optional[Tensor] = None) -> None:
+    B = inv0.shape[0]
+    HW = inv0.numel() // B
+    check(_cabi.lib().dmvs_refine_update(mode, _ptr(inv0), _ptr(src), src_ps, scale, _ptr(delta), _ptr(inv), _ptr(inv_slot),
+                                         slot_ps, _ptr(depth_min), _ptr(depth_max), _ptr(depth), B, HW, _stream()),
+          "dmvs_refine_update")
+
+
+@_profiled("ddim_step")
+def ddim_step(img: Tensor, delta: Tensor, noise: Tensor, k_recip: float, k_recipm1: float, sqrt_a_next: float, c: float,
+              sigma: float, scale: float) -> None:
+    check(_cabi.lib().dmvs_ddim_step(_ptr(img), _ptr(delta), _ptr(noise), k_recip, k_recipm1, sqrt_a_next, c, sigma, scale,
+                                     img.numel(), _stream()), "dmvs_ddim_step")
+
+
+@_profiled("upsample_nearest")
+def upsample_nearest(x: Tensor, factor: int) -> Tensor:
+    """x [B,H,W] dense or a [B,H,W,1] channel slice -> [B,fH,fW]."""
+    x_ps = 1
+    if x.dim() == 4:
+        x_ps = pixel_stride(x, "upsample_nearest input")
+    elif not x.is_contiguous():
+        x = x.contiguous()
+    B, H, W = x.shape[:3]
+    y = torch.empty((B, H * factor, W * factor), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_upsample_nearest(_ptr(x), x_ps, _ptr(y), B, H, W, factor, _stream()), "dmvs_upsample_nearest")
+    return y
+
+
+@_profiled("to_nhwc")
+def to_nhwc(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """Logical NCHW tensor -> [N,H,W,C] (zero-copy when x is already channels_last)."""
+    _req_cuda_f32(x, "input")
+    N, Cc, H, W = x.shape
+    v = x.permute(0, 2, 3, 1)
+    if out is None and v.is_contiguous():
+        return v
+    if out is None:
+        out = torch.empty((N, H, W, Cc), device=x.device, dtype=torch.float32)
+    if v.is_contiguous():
+        out.copy_(v)
+        return out
+    xc = x.contiguous()
+    check(_cabi.lib().dmvs_nchw_to_nhwc(_ptr(xc), _ptr(out), pixel_stride(out, "out"), N, Cc, H * W, _stream()),
+          "dmvs_nchw_to_nhwc")
+    return out
+
+
+def to_nchw_view(y: Tensor) -> Tensor:
+    """[N,H,W,C] -> logical NCHW view (channels_last memory format, no copy)."""
+    return y.permute(0, 3, 1, 2)
+
+
+@_profiled("to_nchw_dense")
+def to_nchw_dense(y: Tensor) -> Tensor:
+    """[N,H,W,C] (possibly a channel slice) -> contiguous NCHW copy."""
+    N, H, W, Cc = y.shape
+    out = torch.empty((N, Cc, H, W), device=y.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_nhwc_to_nchw(_ptr(y), pixel_stride(y, "y"), _ptr(out), N, Cc, H * W, _stream()),
+          "dmvs_nhwc_to_nchw")
+    return out

@@ -1,0 +1,154 @@
+"""Host-side weight preparation: reference state-dict entries -> kernel-ready constants.
+
+Done once per (weights, device): eval-mode BatchNorm is folded into the preceding convolution
+(`module.py:42-58,88-102,130-144,279-301`), weight standardisation is applied up front
+(`update.py:81-94`), pixel-unshuffle + 1x1 becomes a 2x2 stride-2 convolution (`update.py:44-48`),
+the GRU z/r gates are concatenated (`module.py:156-162`), the 0.25 mask scale is folded
+(`module.py:511`, `update.py:473`), and the time-embedding MLP is evaluated for the (constant)
+timestep (`update.py:50-62,138-153,205-211`).  All arithmetic here is plain fp32 torch on the host.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .ops import PackedConv
+
+SD = Dict[str, torch.Tensor]
+BN_EPS = 1e-5
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedConv:
+    """w [Cout,Cin,KH,KW] or [Cout,Cin,KD,KH,KW] -> PackedConv ([KD,KH,KW,cin_pad,cout_pad])."""
+    w = w.detach().float().cpu()
+    if w.dim() == 4:
+        w = w.unsqueeze(2)
+    cout, cin, kd, kh, kw = w.shape
+    packed = torch.zeros(kd, kh, kw, _pad4(cin), _pad4(cout), dtype=torch.float32)
+    packed[:, :, :, :cin, :cout] = w.permute(2, 3, 4, 1, 0)
+    b = None if bias is None else bias.detach().float().cpu().contiguous()
+    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw))
+
+
+def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:
+    scale = sd[p + ".weight"].float() / torch.sqrt(sd[p + ".running_var"].float() + BN_EPS)
+    shift = sd[p + ".bias"].float() - sd[p + ".running_mean"].float() * scale
+    return scale, shift
+
+
+def pack_conv_bn(sd: SD, p: str) -> PackedConv:
+    """`module.Conv2d/Conv3d/ConvBnReLU/ConvBn`: conv (no bias) followed by eval BN."""
+    w = sd[p + ".conv.weight"].float()
+    scale, shift = bn_scale_shift(sd, p + ".bn")
+    w = w * scale.view(-1, *([1] * (w.dim() - 1)))
+    if (p + ".conv.bias") in sd:
+        shift = shift + sd[p + ".conv.bias"].float() * scale
+    return pack_weight(w, shift)
+
+
+def pack_conv(sd: SD, p: str, gain: float = 1.0, rows: Optional[slice] = None) -> PackedConv:
+    """Plain conv `p.weight` [+ `p.bias`], optionally a slice of output channels and a scalar gain."""
+    w = sd[p + ".weight"].float()
+    b = sd.get(p + ".bias")
+    if rows is not None:
+        w = w[rows]
+        b = None if b is None else b[rows]
+    if gain != 1.0:
+        w = w * gain
+        b = None if b is None else b.float() * gain
+    return pack_weight(w, b)
+
+
+def pack_deconv3d_bn(sd: SD, p: str):
+    """ConvTranspose3d weight [Cin,Cout,3,3,3] + BN -> ([27,Cin,Cout] folded, bias[Cout])."""
+    w = sd[p + ".conv.weight"].float()
+    scale, shift = bn_scale_shift(sd, p + ".bn")
+    w = w * scale.view(1, -1, 1, 1, 1)
+    packed = w.permute(2, 3, 4, 0, 1).reshape(27, w.shape[0], w.shape[1]).contiguous().cpu()
+    return packed, shift.contiguous().cpu()
+
+
+def standardize_weight(w: torch.Tensor) -> torch.Tensor:
+    """`WeightStandardizedConv2d.forward` weight transform, fp32 branch (`update.py:86-92`)."""
+    w = w.float()
+    mean = w.mean(dim=(1, 2, 3), keepdim=True)
+    var = w.var(dim=(1, 2, 3), unbiased=False, keepdim=True)
+    return (w - mean) * (var + 1e-5).rsqrt()
+
+
+def pack_unshuffle_conv(sd: SD, p: str) -> PackedConv:
+    """Rearrange('b c (h p1) (w p2) -> b (c p1 p2) h w') + 1x1 conv == 2x2 stride-2 conv."""
+    w = sd[p + ".weight"].float()          # [Cout, C*4, 1, 1]
+    cout, c4 = w.shape[:2]
+    return pack_weight(w.view(cout, c4 // 4, 2, 2), sd.get(p + ".bias"))
+
+
+def pack_gru(sd: SD, p: str, tag: str):
+    """(z|r gate conv with 2*hidden outputs, q conv) for direction `tag` in {"1","2"}."""
+    pre = p + "." if p else ""
+    wz, wr = sd[f"{pre}convz{tag}.weight"].float(), sd[f"{pre}convr{tag}.weight"].float()
+    bz, br = sd[f"{pre}convz{tag}.bias"].float(), sd[f"{pre}convr{tag}.bias"].float()
+    zr = pack_weight(torch.cat((wz, wr), 0), torch.cat((bz, br), 0))
+    q = pack_conv(sd, f"{pre}convq{tag}")
+    return zr, q
+
+
+# --------------------------------------------------------------------------------------------
+# time conditioning
+# --------------------------------------------------------------------------------------------
+def time_embedding(sd: SD, p: str, t: int, dim: int) -> torch.Tensor:
+    """SinusoidalPosEmb(dim) -> Linear -> GELU -> Linear for a scalar timestep (`update.py:50-62,205-211`)."""
+    half = dim // 2
+    freq = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    ang = torch.tensor([t], dtype=torch.long)[:, None] * freq[None, :]
+    emb = torch.cat((ang.sin(), ang.cos()), dim=-1)
+    e = F.linear(emb, sd[f"{p}.1.weight"].float().cpu(), sd[f"{p}.1.bias"].float().cpu())
+    return F.linear(F.gelu(e), sd[f"{p}.3.weight"].float().cpu(), sd[f"{p}.3.bias"].float().cpu())
+
+
+def block_affine(sd: SD, p: str, temb: Optional[torch.Tensor]):
+    """(g1, g0) per Block: GN(x)*(scale+1)+shift == (x-mean)*rstd*g1 + g0 (`update.py:124-131,147-153`)."""
+    out = {}
+    ss = None
+    if temb is not None and f"{p}.mlp.1.weight" in sd:
+        e = F.linear(F.silu(temb), sd[f"{p}.mlp.1.weight"].float().cpu(), sd[f"{p}.mlp.1.bias"].float().cpu())[0]
+        ss = e.chunk(2, dim=0)
+    for b in ("block1", "block2"):
+        gamma = sd[f"{p}.{b}.norm.weight"].float().cpu()
+        beta = sd[f"{p}.{b}.norm.bias"].float().cpu()
+        if b == "block1" and ss is not None:
+            scale, shift = ss
+            out[b] = ((gamma * (scale + 1)).contiguous(), (beta * (scale + 1) + shift).contiguous())
+        else:
+            out[b] = (gamma.contiguous(), beta.contiguous())
+    return out
+
+
+def cosine_schedule(timesteps: int, s: float = 0.008) -> Dict[str, torch.Tensor]:
+    """`cosine_beta_schedule` + derived buffers (`update.py:26-36,354-390`)."""
+    x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64)
+    ac = torch.cos(((x / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999).float()
+    alphas = 1.0 - betas
+    alphas_cumprod = torch.cumprod(alphas, dim=0)
+    alphas_cumprod_prev = F.pad(alphas_cumprod[:-1], (1, 0), value=1.0)
+    return {
+        "betas": betas,
+        "alphas_cumprod": alphas_cumprod,
+        "alphas_cumprod_prev": alphas_cumprod_prev,
+        "sqrt_alphas_cumprod": torch.sqrt(alphas_cumprod),
+        "sqrt_one_minus_alphas_cumprod": torch.sqrt(1.0 - alphas_cumprod),
+        "log_one_minus_alphas_cumprod": torch.log(1.0 - alphas_cumprod),
+        "sqrt_recip_alphas": torch.sqrt(1.0 / alphas),
+        "sqrt_recip_alphas_cumprod": torch.sqrt(1.0 / alphas_cumprod),
+        "sqrt_recipm1_alphas_cumprod": torch.sqrt(1.0 / alphas_cumprod - 1),
+        "posterior_variance": betas * (1.0 - alphas_cumprod_prev) / (1.0 - alphas_cumprod),
+    }

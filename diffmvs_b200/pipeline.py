@@ -1,0 +1,491 @@
+"""Execution plans: the DiffMVS / CasDiffMVS forward expressed as launches of the C-ABI kernels.
+
+A *plan* owns the kernel-ready constants of one reference operator (packed on the host by
+`packing.py`, uploaded once) and replays the operator's dataflow with `ops.*` calls.  All activations
+are channels-last; `torch.cat`/`split` of the reference never materialise - producers write straight
+into channel slices of the consumer's input buffer.  Reference lines are cited per plan.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops, packing
+from .ops import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, RES_POST_ACT, RES_PRE_ACT,
+                  GroupNormIn, PackedConv)
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+UNET_MULTS = ((1,), (1, 2), (1, 2, 4))   # diffusion.py:33
+INTERVAL_RATIO = (4, 2, 1)               # diffusion.py:15
+
+
+def _sub(sd: SD, prefix: str) -> SD:
+    """Entries of `sd` under `prefix.` with the prefix stripped."""
+    if not prefix:
+        return sd
+    n = len(prefix) + 1
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
+
+
+class StatsArena:
+    """Zero-initialised GroupNorm accumulators ([N,4,2] float64 slots) for one forward pass."""
+
+    def __init__(self, device, batch: int, slots: int):
+        self.buf = torch.zeros((slots, batch, 4, 2), device=device, dtype=torch.float64)
+        self.next = 0
+
+    def slot(self) -> Tensor:
+        if self.next >= self.buf.shape[0]:
+            raise RuntimeError("StatsArena exhausted")
+        t = self.buf[self.next]
+        self.next += 1
+        return t
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 FeatureNet (module.py:357-420)
+# ------------------------------------------------------------------------------------------------
+class FeatureNetPlan:
+    def __init__(self, sd: SD, device, cas: bool):
+        self.cas = cas
+        up = lambda pc: pc.to(device)
+        self.c0 = [up(packing.pack_conv_bn(sd, f"conv0.{i}")) for i in range(2)]
+        self.lv = [[up(packing.pack_conv_bn(sd, f"conv{l}.{i}")) for i in range(3)] for l in (1, 2, 3)]
+        self.out1 = up(packing.pack_conv(sd, "out1"))
+        self.inner1 = up(packing.pack_conv(sd, "inner1"))
+        self.out2 = up(packing.pack_conv(sd, "out2"))
+        if cas:
+            self.inner2 = up(packing.pack_conv(sd, "inner2"))
+            self.out3 = up(packing.pack_conv(sd, "out3"))
+
+    def __call__(self, x: Tensor) -> Dict[str, Tensor]:
+        """x [N,H,W,3] -> {"stage1": [N,H/8,W/8,48], "stage2": [N,H/4,W/4,32], ["stage3": [N,H/2,W/2,16]]}."""
+        x = ops.conv(x, self.c0[0], act=ACT_RELU)
+        x = ops.conv(x, self.c0[1], act=ACT_RELU)
+        levels = []
+        for l in range(3):
+            x = ops.conv(x, self.lv[l][0], stride=2, act=ACT_RELU)
+            x = ops.conv(x, self.lv[l][1], act=ACT_RELU)
+            x = ops.conv(x, self.lv[l][2], act=ACT_RELU)
+            levels.append(x)
+        c1, c2, c3 = levels
+        out = {"stage1": ops.conv(c3, self.out1)}
+        intra = ops.conv(c2, self.inner1, res=c3, res_mode=RES_PRE_ACT, res_up2=True)
+        out["stage2"] = ops.conv(intra, self.out2)
+        if self.cas:
+            intra = ops.conv(c1, self.inner2, res=intra, res_mode=RES_PRE_ACT, res_up2=True)
+            out["stage3"] = ops.conv(intra, self.out3)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# a2 ContextNet (module.py:303-355)
+# ------------------------------------------------------------------------------------------------
+class ContextNetPlan:
+    """Heads are packed twice: whole (raw operator output) and split into the hidden / context
+    halves the model consumes (`diffusion.py:194,223-231`)."""
+
+    def __init__(self, sd: SD, device, out_dim: Sequence[int], hidden_dim: Sequence[int]):
+        up = lambda pc: pc.to(device)
+        self.out_dim = list(out_dim)
+        self.hidden_dim = list(hidden_dim)
+        self.conv1 = up(packing.pack_conv_bn(sd, "conv1"))
+        self.layers = []
+        for li in (1, 2, 3):
+            blocks = []
+            for bi in (0, 1):
+                p = f"layer{li}.{bi}"
+                blk = {"c1": up(packing.pack_conv_bn(sd, p + ".conv1")), "c2": up(packing.pack_conv_bn(sd, p + ".conv2"))}
+                if (p + ".downsample.conv.weight") in sd:
+                    blk["ds"] = up(packing.pack_conv_bn(sd, p + ".downsample"))
+                blocks.append(blk)
+            self.layers.append(blocks)
+        self.heads_raw, self.heads_hidden, self.heads_ctx = {}, {}, {}
+        for s in (1, 2, 3):
+            if out_dim[s - 1] <= 0:
+                continue
+            name = f"output{s}"
+            self.heads_raw[s] = up(packing.pack_conv(sd, name))
+            hd = hidden_dim[s - 1]
+            if hd > 0:
+                self.heads_hidden[s] = up(packing.pack_conv(sd, name, rows=slice(0, hd)))
+            self.heads_ctx[s] = up(packing.pack_conv(sd, name, rows=slice(hd, out_dim[s - 1])))
+
+    @staticmethod
+    def _block(x: Tensor, blk, stride: int) -> Tensor:
+        y = ops.conv(x, blk["c1"], stride=stride, act=ACT_RELU)
+        if "ds" in blk:
+            x = ops.conv(x, blk["ds"], stride=stride)
+        return ops.conv(y, blk["c2"], act=ACT_RELU, res=x, res_mode=RES_PRE_ACT)
+
+    def trunk(self, x: Tensor) -> Dict[int, Tensor]:
+        x = ops.conv(x, self.conv1, act=ACT_RELU)
+        feats = {}
+        for li, blocks in enumerate(self.layers):
+            x = self._block(x, blocks[0], 2)
+            x = self._block(x, blocks[1], 1)
+            feats[3 - li] = x     # layer1 -> stage3 (1/2), layer2 -> stage2 (1/4), layer3 -> stage1 (1/8)
+        return feats
+
+    def raw(self, x: Tensor) -> Dict[str, Tensor]:
+        f = self.trunk(x)
+        return {f"stage{s}": ops.conv(f[s], self.heads_raw[s]) for s in self.heads_raw}
+
+
+# ------------------------------------------------------------------------------------------------
+# a4-a6 InitialCost (module.py:422-573)
+# ------------------------------------------------------------------------------------------------
+class ViewWeightPlan:
+    """PixelViewWeight (module.py:450-463): cor [N,D,H,W,G] -> [N,H,W]."""
+
+    def __init__(self, sd: SD, device):
+        self.c0 = packing.pack_conv_bn(sd, "conv.0").to(device)
+        self.c1 = packing.pack_conv(sd, "conv.1").to(device)
+
+    def __call__(self, cor: Tensor) -> Tensor:
+        y = ops.conv(cor, self.c0, act=ACT_RELU)
+        logit = ops.conv(y, self.c1)                      # [N,D,H,W,1]
+        return ops.view_weight_max(logit.squeeze(-1))
+
+
+class CostRegPlan:
+    """CostRegNet_small (module.py:422-448): [B,D,H,W,G] -> logits [B,D,H,W]."""
+
+    def __init__(self, sd: SD, device):
+        self.reg = [packing.pack_conv_bn(sd, f"conv{i}").to(device) for i in range(6)]
+        self.dc6 = tuple(t.to(device) for t in packing.pack_deconv3d_bn(sd, "conv6"))
+        self.dc7 = tuple(t.to(device) for t in packing.pack_deconv3d_bn(sd, "conv7"))
+        self.prob = packing.pack_conv(sd, "prob").to(device)
+
+    def __call__(self, vol: Tensor) -> Tensor:
+        if vol.shape[1] % 4 or vol.shape[2] % 4 or vol.shape[3] % 4:
+            raise ValueError(f"cost volume {tuple(vol.shape)}: D, H, W must be multiples of 4 (two stride-2 levels)")
+        c1 = ops.conv(ops.conv(vol, self.reg[0], act=ACT_RELU), self.reg[1], act=ACT_RELU)
+        c3 = ops.conv(ops.conv(c1, self.reg[2], stride=2, act=ACT_RELU), self.reg[3], act=ACT_RELU)
+        x = ops.conv(ops.conv(c3, self.reg[4], stride=2, act=ACT_RELU), self.reg[5], act=ACT_RELU)
+        x = ops.deconv3d(x, self.dc6[0], self.dc6[1], c3)
+        x = ops.deconv3d(x, self.dc7[0], self.dc7[1], c1)
+        return ops.conv(x, self.prob).squeeze(-1)
+
+
+class InitialCostPlan:
+    def __init__(self, sd: SD, device, group_dim: int):
+        up = lambda pc: pc.to(device)
+        self.G = group_dim
+        self.view_weights = ViewWeightPlan(_sub(sd, "pixel_view_weight"), device)
+        self.regularize = CostRegPlan(_sub(sd, "cost_regularization"), device)
+        self.mask0 = up(packing.pack_conv(sd, "mask.0"))
+        self.mask2 = up(packing.pack_conv(sd, "mask.2", gain=0.25))
+
+    def mask(self, context: Tensor) -> Tensor:
+        return ops.conv(ops.conv(context, self.mask0, act=ACT_RELU), self.mask2)
+
+    def __call__(self, feats: Tensor, context: Tensor, hom: Tensor, plane_depth: Tensor, depth_min: Tensor,
+                 depth_max: Tensor, taps: Optional[dict] = None):
+        """feats [V,B,H,W,C], context [B,H,W,cd] (already ReLU'd), hom [B,V-1,12], plane_depth [B,D].
+        Returns mask [B,H,W,36], norm inverse depth [B,H,W], depth [B,H,W], view weights [B,V-1,H,W], conf [B,H,W]."""
+        V, B, H, W, _ = feats.shape
+        mask = self.mask(context)
+        cor = ops.plane_sweep_corr(feats, hom, plane_depth, self.G)          # [B*(V-1),D,H,W,G]
+        vw = self.view_weights(cor)                                          # [B*(V-1),H,W]
+        vol = ops.aggregate_views(cor, vw, B)
+        logits = self.regularize(vol)
+        n, depth, conf, fl = ops.depth_regression(logits, depth_min, depth_max, want_floor=taps is not None)
+        if taps is not None:
+            taps.update(stage1_cor=cor, stage1_volume=vol, stage1_logits=logits, stage1_floor=fl)
+        return mask, n, depth, vw.view(B, V - 1, H, W), conf
+
+
+# ------------------------------------------------------------------------------------------------
+# a8-a10 ConditionEncoder, Unet, SepConvGRU (update.py:117-297, module.py:152-179)
+# ------------------------------------------------------------------------------------------------
+class ResnetBlockPlan:
+    def __init__(self, sd: SD, p: str, device, temb: Optional[Tensor]):
+        up = lambda pc: pc.to(device)
+        w1 = packing.standardize_weight(sd[f"{p}.block1.proj.weight"])
+        w2 = packing.standardize_weight(sd[f"{p}.block2.proj.weight"])
+        self.conv1 = up(packing.pack_weight(w1, sd[f"{p}.block1.proj.bias"]))
+        self.conv2 = up(packing.pack_weight(w2, sd[f"{p}.block2.proj.bias"]))
+        aff = packing.block_affine(sd, p, temb)
+        self.aff1 = tuple(t.to(device) for t in aff["block1"])
+        self.aff2 = tuple(t.to(device) for t in aff["block2"])
+        self.res = up(packing.pack_conv(sd, f"{p}.res_conv")) if f"{p}.res_conv.weight" in sd else None
+
+    def __call__(self, x: Tensor, arena: StatsArena, x2: Optional[Tensor] = None) -> Tensor:
+        s1, s2 = arena.slot(), arena.slot()
+        y1 = ops.conv(x, self.conv1, x2=x2, out_stats=s1)
+        y2 = ops.conv(y1, self.conv2, in_gn=GroupNormIn(s1, *self.aff1), out_stats=s2)
+        if self.res is not None:
+            res = ops.conv(x, self.res, x2=x2)
+        else:
+            if x2 is not None:
+                raise ValueError("identity residual with a concatenated input")
+            res = x
+        return ops.groupnorm_silu_add(y2, GroupNormIn(s2, *self.aff2), res)
+
+
+class UnetPlan:
+    """`Unet` (update.py:161-274) for one fixed timestep (time-MLP constants folded)."""
+
+    def __init__(self, sd: SD, device, dim: int, mults: Sequence[int], hidden_dim: int, t: int):
+        up = lambda pc: pc.to(device)
+        self.dim, self.hidden_dim, self.levels = dim, hidden_dim, len(mults)
+        temb = packing.time_embedding(sd, "time_mlp", t, dim)
+        self.init = up(packing.pack_conv(sd, "init_conv"))
+        L = self.levels
+        self.down_rb = [ResnetBlockPlan(sd, f"downs.{i}.0", device, temb) for i in range(L)]
+        self.down = [up(packing.pack_unshuffle_conv(sd, f"downs.{i}.1.1")) if i < L - 1
+                     else up(packing.pack_conv(sd, f"downs.{i}.1")) for i in range(L)]
+        self.gru = [tuple(up(pc) for pc in packing.pack_gru(sd, "gru", tag)) for tag in ("1", "2")]
+        self.mid = ResnetBlockPlan(sd, "mid", device, None)
+        self.up_rb = [ResnetBlockPlan(sd, f"ups.{i}.0", device, temb) for i in range(L)]
+        self.up = [up(packing.pack_conv(sd, f"ups.{i}.1.1")) if i < L - 1
+                   else up(packing.pack_conv(sd, f"ups.{i}.1")) for i in range(L)]
+        self.final = ResnetBlockPlan(sd, "final_res_block", device, temb)
+        # final_conv (delta) and conf share one 1x1 launch: channel 0 = delta, channel 1 = sigmoid(conf)
+        w = torch.cat((sd["final_conv.weight"].float(), sd["conf.weight"].float()), 0)
+        b = torch.cat((sd["final_conv.bias"].float(), sd["conf.bias"].float()), 0)
+        self.head = up(packing.pack_weight(w, b))
+        self.slots_per_call = 2 * (2 * L + 2)
+
+    def __call__(self, x: Tensor, hidden: Tensor, arena: StatsArena) -> Tuple[Tensor, Tensor]:
+        """x [B,H,W,Cin], hidden [B,H/8',W/8',hid] -> (hidden, head [B,H,W,2] = (delta, conf))."""
+        L, hid = self.levels, self.hidden_dim
+        x = ops.conv(x, self.init)
+        r = x
+        skips: List[Tensor] = []
+        for i in range(L):
+            x = self.down_rb[i](x, arena)
+            skips.append(x)
+            if i < L - 1:
+                x = ops.conv(x, self.down[i], stride=2, pad=(0, 0, 0))
+            else:
+                x = ops.conv(x, self.down[i])
+        for (zr_pc, q_pc), pad in zip(self.gru, ((0, 0, 2), (0, 2, 0))):
+            zr = ops.conv(hidden, zr_pc, x2=x, pad=pad, epi=EPI_GRU_ZR, aux1=hidden, gru_hidden=hid)
+            hidden = ops.conv(zr[..., hid:], q_pc, x2=x, pad=pad, epi=EPI_GRU_Q, aux1=zr[..., :hid], aux2=hidden)
+        x = self.mid(hidden, arena)
+        for i in range(L):
+            x = self.up_rb[i](x, arena, x2=skips.pop())
+            x = ops.conv(x, self.up[i], in_up2=(i < L - 1))
+        x = self.final(x, arena, x2=r)
+        head = ops.conv(x, self.head, act=ACT_SIGMOID, act_c0=1)
+        return hidden, head
+
+
+class EncoderPlan:
+    """`ConditionEncoder` (update.py:276-297); writes into the U-Net input buffer slice."""
+
+    def __init__(self, sd: SD, device):
+        up = lambda pc: pc.to(device)
+        self.c1, self.c2 = up(packing.pack_conv(sd, "convc1")), up(packing.pack_conv(sd, "convc2"))
+        self.d1, self.d2 = up(packing.pack_conv(sd, "convd1")), up(packing.pack_conv(sd, "convd2"))
+        self.out = up(packing.pack_conv(sd, "output"))
+        self.ctx = self.c2.cout
+
+    def __call__(self, cost: Tensor, samples: Tensor, out: Tensor) -> None:
+        B, H, W, _ = cost.shape
+        cd = torch.empty((B, H, W, 2 * self.ctx), device=cost.device, dtype=torch.float32)
+        ops.conv(ops.conv(cost, self.c1, act=ACT_RELU), self.c2, act=ACT_RELU, out=cd[..., :self.ctx])
+        ops.conv(ops.conv(samples, self.d1, act=ACT_RELU), self.d2, act=ACT_RELU, out=cd[..., self.ctx:])
+        ops.conv(cd, self.out, act=ACT_RELU, out=out)
+
+
+class UpdateBlockPlan:
+    """Eval branch of `DiffusionUpdateBlockDepth.forward` (update.py:466-521)."""
+
+    def __init__(self, sd: SD, device, *, dim: int, mults: Sequence[int], hidden_dim: int, context_dim: int,
+                 iters: int, scale: float, timesteps: int, sampling_timesteps: int, eta: float):
+        self.sd, self.device = sd, device
+        self.dim, self.mults, self.hidden_dim, self.ctx = dim, tuple(mults), hidden_dim, context_dim
+        self.iters, self.scale, self.eta = iters, float(scale), float(eta)
+        self.timesteps, self.sampling_timesteps = timesteps, sampling_timesteps
+        up = lambda pc: pc.to(device)
+        self.encoder = EncoderPlan(_sub(sd, "encoder"), device)
+        self.mask0 = up(packing.pack_conv(sd, "mask.0"))
+        self.mask2 = up(packing.pack_conv(sd, "mask.2", gain=0.25))
+        self._unets: Dict[int, UnetPlan] = {}
+        sched = packing.cosine_schedule(timesteps)
+        # prefer the buffers stored with the weights (a checkpoint may carry its own)
+        self.sched = {k: (sd[k].detach().float().cpu() if k in sd else v) for k, v in sched.items()}
+        times = torch.linspace(-1, timesteps - 1, steps=sampling_timesteps + 1)
+        times = list(reversed(times.int().tolist()))
+        self.time_pairs = list(zip(times[:-1], times[1:]))
+
+    def unet(self, t: int) -> UnetPlan:
+        if t not in self._unets:
+            self._unets[t] = UnetPlan(_sub(self.sd, "unet"), self.device, self.dim, self.mults, self.hidden_dim, t)
+        return self._unets[t]
+
+    def stats_slots(self) -> int:
+        return len(self.time_pairs) * self.iters * self.unet(self.time_pairs[0][0]).slots_per_call
+
+    def mask(self, context: Tensor) -> Tensor:
+        return ops.conv(ops.conv(context, self.mask0, act=ACT_RELU), self.mask2)
+
+    def __call__(self, cost_fn: Callable, inv0: Tensor, hidden: Tensor, ubuf: Tensor, depth_min: Tensor,
+                 depth_max: Tensor, arena: StatsArena, taps: Optional[dict] = None, tag: str = ""):
+        """inv0 [B,H,W]; hidden [B,h,w,hid]; ubuf [B,H,W,2*ctx] whose first ctx channels hold ReLU(context).
+        cost_fn(inv [B,H,W], conf or None) -> (cost [B,H,W,G*D], samples [B,H,W,D]).
+        Returns mask [B,H,W,9r^2], hidden, inv_last [B,H,W], conf_last ([B,H,W,1] view), depth_last [B,H,W]."""
+        B, H, W = inv0.shape
+        ctx = self.ctx
+        # the reference draws randn_like(inv_depth) with inv_depth [B,1,H,W] on the default generator
+        noise = torch.randn_like(inv0.view(B, 1, H, W))
+        mask = self.mask(ubuf[..., :ctx])
+        delta = torch.empty_like(inv0)
+        inv = torch.empty_like(inv0)
+        depth = torch.empty_like(inv0)
+        slot_ptr_view = ubuf[..., 2 * ctx - 1:2 * ctx]
+        img = None
+        cur_hidden, head = hidden, None
+        multi = len(self.time_pairs) > 1
+        for step, (time, time_next) in enumerate(self.time_pairs):
+            unet = self.unet(time)
+            if step == 0:
+                ops.refine_update(0, inv0, noise, 1, self.scale, delta, inv, slot_ptr_view, 2 * ctx)
+            else:
+                ops.refine_update(0, inv0, img, 1, 1.0, delta, inv, slot_ptr_view, 2 * ctx)
+            if multi:
+                img = delta.clone()
+            cur_hidden, conf = hidden, None
+            for it in range(self.iters):
+                cost, samples = cost_fn(inv, conf)
+                self.encoder(cost, samples, ubuf[..., ctx:2 * ctx - 1])
+                cur_hidden, head = unet(ubuf, cur_hidden, arena)
+                if taps is not None:
+                    taps[f"{tag}_it{it}_cost"] = cost
+                    taps[f"{tag}_it{it}_samples"] = samples
+                    taps[f"{tag}_it{it}_update"] = head[..., 0].clone()
+                    taps[f"{tag}_it{it}_hidden"] = cur_hidden
+                conf = head[..., 1:2]
+                last = it == self.iters - 1
+                ops.refine_update(1, inv0, head, 2, 1.0, delta, inv, slot_ptr_view, 2 * ctx, depth_min, depth_max,
+                                  depth if (last and depth_min is not None) else None)
+            if time_next < 0:
+                continue
+            f = lambda k, i: float(self.sched[k][i])
+            a, a_next = self.sched["alphas_cumprod"][time], self.sched["alphas_cumprod"][time_next]
+            sigma = self.eta * ((1 - a / a_next) * (1 - a_next) / (1 - a)).sqrt()
+            c = (1 - a_next - sigma ** 2).sqrt()
+            step_noise = torch.randn_like(inv0.view(B, 1, H, W))
+            ops.ddim_step(img, delta, step_noise, f("sqrt_recip_alphas_cumprod", time),
+                          f("sqrt_recipm1_alphas_cumprod", time), float(a_next.sqrt()), float(c), float(sigma), self.scale)
+        return mask, cur_hidden, inv, head[..., 1:2], depth
+
+
+# ------------------------------------------------------------------------------------------------
+# a13 CasDiffMVS.forward, test mode (diffusion.py:139-295)
+# ------------------------------------------------------------------------------------------------
+class HiddenInitPlan:
+    """`hidden_init[s-1]` (diffusion.py:53-58,91-101) followed by tanh (diffusion.py:230)."""
+
+    def __init__(self, sd: SD, device, n_strided: int):
+        self.strided = [packing.pack_conv_bn(sd, str(i)).to(device) for i in range(n_strided)]
+        self.last = packing.pack_conv(sd, str(n_strided)).to(device)
+
+    def __call__(self, x: Tensor) -> Tensor:
+        for pc in self.strided:
+            x = ops.conv(x, pc, stride=2, act=ACT_RELU)
+        return ops.conv(x, self.last, act=ACT_TANH)
+
+
+class CasDiffMVSPlan:
+    def __init__(self, sd: SD, args, device, test: bool = True):
+        self.args, self.device = args, device
+        self.cas = args.stage_iters[2] != 0
+        self.up_ratio = 2 if self.cas else 4
+        hd, cd = list(args.hidden_dim), list(args.context_dim)
+        self.hd, self.cd = hd, cd
+        self.feature = FeatureNetPlan(_sub(sd, "feature"), device, self.cas)
+        self.context = ContextNetPlan(_sub(sd, "context"), device, [hd[i] + cd[i] for i in range(3)], hd)
+        self.depthnet = InitialCostPlan(_sub(sd, "depthnet"), device, args.cost_dim_stage[0])
+        self.hidden_init: Dict[int, HiddenInitPlan] = {}
+        self.blocks: Dict[int, UpdateBlockPlan] = {}
+        for s in (1, 2):
+            if args.stage_iters[s] == 0:
+                continue
+            self.hidden_init[s] = HiddenInitPlan(_sub(sd, f"hidden_init.{s - 1}"), device, s)
+            self.blocks[s] = UpdateBlockPlan(
+                _sub(sd, f"update_block_depth{s + 1}"), device, dim=args.unet_dim[s], mults=UNET_MULTS[s],
+                hidden_dim=hd[s], context_dim=cd[s], iters=args.stage_iters[s], scale=args.scale[s],
+                timesteps=args.timesteps[s], sampling_timesteps=args.sampling_timesteps[s], eta=args.ddim_eta[s])
+
+    def forward(self, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
+                taps: Optional[dict] = None) -> Dict[str, List[Tensor]]:
+        args = self.args
+        V = len(imgs)
+        B, _, H, W = imgs[0].shape
+        dev = imgs[0].device
+        if H % 32 or W % 32:
+            raise ValueError(f"image size {H}x{W} must be a multiple of 32 (datasets/mvs.py:104-115)")
+        depth_values = depth_values.float()
+        depth_max = (1.0 / depth_values[:, 0]).contiguous()    # diffusion.py:140-143
+        depth_min = (1.0 / depth_values[:, -1]).contiguous()
+        interval0 = 1.0 / depth_values.size(1)
+
+        # all views through FeatureNet as one batch (the reference loops, diffusion.py:156-157)
+        x_all = torch.empty((V, B, H, W, 3), device=dev, dtype=torch.float32)
+        for v, im in enumerate(imgs):
+            ops.to_nhwc(im.float(), out=x_all[v])
+        feats = self.feature(x_all.view(V * B, H, W, 3))
+        ctx_feats = self.context.trunk(x_all[0])
+
+        slots = sum(b.stats_slots() for b in self.blocks.values())
+        arena = StatsArena(dev, B, max(slots, 1))
+
+        depths: List[Tensor] = []
+        confs: List[Tensor] = []
+        view_weights = None
+        norm_cur = None
+        for s in range(3):
+            if args.stage_iters[s] == 0:
+                continue
+            key = f"stage{s + 1}"
+            fs = feats[key]
+            fs = fs.view(V, B, *fs.shape[1:])
+            hom = ops.compose_homographies(proj_matrices[key].float())
+            h, w = fs.shape[2], fs.shape[3]
+            if s == 0:
+                D0 = args.numdepth_initial
+                # plane depths: disp_to_depth(d/(D-1)) exactly as diffusion.py:187-192 / module.py:220-227
+                planes = torch.arange(D0, device=dev, dtype=torch.float32).view(1, D0) / (D0 - 1.0)
+                min_disp, max_disp = 1 / depth_max.view(B, 1), 1 / depth_min.view(B, 1)
+                plane_depth = 1 / (min_disp + (max_disp - min_disp) * planes).clamp(min=1e-6)
+                context = ops.conv(ctx_feats[1], self.context.heads_ctx[1], act=ACT_RELU)
+                mask, n, depth, view_weights, conf = self.depthnet(fs, context, hom, plane_depth, depth_min, depth_max,
+                                                                   taps)
+                depths.append(depth)
+                confs.append(ops.upsample_nearest(conf, 8))
+                depth_up, norm_cur = ops.upsample_depth(n, mask, depth_min, depth_max, 2)
+                depths.append(depth_up)
+                if taps is not None:
+                    taps.update(stage1_mask=mask, stage1_inv=n, view_weights=view_weights, stage1_conf=conf,
+                                feat_stage1=fs, context1=context)
+            else:
+                blk = self.blocks[s]
+                cdim, hdim = self.cd[s], self.hd[s]
+                ubuf = torch.empty((B, h, w, 2 * cdim), device=dev, dtype=torch.float32)
+                hidden_raw = ops.conv(ctx_feats[s + 1], self.context.heads_hidden[s + 1])
+                ops.conv(ctx_feats[s + 1], self.context.heads_ctx[s + 1], act=ACT_RELU, out=ubuf[..., :cdim])
+                hidden = self.hidden_init[s](hidden_raw)
+                G, D = args.cost_dim_stage[1], args.CostNum[s]
+                interval = interval0 * INTERVAL_RATIO[s]
+
+                def cost_fn(inv, conf, fs=fs, hom=hom, s=s, G=G, D=D, interval=interval):
+                    return ops.get_cost(fs, hom, inv, conf, view_weights, depth_min, depth_max, G, D, s, interval,
+                                        float(args.min_radius), float(args.max_radius))
+
+                mask, hidden, inv_last, conf_last, depth_last = blk(cost_fn, norm_cur, hidden, ubuf, depth_min, depth_max,
+                                                                    arena, taps, key)
+                depths.append(depth_last)
+                confs.append(ops.upsample_nearest(conf_last, 2 ** (3 - s)))
+                depth_up, norm_cur = ops.upsample_depth(inv_last, mask, depth_min, depth_max, self.up_ratio)
+                depths.append(depth_up)
+                if taps is not None:
+                    taps[f"{key}_mask"] = mask
+                    taps[f"{key}_hidden0"] = hidden
+        return {"depth": depths, "conf": [], "photometric_confidence": confs}

@@ -1,0 +1,198 @@
+/*
+ * diffmvs_b200 - C ABI of the B200 (sm_100a) kernels behind the DiffMVS / CasDiffMVS hot path.
+ *
+ * The reference (cvg/diffmvs) is pure PyTorch and has no FFI of its own; the
+ * boundary it offers is the Python `models/` operator surface.  Every entry point below replaces the
+ * ATen call sequence of one reference operator (file:line cited per function) and is bound from
+ * `diffmvs_b200/_cabi.py` with ctypes - plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - all tensors are fp32, device memory, channels-last: 2-D maps are [N][H][W][C], volumes are
+ *     [N][D][H][W][C].  A "pixel stride" (`*_ps`) is the distance in floats between consecutive
+ *     pixels, so a channel slice of a wider buffer is addressed with ptr+offset and the wide stride
+ *     (this is how every `torch.cat`/`torch.split` of the reference is made free).
+ *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*); it never
+ *     allocates, synchronises or throws.  Return value: 0 on success, DMVS_ERR_* (<0) for invalid
+ *     arguments, or a positive cudaError_t from the launch.
+ *   - outputs are written in full; `*_stats` accumulators must be zeroed by the caller.
+ */
+#ifndef DIFFMVS_B200_H
+#define DIFFMVS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMVS_ABI_VERSION 1
+
+#define DMVS_ERR_ARG (-1)      /* null pointer / non-positive size / unsupported combination */
+#define DMVS_ERR_ALIGN (-2)    /* pointer or stride not aligned as documented */
+#define DMVS_ERR_UNSUPPORTED (-3)
+
+/* activation codes */
+#define DMVS_ACT_NONE 0
+#define DMVS_ACT_RELU 1
+#define DMVS_ACT_SIGMOID 2
+#define DMVS_ACT_TANH 3
+#define DMVS_ACT_SILU 4
+
+/* residual placement */
+#define DMVS_RES_NONE 0
+#define DMVS_RES_PRE_ACT 1  /* y = act(conv + bias + res)   ResidualBlock, module.py:315-319 */
+#define DMVS_RES_POST_ACT 2 /* y = act(conv + bias) + res   CostRegNet skips, module.py:445-446 */
+
+/* epilogue kinds */
+#define DMVS_EPI_STD 0
+#define DMVS_EPI_GRU_ZR 1 /* c<hid: z=sigmoid(v); c>=hid: r*h = sigmoid(v)*aux1[c-hid]   module.py:166-168 */
+#define DMVS_EPI_GRU_Q 2  /* h' = (1-z)*h + z*tanh(v), z=aux1, h=aux2                     module.py:169-170 */
+
+int dmvs_abi_version(void);
+/* Human-readable build string ("sm_100a, nvcc 12.9, ..."). */
+const char* dmvs_build_info(void);
+/* Kernels launched by this library since it was loaded (host-side counter, for bench.py's gpu_launches). */
+uint64_t dmvs_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Direct convolution, 2-D or 3-D (KD=1,D=1 for 2-D), stride 1 or 2 in every spatial dim, zero pad.
+ * Replaces nn.Conv2d / nn.Conv3d (+ folded eval BatchNorm, + activation, + residual) everywhere
+ * in the reference: module.py:42-58,88-102,282-301,332-336,364-396,427-439,455-456,481-485;
+ * update.py:44-48,94,186,222,237-243,281-287,335-339; SepConvGRU module.py:156-177.
+ *
+ * Weights are pre-packed by the host as [KD][KH][KW][cin_pad][cout_pad] (cin_pad = (C1+C2) rounded
+ * up to 4, cout_pad = Cout rounded up to 4, zero filled), BN scale folded in, BN shift in `bias`.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dmvs_conv_desc {
+  /* input (virtual concat of x[.., C1] and x2[.., C2] along channels; x2 may be NULL) */
+  const float* x;
+  const float* x2;
+  int32_t N, D, H, W;       /* logical input size (after the optional nearest x2 upsample) */
+  int32_t C1, C2;
+  int32_t x_ps, x2_ps;      /* pixel strides of x / x2 in floats */
+  int32_t in_up2;           /* 1: x is stored at (H/2, W/2) and nearest-upsampled on load (update.py:38-42) */
+  /* optional GroupNorm(4 groups)+affine+SiLU applied to x on load (update.py:117-133):
+   * v = silu((v - mean_g) * rstd_g * in_g1[c] + in_g0[c]); stats = [N][4][2] doubles (sum, sumsq) */
+  const double* in_stats;
+  const float* in_g1;
+  const float* in_g0;
+  float in_inv_count;       /* 1 / (elements per (sample, group)) */
+  /* weights */
+  const float* w;
+  const float* bias;        /* [Cout] or NULL */
+  int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;
+  /* output */
+  float* y;
+  int32_t Do, Ho, Wo, Cout;
+  int32_t y_ps;
+  /* epilogue */
+  int32_t act, act_c0;      /* activation applied to channels >= act_c0 */
+  int32_t res_mode;
+  const float* res;
+  int32_t res_ps, res_up2;  /* res_up2: residual stored at half resolution, nearest-upsampled (module.py:409-416) */
+  int32_t epi;
+  const float* aux1;
+  const float* aux2;
+  int32_t aux1_ps, aux2_ps, gru_hidden;
+  double* out_stats;        /* optional [N][4][2] sum / sumsq of the written values per GroupNorm group */
+} dmvs_conv_desc;
+
+int dmvs_conv_f32(const dmvs_conv_desc* desc, void* stream);
+
+/* ConvTranspose3d(k=3, s=2, p=1, output_padding=1) + folded BN + ReLU + skip add
+ * (module.Deconv3d as used by CostRegNet_small, module.py:110-144,436-437,445-446).
+ * x [N][D][H][W][Cin] -> y [N][2D][2H][2W][Cout]; w packed [27][Cin][Cout]; skip has y's shape. */
+int dmvs_deconv3d_f32(const float* x, const float* w, const float* bias, const float* skip, float* y,
+                      int32_t N, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Homography warp + group-wise correlation (module.py:181-218, 514-548, 575-667).
+ * ------------------------------------------------------------------------------------------- */
+
+/* proj [B][V][2][4][4] (extrinsic, intrinsic) -> hom [B][V-1][12] = rows of [R|t] of
+ * P_src @ inverse(P_ref), P = [K E[:3,:4]; 0 0 0 1]   (module.py:188-190, 520-525).  fp64 inside. */
+int dmvs_compose_homographies(const float* proj, float* hom, int32_t B, int32_t V, void* stream);
+
+/* differentiable_warping (module.py:181-218): src [B][Hs][Ws][C] (pixel stride src_ps), hom [B][12],
+ * depth [B][D][H][W] -> out [B][D][H][W][C] (channels-last volume).  Operator-surface entry point; the
+ * fused kernels below never materialise this volume. */
+int dmvs_warp_volume(const float* src, int32_t src_ps, const float* hom, const float* depth, float* out,
+                     int32_t B, int32_t C, int32_t Hs, int32_t Ws, int32_t D, int32_t H, int32_t W, void* stream);
+
+/* Stage-1 sweep (module.py:518-531): for every source view v and plane d, cor[b][v][d][y][x][g] =
+ * mean_k ref[g*C/G+k] * warp(src_v)[g*C/G+k].  feats [V][B][H][W][C] (view 0 = reference, pixel
+ * stride C), hom [B][V-1][12], plane_depth [B][D] metric depth per plane.  cor [B*(V-1)][D][H][W][G]. */
+int dmvs_plane_sweep_corr(const float* feats, const float* hom, const float* plane_depth, float* cor,
+                          int32_t B, int32_t V, int32_t C, int32_t G, int32_t D, int32_t H, int32_t W, void* stream);
+
+/* PixelViewWeight tail (module.py:460-463): logit [N][D][H][W] -> w [N][H][W] = max_d sigmoid(logit). */
+int dmvs_view_weight_max(const float* logit, float* w, int32_t N, int32_t D, int32_t HW, void* stream);
+
+/* Stage-1 aggregation (module.py:539-548): vol[b] = sum_v w_v*cor_v / (1e-8 + sum_v w_v).
+ * cor [B][V1][D][H][W][G], w [B][V1][H][W] -> vol [B][D][H][W][G]. */
+int dmvs_aggregate_views(const float* cor, const float* w, float* vol, int32_t B, int32_t V1, int32_t D,
+                         int32_t HW, int32_t G, void* stream);
+
+/* softmax over D + expected index + window-4 confidence (module.py:554-571).
+ * logits [B][D][H][W] -> norm_inv [B][H][W] (= idx/(D-1)), depth [B][H][W], conf [B][H][W],
+ * floor_idx [B][H][W] (int32, optional).  depth_min/depth_max [B] = 1/depth_values[:,-1], 1/depth_values[:,0]
+ * (diffusion.py:140-143). */
+int dmvs_depth_regression(const float* logits, const float* depth_min, const float* depth_max, float* norm_inv,
+                          float* depth, float* conf, int32_t* floor_idx, int32_t B, int32_t D, int32_t HW,
+                          void* stream);
+
+/* GetCost (module.py:250-277, 583-667) fused: hypothesis sampler + V-1 warps + group correlation +
+ * view-weighted mean.  feats [V][B][H][W][C]; inv_depth [B][H][W]; conf [B][H][W] or NULL;
+ * view_w [B][V-1][H>>wshift][W>>wshift] (stage-1 weights, nearest-upsampled on the fly,
+ * diffusion.py:219-221); cost [B][H][W][G*D] channel g*D+d (pixel stride cost_ps);
+ * samples [B][H][W][D] (pixel stride samp_ps). */
+int dmvs_get_cost(const float* feats, const float* hom, const float* inv_depth, const float* conf, int32_t conf_ps,
+                  const float* view_w, const float* depth_min, const float* depth_max, float* cost, int32_t cost_ps,
+                  float* samples, int32_t samp_ps, int32_t B, int32_t V, int32_t C, int32_t G, int32_t D, int32_t H,
+                  int32_t W, int32_t wshift, float interval, float min_radius, float max_radius, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Point-wise pieces
+ * ------------------------------------------------------------------------------------------- */
+
+/* Block tail of ResnetBlock (update.py:117-159): y = silu(GN(x)*g1+g0) + res.
+ * x [N][HW][C] raw conv output, stats [N][4][2]; res (pixel stride res_ps) or NULL. */
+int dmvs_groupnorm_silu_add(const float* x, const double* stats, const float* g1, const float* g0, const float* res,
+                            int32_t res_ps, float* y, int32_t y_ps, int32_t N, int32_t HW, int32_t C, void* stream);
+
+/* upsample_depth (module.py:237-248) + disp_to_depth (module.py:220-227) + depth_to_disp (:229-235).
+ * n [B][H][W], mask [B][H][W][9*r*r] -> raw_up [B][rH][rW] (the convex combination itself), depth_up
+ * (= disp_to_depth(raw_up)), norm_up (= depth_to_disp(depth_up), the value the next stage starts from,
+ * diffusion.py:215-217).  Each output is optional; depth_min/max are needed for the last two. */
+int dmvs_upsample_depth(const float* n, const float* mask, int32_t mask_ps, const float* depth_min,
+                        const float* depth_max, float* raw_up, float* depth_up, float* norm_up, int32_t B, int32_t H,
+                        int32_t W, int32_t ratio, void* stream);
+
+/* Refinement state update (update.py:479-483, 496-502).
+ * mode 0 (start of a DDIM step): inv = clamp(inv0 + img, 0, 1); delta = inv - inv0, img = scale*noise
+ *        when noise != NULL else img read from `delta` (in place).
+ * mode 1 (after an iteration):   delta += upd; inv = clamp(inv0 + delta, 0, 1); delta = inv - inv0.
+ * inv is written twice: dense [B][HW] and into channel `inv_slot` of a [B][HW][slot_ps] buffer (the
+ * U-Net input, update.py:297,493).  depth (optional) = disp_to_depth(inv). */
+int dmvs_refine_update(int32_t mode, const float* inv0, const float* noise_or_upd, int32_t upd_ps, float scale,
+                       float* delta, float* inv, float* inv_slot, int32_t slot_ps, const float* depth_min,
+                       const float* depth_max, float* depth, int32_t B, int32_t HW, void* stream);
+
+/* DDIM step (update.py:504-519): img = delta*sqrt(a_next) + c*pred_noise + sigma*(scale*noise) with
+ * pred_noise = (k_recip*img - delta)/k_recipm1.  All scalars precomputed on the host. */
+int dmvs_ddim_step(float* img, const float* delta, const float* noise, float k_recip, float k_recipm1,
+                   float sqrt_a_next, float c, float sigma, float scale, int64_t count, void* stream);
+
+/* nearest-neighbour upsampling of a [B][H][W] map (element stride x_ps) by an integer factor
+ * (diffusion.py:205-207,274-278). */
+int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int32_t B, int32_t H, int32_t W, int32_t factor,
+                          void* stream);
+
+/* layout transposes between the reference's NCHW operator surface and channels-last */
+int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t N, int32_t C, int32_t HW, void* stream);
+int dmvs_nhwc_to_nchw(const float* x, int32_t x_ps, float* y, int32_t N, int32_t C, int32_t HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFMVS_B200_H */

@@ -1,0 +1,378 @@
+"""Operator-level parity of the CUDA kernels (through the C ABI) against the CPU oracle / plain torch fp32.
+
+Everything here needs a GPU (`-m gpu`).  References are computed on the CPU in fp32 with stock torch ops
+(the same ops the reference model issues); tolerances are stated per test.  fp32 kernels with a
+different summation order agree to ~1e-6 relative; integer outputs (floor index) must match exactly.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffmvs_b200 import ops, packing
+from oracle import diffmvs_ref as O
+from tests.helpers import load_golden, rel_l1
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, lo=-1.0, hi=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return lo + (hi - lo) * torch.rand(*shape, generator=g)
+
+
+def _nhwc(x):  # CPU NCHW -> GPU [N,H,W,C]
+    return x.permute(0, 2, 3, 1).contiguous().to(DEV)
+
+
+def _nchw(y):  # GPU [N,H,W,C] -> CPU NCHW
+    return y.permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def _close(got, ref, tol=2e-6, what=""):
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    assert err <= tol * max(scale, 1.0), f"{what}: max abs err {err:.3e} (scale {scale:.3e})"
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # cin, cout, k, stride, H, W
+    (3, 8, (3, 3), 1, 40, 72),
+    (8, 8, (3, 3), 1, 33, 50),
+    (8, 16, (5, 5), 2, 64, 96),
+    (16, 32, (5, 5), 2, 32, 64),
+    (32, 64, (5, 5), 2, 32, 32),
+    (64, 64, (3, 3), 1, 16, 20),
+    (64, 48, (1, 1), 1, 16, 20),
+    (64, 16, (7, 7), 1, 32, 40),
+    (32, 8, (7, 7), 1, 64, 80),
+    (24, 31, (3, 3), 1, 32, 40),
+    (6, 32, (3, 3), 1, 32, 40),
+    (64, 36, (1, 1), 1, 32, 40),
+    (64, 144, (1, 1), 1, 16, 24),
+    (52, 40, (1, 5), 1, 16, 20),
+    (52, 20, (5, 1), 1, 16, 20),
+    (16, 2, (1, 1), 1, 32, 40),
+    (4, 1, (3, 3), 1, 17, 19),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", CONV_CASES)
+def test_conv2d_matches_torch(cin, cout, k, stride, H, W):
+    N = 2
+    x = _rand(N, cin, H, W, seed=1)
+    w = _rand(cout, cin, *k, seed=2) * (1.0 / math.sqrt(cin * k[0] * k[1]))
+    b = _rand(cout, seed=3)
+    pad = (k[0] // 2, k[1] // 2)
+    ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=pad))
+    pc = packing.pack_weight(w, b).to(DEV)
+    y = ops.conv(_nhwc(x), pc, stride=stride, act=ops.ACT_RELU)
+    assert tuple(y.shape) == (N, ref.shape[2], ref.shape[3], cout)
+    _close(_nchw(y), ref, what=f"conv {cin}->{cout} k{k} s{stride}")
+
+
+def test_conv2d_epilogues_and_views():
+    N, H, W = 1, 24, 40
+    x1, x2 = _rand(N, 16, H, W, seed=1), _rand(N, 8, H, W, seed=2)
+    w, b = _rand(20, 24, 3, 3, seed=3) * 0.1, _rand(20, seed=4)
+    res = _rand(N, 20, H, W, seed=5)
+    pc = packing.pack_weight(w, b).to(DEV)
+    conv = F.conv2d(torch.cat((x1, x2), 1), w, b, padding=1)
+    # virtual concat + residual before ReLU (ResidualBlock)
+    y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), act=ops.ACT_RELU, res=_nhwc(res), res_mode=ops.RES_PRE_ACT)
+    _close(_nchw(y), F.relu(conv + res), what="concat+res_pre")
+    # residual after ReLU (CostRegNet skip)
+    y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), act=ops.ACT_RELU, res=_nhwc(res), res_mode=ops.RES_POST_ACT)
+    _close(_nchw(y), F.relu(conv) + res, what="res_post")
+    # activation only from channel 5 on, tanh / sigmoid / silu
+    for act, fn in ((ops.ACT_TANH, torch.tanh), (ops.ACT_SIGMOID, torch.sigmoid), (ops.ACT_SILU, F.silu)):
+        y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), act=act, act_c0=5)
+        ref = conv.clone()
+        ref[:, 5:] = fn(conv[:, 5:])
+        _close(_nchw(y), ref, what=f"act {act} from c5")
+    # channel-sliced input and output inside wider buffers
+    wide_in = torch.zeros(N, H, W, 40, device=DEV)
+    wide_in[..., 8:24] = _nhwc(x1)
+    wide_in[..., 32:40] = _nhwc(x2)
+    wide_out = torch.full((N, H, W, 64), 7.0, device=DEV)
+    ops.conv(wide_in[..., 8:24], pc, x2=wide_in[..., 32:40], out=wide_out[..., 4:24])
+    _close(_nchw(wide_out[..., 4:24]), conv, what="sliced io")
+    assert torch.all(wide_out[..., :4] == 7.0) and torch.all(wide_out[..., 24:] == 7.0)
+    # nearest-upsampled residual (FPN lateral, module.py:409-416)
+    small = _rand(N, 20, H // 2, W // 2, seed=6)
+    y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), res=_nhwc(small), res_mode=ops.RES_PRE_ACT, res_up2=True)
+    _close(_nchw(y), conv + F.interpolate(small, scale_factor=2, mode="nearest"), what="res_up2")
+    # nearest-upsampled input (update.py:38-42)
+    xs = _rand(N, 24, H // 2, W // 2, seed=7)
+    y = ops.conv(_nhwc(xs), pc, in_up2=True)
+    _close(_nchw(y), F.conv2d(F.interpolate(xs, scale_factor=2, mode="nearest"), w, b, padding=1), what="in_up2")
+
+
+def test_conv_unshuffle_equals_reference_downsample():
+    x = _rand(2, 8, 32, 48, seed=1)
+    w, b = _rand(16, 32, 1, 1, seed=2) * 0.2, _rand(16, seed=3)
+    ref = F.conv2d(O.pixel_unshuffle2(x), w, b)
+    pc = packing.pack_unshuffle_conv({"d.weight": w, "d.bias": b}, "d").to(DEV)
+    y = ops.conv(_nhwc(x), pc, stride=2, pad=(0, 0, 0))
+    _close(_nchw(y), ref, what="pixel-unshuffle conv")
+
+
+def test_conv_bn_folding():
+    sd = {"c.conv.weight": _rand(16, 8, 3, 3, seed=1) * 0.2, "c.bn.weight": _rand(16, seed=2, lo=0.5, hi=1.5),
+          "c.bn.bias": _rand(16, seed=3), "c.bn.running_mean": _rand(16, seed=4),
+          "c.bn.running_var": _rand(16, seed=5, lo=0.5, hi=2.0)}
+    x = _rand(1, 8, 20, 36, seed=6)
+    ref = O.conv_bn_act(sd, "c", x)
+    y = ops.conv(_nhwc(x), packing.pack_conv_bn(sd, "c").to(DEV), act=ops.ACT_RELU)
+    _close(_nchw(y), ref, tol=5e-6, what="conv+bn fold")
+
+
+@pytest.mark.parametrize("cin,cout,stride", [(4, 8, 1), (8, 8, 1), (8, 16, 2), (16, 32, 2), (32, 32, 1), (8, 1, 1)])
+def test_conv3d_matches_torch(cin, cout, stride):
+    N, D, H, W = 2, 8, 12, 20
+    x = _rand(N, cin, D, H, W, seed=1)
+    w, b = _rand(cout, cin, 3, 3, 3, seed=2) * (1 / math.sqrt(27 * cin)), _rand(cout, seed=3)
+    ref = F.relu(F.conv3d(x, w, b, stride=stride, padding=1))
+    y = ops.conv(x.permute(0, 2, 3, 4, 1).contiguous().to(DEV), packing.pack_weight(w, b).to(DEV), stride=stride,
+                 act=ops.ACT_RELU)
+    _close(y.permute(0, 4, 1, 2, 3).cpu(), ref, what=f"conv3d {cin}->{cout} s{stride}")
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 16), (16, 8)])
+def test_deconv3d_matches_torch(cin, cout):
+    N, D, H, W = 1, 3, 5, 7
+    sd = {"d.conv.weight": _rand(cin, cout, 3, 3, 3, seed=1) * 0.1, "d.bn.weight": _rand(cout, seed=2, lo=0.5, hi=1.5),
+          "d.bn.bias": _rand(cout, seed=3), "d.bn.running_mean": _rand(cout, seed=4) * 0.1,
+          "d.bn.running_var": _rand(cout, seed=5, lo=0.5, hi=2.0)}
+    x = _rand(N, cin, D, H, W, seed=6)
+    skip = _rand(N, cout, 2 * D, 2 * H, 2 * W, seed=7)
+    ref = skip + O.deconv3d_bn_relu(sd, "d", x)
+    w, b = packing.pack_deconv3d_bn(sd, "d")
+    y = ops.deconv3d(x.permute(0, 2, 3, 4, 1).contiguous().to(DEV), w.to(DEV), b.to(DEV),
+                     skip.permute(0, 2, 3, 4, 1).contiguous().to(DEV))
+    _close(y.permute(0, 4, 1, 2, 3).cpu(), ref, tol=5e-6, what="deconv3d")
+
+
+def test_groupnorm_pipeline_matches_resnet_block():
+    """conv(+stats) -> conv(GN+SiLU prologue, +stats) -> groupnorm_silu_add == oracle resnet_block."""
+    from diffmvs_b200 import pipeline
+    dim_in, dim_out, H, W, N = 24, 16, 20, 28, 2
+    g = lambda *s, seed: _rand(*s, seed=seed) * 0.3
+    sd = {"rb.block1.proj.weight": g(dim_out, dim_in, 3, 3, seed=1), "rb.block1.proj.bias": g(dim_out, seed=2),
+          "rb.block1.norm.weight": _rand(dim_out, seed=3, lo=0.5, hi=1.5), "rb.block1.norm.bias": g(dim_out, seed=4),
+          "rb.block2.proj.weight": g(dim_out, dim_out, 3, 3, seed=5), "rb.block2.proj.bias": g(dim_out, seed=6),
+          "rb.block2.norm.weight": _rand(dim_out, seed=7, lo=0.5, hi=1.5), "rb.block2.norm.bias": g(dim_out, seed=8),
+          "rb.res_conv.weight": g(dim_out, dim_in, 1, 1, seed=9), "rb.res_conv.bias": g(dim_out, seed=10),
+          "rb.mlp.1.weight": g(2 * dim_out, 64, seed=11), "rb.mlp.1.bias": g(2 * dim_out, seed=12)}
+    temb = _rand(1, 64, seed=13)
+    x = _rand(N, dim_in, H, W, seed=14)
+    ref = O.resnet_block(sd, "rb", x, temb.expand(N, -1))
+    plan = pipeline.ResnetBlockPlan(sd, "rb", DEV, temb)
+    arena = pipeline.StatsArena(DEV, N, 2)
+    xg = _nhwc(x)
+    y = plan(xg[..., :16], arena, x2=xg[..., 16:])
+    assert rel_l1(_nchw(y), ref) < 2e-6
+    _close(_nchw(y), ref, tol=2e-5, what="resnet block")
+
+
+def test_gru_matches_oracle():
+    from diffmvs_b200.models.module import SepConvGRU
+    hid, cin, H, W = 20, 32, 18, 25
+    gru = SepConvGRU(hid, cin).eval()
+    sd = {k: _rand(*v.shape, seed=i) * 0.2 for i, (k, v) in enumerate(gru.state_dict().items())}
+    gru.load_state_dict(sd)
+    h, x = torch.tanh(_rand(1, hid, H, W, seed=50)), _rand(1, cin, H, W, seed=51)
+    ref = O.sep_conv_gru({"g." + k: v for k, v in sd.items()}, "g", h, x)
+    out = gru.to(DEV)(h.to(DEV), x.to(DEV))
+    _close(out.cpu(), ref, tol=5e-6, what="SepConvGRU")
+
+
+# ------------------------------------------------------------------------------------------------
+# warp / correlation
+# ------------------------------------------------------------------------------------------------
+def _cameras(B, V, W, H, seed=0, rot=True):
+    """[B,V,2,4,4] with mild rotations so that some samples leave the image and z varies."""
+    g = torch.Generator().manual_seed(seed)
+    P = torch.zeros(B, V, 2, 4, 4)
+    for b in range(B):
+        for v in range(V):
+            E = torch.eye(4)
+            if v > 0:
+                if rot:
+                    a = (torch.rand(3, generator=g) - 0.5) * 0.08
+                    Rx = torch.tensor([[1, 0, 0], [0, math.cos(a[0]), -math.sin(a[0])], [0, math.sin(a[0]), math.cos(a[0])]])
+                    Ry = torch.tensor([[math.cos(a[1]), 0, math.sin(a[1])], [0, 1, 0], [-math.sin(a[1]), 0, math.cos(a[1])]])
+                    Rz = torch.tensor([[math.cos(a[2]), -math.sin(a[2]), 0], [math.sin(a[2]), math.cos(a[2]), 0], [0, 0, 1]])
+                    E[:3, :3] = Rz @ Ry @ Rx
+                E[:3, 3] = (torch.rand(3, generator=g) - 0.5) * torch.tensor([120.0, 60.0, 20.0])
+            K = torch.tensor([[1.8 * W, 0, W / 2], [0, 1.8 * W, H / 2], [0, 0, 1.0]])
+            P[b, v, 0] = E
+            P[b, v, 1, :3, :3] = K
+    return P
+
+
+def test_warp_matches_golden_reference():
+    g = load_golden("cas_tiny")
+    t = lambda k: torch.from_numpy(g["tap_" + k])
+    from diffmvs_b200.models.module import differentiable_warping
+    out = differentiable_warping(t("warp_src").to(DEV), t("warp_src_proj").to(DEV), t("warp_ref_proj").to(DEV),
+                                 t("warp_depth").to(DEV))
+    assert tuple(out.shape) == tuple(t("warp_out").shape)
+    assert rel_l1(out, t("warp_out")) < 1e-5
+
+
+@pytest.mark.parametrize("C", [16, 32, 48, 5])
+def test_warp_volume_matches_oracle_with_out_of_bounds(C):
+    B, H, W, D = 2, 24, 40, 6
+    P = _cameras(B, 2, W, H, seed=3)
+    src = _rand(B, C, H, W, seed=1)
+    depth = 400 + 600 * torch.rand(B, D, H, W, generator=torch.Generator().manual_seed(2))
+    depth[0, 0, :4] = -50.0         # negative z is not masked by the reference
+    ref = O.differentiable_warping(src, O.compose_projection(P[:, 1]), O.compose_projection(P[:, 0]), depth)
+    hom = ops.compose_homographies(P.to(DEV))[:, 0].contiguous()
+    out = ops.warp_volume(_nhwc(src), hom, depth.to(DEV))
+    got = out.permute(0, 4, 1, 2, 3).cpu()
+    # homography computed in fp64 here vs fp32 LU in torch: coordinates agree to ~1e-4 px
+    assert rel_l1(got, ref) < 2e-4
+    frac_oob = (ref == 0).float().mean().item()
+    assert 0.0 < frac_oob < 0.9
+
+
+def test_plane_sweep_aggregate_and_regression_match_oracle():
+    B, V, C, G, D, H, W = 1, 4, 48, 4, 8, 16, 20
+    P = _cameras(B, V, W, H, seed=5)
+    feats = [_rand(B, C, H, W, seed=10 + v) for v in range(V)]
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384).view(1, -1)
+    rng = O.DepthRange(dv)
+    planes = rng.to_depth((torch.arange(D).float() / (D - 1.0)).view(1, D, 1, 1).repeat(1, 1, H, W))
+    ref_proj = O.compose_projection(P[:, 0])
+    cors = [O.group_correlation(O.differentiable_warping(feats[v], O.compose_projection(P[:, v]), ref_proj, planes),
+                                feats[0], G) for v in range(1, V)]
+    hom = ops.compose_homographies(P.to(DEV))
+    fs = torch.stack([_nhwc(f) for f in feats], 0)
+    cor = ops.plane_sweep_corr(fs, hom, planes[:, :, 0, 0].contiguous().to(DEV), G)
+    for v in range(V - 1):
+        got = cor[v].permute(3, 0, 1, 2).cpu().unsqueeze(0)       # [1,G,D,H,W]
+        assert rel_l1(got, cors[v]) < 2e-4, v
+    # aggregation with given weights, using the kernel's own correlation volumes as input
+    w = torch.rand(B * (V - 1), H, W, generator=torch.Generator().manual_seed(3))
+    vol = ops.aggregate_views(cor, w.to(DEV), B)
+    cc = cor.cpu()
+    acc, ws = 0, 1e-8
+    for v in range(V - 1):
+        ws = ws + w[v].view(1, H, W, 1)
+        acc = acc + w[v].view(1, H, W, 1) * cc[v]
+    _close(vol[0].cpu(), acc / ws, tol=1e-6, what="aggregate")
+    # view-weight max
+    logit = _rand(3, D, H, W, seed=4) * 3
+    _close(ops.view_weight_max(logit.to(DEV)).cpu(), torch.sigmoid(logit).max(1)[0], tol=1e-6, what="view weight max")
+
+
+@pytest.mark.parametrize("D", [8, 48, 96])
+def test_depth_regression_indices_bit_exact(D):
+    B, H, W = 2, 36, 50
+    logits = _rand(B, D, H, W, seed=D) * 4.0
+    logits[0, :, 0, 0] = 0.0                     # uniform -> expected index (D-1)/2
+    logits[0, :, 0, 1] = -30.0
+    logits[0, D - 1, 0, 1] = 30.0                # one-hot at the last plane
+    logits[0, 0, 0, 2] = 40.0                    # one-hot at the first plane
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384).view(1, -1).repeat(B, 1)
+    rng = O.DepthRange(dv)
+    idx, j, conf = O.depth_regression(logits)
+    n_ref = idx / (D - 1.0)
+    n, depth, cf, fl = ops.depth_regression(logits.to(DEV), rng.depth_min.view(B).to(DEV), rng.depth_max.view(B).to(DEV),
+                                            want_floor=True)
+    mism = (fl.cpu().long() != j[:, 0]).float().mean().item()
+    assert mism == 0.0, f"floor(expected index) differs on {mism:.2%} of pixels"
+    _close(n.cpu(), n_ref[:, 0], tol=2e-6, what="normalised index")
+    assert rel_l1(depth, rng.to_depth(n_ref)[:, 0]) < 1e-6
+    _close(cf.cpu(), conf[:, 0], tol=2e-6, what="confidence")
+
+
+@pytest.mark.parametrize("C,D,with_conf,wshift", [(32, 4, False, 1), (32, 6, True, 1), (16, 4, True, 2), (16, 4, False, 0)])
+def test_get_cost_matches_oracle(C, D, with_conf, wshift):
+    B, V, G, H, W = 2, 3, 4, 32, 48
+    P = _cameras(B, V, W, H, seed=7, rot=True)
+    feats = [_rand(B, C, H, W, seed=20 + v) for v in range(V)]
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384).view(1, -1).repeat(B, 1)
+    rng = O.DepthRange(dv)
+    inv = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(1))
+    inv[0, 0, :2] = 0.0
+    inv[0, 0, 2:4] = 1.0
+    conf = torch.rand(B, H, W, generator=torch.Generator().manual_seed(2)) if with_conf else None
+    vw_small = torch.rand(B, V - 1, H >> wshift, W >> wshift, generator=torch.Generator().manual_seed(3))
+    vw = F.interpolate(vw_small, scale_factor=2 ** wshift, mode="nearest") if wshift else vw_small
+    interval = 2.0 / 384
+    cost_ref, samp_ref = O.get_cost(inv, feats, P, interval, rng, D, vw, conf, G, 0.125, 8.0)
+    fs = torch.stack([_nhwc(f) for f in feats], 0)
+    hom = ops.compose_homographies(P.to(DEV))
+    cost, samp = ops.get_cost(fs, hom, inv[:, 0].contiguous().to(DEV), None if conf is None else conf.to(DEV),
+                              vw_small.to(DEV), rng.depth_min.view(B).to(DEV), rng.depth_max.view(B).to(DEV), G, D, wshift,
+                              interval, 0.125, 8.0)
+    _close(_nchw(samp), samp_ref, tol=1e-6, what="hypotheses")
+    assert rel_l1(_nchw(cost), cost_ref) < 3e-4
+
+
+@pytest.mark.parametrize("ratio", [2, 4])
+def test_upsample_depth_matches_oracle(ratio):
+    B, H, W = 2, 18, 26
+    n = torch.rand(B, 1, H, W, generator=torch.Generator().manual_seed(1))
+    mask = _rand(B, 9 * ratio * ratio, H, W, seed=2) * 2
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384).view(1, -1).repeat(B, 1)
+    rng = O.DepthRange(dv)
+    up = O.upsample_depth(n, mask, ratio)
+    dep_ref = rng.to_depth(up.unsqueeze(1)).squeeze(1)
+    raw, dep, nrm = ops.upsample_depth(n[:, 0].contiguous().to(DEV), _nhwc(mask), rng.depth_min.view(B).to(DEV),
+                                       rng.depth_max.view(B).to(DEV), ratio, want="raw+depth+norm")
+    _close(raw.cpu(), up, tol=2e-6, what="convex upsample")
+    assert rel_l1(dep, dep_ref) < 1e-6
+    assert rel_l1(nrm, rng.to_norm(dep_ref.unsqueeze(1)).squeeze(1)) < 1e-5
+
+
+def test_refine_update_and_ddim_step():
+    B, H, W = 2, 10, 12
+    dv = torch.linspace(1 / 935.0, 1 / 425.0, 384).view(1, -1).repeat(B, 1)
+    rng = O.DepthRange(dv)
+    inv0 = torch.rand(B, H, W)
+    noise = torch.randn(B, H, W)
+    delta = torch.empty(B, H, W, device=DEV)
+    inv = torch.empty(B, H, W, device=DEV)
+    ubuf = torch.zeros(B, H, W, 8, device=DEV)
+    ops.refine_update(0, inv0.to(DEV), noise.to(DEV), 1, 0.5, delta, inv, ubuf[..., 7:8], 8)
+    ref_inv = (inv0 + 0.5 * noise).clamp(0, 1)
+    assert torch.equal(inv.cpu(), ref_inv) and torch.equal(ubuf[..., 7].cpu(), ref_inv)
+    assert torch.equal(delta.cpu(), ref_inv - inv0)
+    head = torch.randn(B, H, W, 2) * 0.1
+    depth = torch.empty(B, H, W, device=DEV)
+    ops.refine_update(1, inv0.to(DEV), head.to(DEV), 2, 1.0, delta, inv, ubuf[..., 7:8], 8, rng.depth_min.view(B).to(DEV),
+                      rng.depth_max.view(B).to(DEV), depth)
+    ref2 = (inv0 + ((ref_inv - inv0) + head[..., 0])).clamp(0, 1)
+    assert torch.equal(inv.cpu(), ref2)
+    assert rel_l1(depth, rng.to_depth(ref2.unsqueeze(1)).squeeze(1)) < 1e-6
+    img = torch.randn(B, H, W)
+    img_d = img.to(DEV)
+    ops.ddim_step(img_d, delta, noise.to(DEV), 2.0, 1.7, 0.8, 0.3, 0.2, 0.5)
+    dl = delta.cpu()
+    ref3 = dl * 0.8 + 0.3 * ((2.0 * img - dl) / 1.7) + 0.2 * (0.5 * noise)
+    _close(img_d.cpu(), ref3, tol=1e-6, what="ddim step")
+
+
+def test_layout_transposes_roundtrip():
+    x = _rand(2, 5, 7, 9, seed=1)
+    y = ops.to_nhwc(x.to(DEV))
+    assert torch.equal(y.cpu(), x.permute(0, 2, 3, 1))
+    assert torch.equal(ops.to_nchw_dense(y).cpu(), x)
+    assert torch.equal(ops.upsample_nearest(x[:, 0].contiguous().to(DEV), 4).cpu(),
+                       F.interpolate(x[:, :1], scale_factor=4, mode="nearest")[:, 0])
+
+
+def test_cpu_tensors_are_rejected():
+    pc = packing.pack_weight(_rand(4, 4, 3, 3), None)
+    with pytest.raises(ValueError):
+        ops.conv(torch.zeros(1, 8, 8, 4), pc)
