@@ -24,17 +24,64 @@ struct ConvArgs {
   int co_base;     // first output channel of this launch
   int CK;          // input channels staged per chunk (4, 8, 16)
   int CKP;         // padded pixel pitch of the staged tile in floats
+  int ck4_shift;   // log2(CK / 4)
   int in_rows, in_cols;
-  int vec_x, vec_x2;  // 128-bit loads allowed on x / x2
-  int vec_y;          // 128-bit stores allowed on y
-  int Hs, Ws;         // stored size of x (H/2, W/2 when in_up2)
+  int fast_in;     // every staged 4-channel unit is one aligned 16-byte segment and needs no transform
+  int vec_y;       // 128-bit stores allowed on y
+  int Hs, Ws;      // stored size of x (H/2, W/2 when in_up2)
 };
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;  // src-size 0 -> the 16 bytes are zero-filled (conv zero padding)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// One output value through the fused epilogue (kept out of line: it is cold relative to the FMA loop and
+// inlining it four times per quad blows the kernel past the instruction cache).
+__device__ __noinline__ float epilogue_value(const dmvs_conv_desc& d, float x, int c, int64_t opix, int64_t rpix) {
+  if (d.epi == DMVS_EPI_STD) {
+    if (d.res_mode == DMVS_RES_PRE_ACT) x += __ldg(d.res + rpix * d.res_ps + c);
+    if (c >= d.act_c0) x = apply_act(x, d.act);
+    if (d.res_mode == DMVS_RES_POST_ACT) x += __ldg(d.res + rpix * d.res_ps + c);
+  } else if (d.epi == DMVS_EPI_GRU_ZR) {
+    x = sigmoidf_(x);
+    if (c >= d.gru_hidden) x *= __ldg(d.aux1 + opix * d.aux1_ps + (c - d.gru_hidden));
+  } else {  // DMVS_EPI_GRU_Q
+    const float z = __ldg(d.aux1 + opix * d.aux1_ps + c);
+    const float h = __ldg(d.aux2 + opix * d.aux2_ps + c);
+    x = (1.0f - z) * h + z * tanhf(x);
+  }
+  return x;
+}
+
+// GroupNorm(4)+affine of the producer folded to a per-channel (scale, shift) pair for sample n.
+__device__ __noinline__ void groupnorm_affine(const dmvs_conv_desc& d, int n, int c, float* gn_s) {
+  const int g = c / (d.C1 / 4);
+  const double s = d.in_stats[(n * 4 + g) * 2 + 0];
+  const double q = d.in_stats[(n * 4 + g) * 2 + 1];
+  const double mean = s * (double)d.in_inv_count;
+  double var = q * (double)d.in_inv_count - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+  const float g1 = d.in_g1[c] * rstd;
+  gn_s[c] = g1;
+  gn_s[d.C1 + c] = d.in_g0[c] - (float)mean * g1;
+}
+
+// GroupNorm+SiLU applied to one staged input value.
+__device__ __noinline__ float staged_silu(float v, float scale, float shift) { return siluf_(fmaf(v, scale, shift)); }
 
 template <int CO_T, int WC, int PX, int S>
 __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
   constexpr int WP = 8 / WC;           // warps along output rows
   constexpr int TH = WP * PX;          // output rows per CTA
   constexpr int COUT_S = CO_T * WC;    // output channels per CTA
+  constexpr int N4 = COUT_S / 4;       // channel quads per CTA
+  constexpr int OP = COUT_S + 4;       // pitch of the staged output tile (bank-conflict free)
   const dmvs_conv_desc& d = a.d;
 
   extern __shared__ __align__(16) float smem[];
@@ -58,20 +105,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
 
   if (tid < 8) stat_s[tid] = 0.0f;
   if (d.in_stats != nullptr) {
-    // per-channel affine of the producer's GroupNorm (4 groups) for sample n
-    const int cpg = d.C1 / 4;
-    for (int c = tid; c < d.C1; c += kThreads) {
-      const int g = c / cpg;
-      const double s = d.in_stats[(n * 4 + g) * 2 + 0];
-      const double q = d.in_stats[(n * 4 + g) * 2 + 1];
-      const double mean = s * (double)d.in_inv_count;
-      double var = q * (double)d.in_inv_count - mean * mean;
-      var = var < 0.0 ? 0.0 : var;
-      const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-      const float g1 = d.in_g1[c] * rstd;
-      gn_s[c] = g1;
-      gn_s[d.C1 + c] = d.in_g0[c] - (float)mean * g1;
-    }
+    for (int c = tid; c < d.C1; c += kThreads) groupnorm_affine(d, n, c, gn_s);
   }
 
   float acc[PX][CO_T];
@@ -81,9 +115,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
     for (int j = 0; j < CO_T; ++j) acc[p][j] = 0.0f;
 
   const int ck4 = a.CK >> 2;
-  const int in_units = a.in_rows * a.in_cols * ck4;
+  const int units_per_row = a.in_cols << a.ck4_shift;
   const int w_rows = d.KH * d.KW * a.CK;
-  const int w_units = w_rows * (COUT_S / 4);
+  const int w_units = w_rows * N4;
   const int Ctot = d.C1 + d.C2;
 
   for (int kd = 0; kd < d.KD; ++kd) {
@@ -91,68 +125,70 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
     if (id < 0 || id >= d.D) continue;  // zero padding along depth (uniform for the CTA)
     for (int c0 = 0; c0 < a.cin_pad; c0 += a.CK) {
       __syncthreads();  // previous chunk fully consumed (also orders gn_s / stat_s init)
-      // ---- stage the input tile -------------------------------------------------------------
-      for (int idx = tid; idx < in_units; idx += kThreads) {
-        const int c4 = idx % ck4;
-        const int t = idx / ck4;
-        const int col = t % a.in_cols;
-        const int row = t / a.in_cols;
-        const int iy = iy0 + row, ix = ix0 + col;
-        const int ch = c0 + c4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W && ch < Ctot) {
-          const int sy = d.in_up2 ? (iy >> 1) : iy;
+      // ---- stage the input tile: warps take rows, lanes take (column, channel-quad) units ------
+#pragma unroll 1
+      for (int row = warp; row < a.in_rows; row += 8) {
+        const int iy = iy0 + row;
+        const bool row_ok = iy >= 0 && iy < d.H;
+        const int sy = d.in_up2 ? (iy >> 1) : iy;
+        const int64_t row_pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws;
+        float* row_dst = in_s + row * a.in_cols * a.CKP;
+#pragma unroll 1
+        for (int u = lane; u < units_per_row; u += 32) {
+          const int c4 = u & (ck4 - 1);
+          const int col = u >> a.ck4_shift;
+          const int ix = ix0 + col;
+          const int ch = c0 + c4 * 4;
+          const bool ok = row_ok && ix >= 0 && ix < d.W && ch < Ctot;
           const int sx = d.in_up2 ? (ix >> 1) : ix;
-          const int64_t pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws + sx;
-          if (ch + 3 < d.C1 && a.vec_x) {
-            v = ldg4(d.x + pix * d.x_ps + ch);
-          } else if (ch >= d.C1 && ch + 3 < Ctot && a.vec_x2) {
-            v = ldg4(d.x2 + pix * d.x2_ps + (ch - d.C1));
+          const int64_t pix = row_pix + sx;
+          float* dst = row_dst + col * a.CKP + c4 * 4;
+          if (a.fast_in) {
+            const float* src = d.x;
+            if (ok) src = ch < d.C1 ? d.x + pix * d.x_ps + ch : d.x2 + pix * d.x2_ps + (ch - d.C1);
+            cp_async16(dst, src, ok);
           } else {
-            float e[4];
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = ch + k;
-              e[k] = c < d.C1 ? __ldg(d.x + pix * d.x_ps + c)
-                              : (c < Ctot ? __ldg(d.x2 + pix * d.x2_ps + (c - d.C1)) : 0.0f);
+              for (int k = 0; k < 4; ++k) {
+                const int c = ch + k;
+                if (c < d.C1) {
+                  float v = __ldg(d.x + pix * d.x_ps + c);
+                  if (d.in_stats != nullptr) v = staged_silu(v, gn_s[c], gn_s[d.C1 + c]);
+                  e[k] = v;
+                } else if (c < Ctot) {
+                  e[k] = __ldg(d.x2 + pix * d.x2_ps + (c - d.C1));
+                }
+              }
             }
-            v = make_float4(e[0], e[1], e[2], e[3]);
-          }
-          if (d.in_stats != nullptr) {
-            // GroupNorm affine + SiLU of the producer (only defined for the x part, C2 == 0)
-            float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = ch + k;
-              if (c < d.C1) e[k] = siluf_(fmaf(e[k], gn_s[c], gn_s[d.C1 + c]));
-            }
-            v = make_float4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
           }
         }
-        *reinterpret_cast<float4*>(in_s + (row * a.in_cols + col) * a.CKP + c4 * 4) = v;
       }
       // ---- stage the weight slab [KH*KW][CK][COUT_S] ----------------------------------------
+#pragma unroll 1
       for (int idx = tid; idx < w_units; idx += kThreads) {
-        const int j4 = idx % (COUT_S / 4);
-        const int r = idx / (COUT_S / 4);
-        const int ci = r % a.CK;
+        const int j4 = idx % N4;
+        const int r = idx / N4;
+        const int ci = r & (a.CK - 1);
         const int tap = r / a.CK;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + ci < a.cin_pad) {
-          const int64_t off = ((int64_t)((kd * d.KH * d.KW + tap) * a.cin_pad + c0 + ci)) * a.w_cstride +
-                              a.co_base + j4 * 4;
-          v = ldg4(d.w + off);
-        }
-        *reinterpret_cast<float4*>(w_s + r * COUT_S + j4 * 4) = v;
+        const bool ok = c0 + ci < a.cin_pad;
+        const int64_t off = ((int64_t)((kd * d.KH * d.KW + tap) * a.cin_pad + c0 + ci)) * a.w_cstride + a.co_base + j4 * 4;
+        cp_async16(w_s + r * COUT_S + j4 * 4, ok ? d.w + off : d.w, ok);
       }
+      cp_async_wait_all();
       __syncthreads();
       // ---- accumulate -----------------------------------------------------------------------
       const float* in_base = in_s + ((wp * PX * S) * a.in_cols + lane * S) * a.CKP;
       const int row_pitch = S * a.in_cols * a.CKP;
+#pragma unroll 1
       for (int kh = 0; kh < d.KH; ++kh) {
+#pragma unroll 1
         for (int kw = 0; kw < d.KW; ++kw) {
           const float* ip = in_base + (kh * a.in_cols + kw) * a.CKP;
           const float* wt = w_s + ((kh * d.KW + kw) * a.CK) * COUT_S + wc * CO_T;
+#pragma unroll 1
           for (int c4 = 0; c4 < ck4; ++c4) {
             float av[PX][4];
 #pragma unroll
@@ -181,62 +217,73 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
     }
   }
 
-  // ---- epilogue -----------------------------------------------------------------------------
-  const int ox = tx0 + lane;
-  const int cbase = a.co_base + wc * CO_T;  // first absolute output channel of this thread
-  float gsum[4] = {0.f, 0.f, 0.f, 0.f}, gsq[4] = {0.f, 0.f, 0.f, 0.f};
-  const int cpg_out = d.Cout >= 4 ? d.Cout / 4 : 1;
+  // ---- epilogue: accumulators -> shared tile -> compact, fully coalesced write-out ---------------
+  __syncthreads();  // every warp is done with in_s / w_s
+  float* out_s = smem;  // [TH*32][OP]
 #pragma unroll
   for (int p = 0; p < PX; ++p) {
-    const int oy = ty0 + wp * PX + p;
-    if (ox >= d.Wo || oy >= d.Ho) continue;
-    const int64_t opix = ((int64_t)(n * d.Do + od) * d.Ho + oy) * d.Wo + ox;
-    int64_t rpix = opix;
-    if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
-    float out[CO_T];
+    float* op = out_s + ((wp * PX + p) * kTileW + lane) * OP + wc * CO_T;
 #pragma unroll
-    for (int j = 0; j < CO_T; ++j) {
-      const int c = cbase + j;
-      float v = acc[p][j];
-      if (c < d.Cout) {
-        if (d.bias != nullptr) v += __ldg(d.bias + c);
-        if (d.epi == DMVS_EPI_STD) {
-          if (d.res_mode == DMVS_RES_PRE_ACT) v += __ldg(d.res + rpix * d.res_ps + c);
-          if (c >= d.act_c0) v = apply_act(v, d.act);
-          if (d.res_mode == DMVS_RES_POST_ACT) v += __ldg(d.res + rpix * d.res_ps + c);
-        } else if (d.epi == DMVS_EPI_GRU_ZR) {
-          v = sigmoidf_(v);
-          if (c >= d.gru_hidden) v *= __ldg(d.aux1 + opix * d.aux1_ps + (c - d.gru_hidden));
-        } else {  // DMVS_EPI_GRU_Q
-          const float z = __ldg(d.aux1 + opix * d.aux1_ps + c);
-          const float h = __ldg(d.aux2 + opix * d.aux2_ps + c);
-          v = (1.0f - z) * h + z * tanhf(v);
-        }
-        if (d.out_stats != nullptr) {
-          const int g = c / cpg_out;
-          gsum[g] += v;
-          gsq[g] += v * v;
-        }
+    for (int j4 = 0; j4 < CO_T / 4; ++j4)
+      *reinterpret_cast<float4*>(op + j4 * 4) =
+          make_float4(acc[p][j4 * 4], acc[p][j4 * 4 + 1], acc[p][j4 * 4 + 2], acc[p][j4 * 4 + 3]);
+  }
+  __syncthreads();
+
+  const int q4 = tid % N4;                 // this thread always handles the same channel quad
+  const int cq = a.co_base + q4 * 4;       // its first absolute output channel
+  float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cq < d.Cout) {
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (d.bias != nullptr && cq + k < d.Cout) bias[k] = __ldg(d.bias + cq + k);
+    const bool full_quad = cq + 4 <= d.Cout;
+#pragma unroll 1
+    for (int pix = tid / N4; pix < TH * kTileW; pix += kThreads / N4) {
+      const int oy = ty0 + (pix >> 5), ox = tx0 + (pix & 31);
+      if (oy >= d.Ho || ox >= d.Wo) continue;
+      const float4 t4 = *reinterpret_cast<const float4*>(out_s + pix * OP + q4 * 4);
+      float v[4] = {t4.x, t4.y, t4.z, t4.w};
+      const int64_t opix = ((int64_t)(n * d.Do + od) * d.Ho + oy) * d.Wo + ox;
+      int64_t rpix = opix;
+      if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = cq + k;
+        if (c >= d.Cout) continue;
+        const float x = epilogue_value(d, v[k] + bias[k], c, opix, rpix);
+        gs[k] += x;
+        gq[k] += x * x;
+        v[k] = x;
       }
-      out[j] = v;
-    }
-    float* yp = d.y + opix * d.y_ps + cbase;
-    if (a.vec_y && cbase + CO_T <= d.Cout) {
+      float* yp = d.y + opix * d.y_ps + cq;
+      if (a.vec_y && full_quad) {
+        *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
 #pragma unroll
-      for (int j4 = 0; j4 < CO_T / 4; ++j4)
-        *reinterpret_cast<float4*>(yp + j4 * 4) = make_float4(out[j4 * 4], out[j4 * 4 + 1], out[j4 * 4 + 2], out[j4 * 4 + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < CO_T; ++j)
-        if (cbase + j < d.Cout) yp[j] = out[j];
+        for (int k = 0; k < 4; ++k)
+          if (cq + k < d.Cout) yp[k] = v[k];
+      }
     }
   }
   if (d.out_stats != nullptr) {
+    // lanes l, l+N4, l+2*N4, ... of a warp share a channel quad: fold them, then one shared atomic per
+    // (quad, element), then one double atomic per (group, moment) per CTA.
+    const int cpg = d.Cout / 4;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float s = warp_sum(gsum[g]);
-      const float q = warp_sum(gsq[g]);
-      if (lane == 0) {
+    for (int k = 0; k < 4; ++k) {
+      float s = gs[k], q = gq[k];
+      if (N4 < 32) {
+#pragma unroll
+        for (int o = 16; o >= (N4 < 32 ? N4 : 32); o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+      }
+      const int c = cq + k;
+      if (lane < N4 && c < d.Cout) {
+        const int g = c / cpg;
         atomicAdd(&stat_s[g * 2 + 0], s);
         atomicAdd(&stat_s[g * 2 + 1], q);
       }
@@ -321,8 +368,9 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
   a.d = d;
   a.cin_pad = (d.C1 + d.C2 + 3) & ~3;
   a.w_cstride = (d.Cout + 3) & ~3;
-  a.vec_x = aligned16(d.x) && (d.x_ps % 4 == 0) && (d.C1 % 4 == 0);
-  a.vec_x2 = d.C2 > 0 && aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C1 % 4 == 0) && (d.C2 % 4 == 0);
+  const bool vec_x = aligned16(d.x) && (d.x_ps % 4 == 0) && (d.C1 % 4 == 0);
+  const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
+  a.fast_in = vec_x && vec_x2 && d.in_stats == nullptr;
   a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
@@ -348,7 +396,9 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
       for (int c = 16; c >= 4; c >>= 1) {
         if (c > a.cin_pad && c > 4) continue;
         const int ckp = c == 4 ? 4 : c + 4;
-        const size_t need = ((size_t)in_rows * in_cols * ckp + (size_t)d.KH * d.KW * c * chunk + 2 * (size_t)d.C1) * 4;
+        size_t need = ((size_t)in_rows * in_cols * ckp + (size_t)d.KH * d.KW * c * chunk + 2 * (size_t)d.C1) * 4;
+        const size_t out_tile = (size_t)th * kTileW * (chunk + 4) * 4;  // epilogue staging reuses the buffer
+        if (out_tile > need) need = out_tile;
         if (need <= (size_t)kSmemBudget) { ck = c; smem = need; break; }
       }
       if (ck) {
@@ -365,6 +415,7 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     a.co_base = co_base;
     a.CK = ck;
     a.CKP = ck == 4 ? 4 : ck + 4;
+    a.ck4_shift = ck == 4 ? 0 : (ck == 8 ? 1 : 2);
     a.in_rows = (th - 1) * S + d.KH;
     a.in_cols = (kTileW - 1) * S + d.KW;
     dim3 grid(ceil_div(d.Wo, kTileW), ceil_div(d.Ho, th), d.N * d.Do);
