@@ -9,71 +9,12 @@
 //     (bank-conflict free), weights as warp-uniform broadcast vectors;
 //   * GroupNorm+SiLU of the producer layer is applied while staging (no extra pass over HBM), and
 //     the GroupNorm statistics of this layer's output are reduced in the epilogue.
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace dmvs {
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kTileW = 32;
-
-struct ConvArgs {
-  dmvs_conv_desc d;
-  int cin_pad;     // (C1 + C2) rounded up to 4
-  int w_cstride;   // total padded Cout of the packed weight tensor
-  int co_base;     // first output channel of this launch
-  int CK;          // input channels staged per chunk (4, 8, 16)
-  int CKP;         // padded pixel pitch of the staged tile in floats
-  int ck4_shift;   // log2(CK / 4)
-  int in_rows, in_cols;
-  int fast_in;     // every staged 4-channel unit is one aligned 16-byte segment and needs no transform
-  int vec_y;       // 128-bit stores allowed on y
-  int Hs, Ws;      // stored size of x (H/2, W/2 when in_up2)
-};
-
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc, bool valid) {
-  const unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-  const int bytes = valid ? 16 : 0;  // src-size 0 -> the 16 bytes are zero-filled (conv zero padding)
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(gsrc), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
-
-// One output value through the fused epilogue (kept out of line: it is cold relative to the FMA loop and
-// inlining it four times per quad blows the kernel past the instruction cache).
-__device__ __noinline__ float epilogue_value(const dmvs_conv_desc& d, float x, int c, int64_t opix, int64_t rpix) {
-  if (d.epi == DMVS_EPI_STD) {
-    if (d.res_mode == DMVS_RES_PRE_ACT) x += __ldg(d.res + rpix * d.res_ps + c);
-    if (c >= d.act_c0) x = apply_act(x, d.act);
-    if (d.res_mode == DMVS_RES_POST_ACT) x += __ldg(d.res + rpix * d.res_ps + c);
-  } else if (d.epi == DMVS_EPI_GRU_ZR) {
-    x = sigmoidf_(x);
-    if (c >= d.gru_hidden) x *= __ldg(d.aux1 + opix * d.aux1_ps + (c - d.gru_hidden));
-  } else {  // DMVS_EPI_GRU_Q
-    const float z = __ldg(d.aux1 + opix * d.aux1_ps + c);
-    const float h = __ldg(d.aux2 + opix * d.aux2_ps + c);
-    x = (1.0f - z) * h + z * tanhf(x);
-  }
-  return x;
-}
-
-// GroupNorm(4)+affine of the producer folded to a per-channel (scale, shift) pair for sample n.
-__device__ __noinline__ void groupnorm_affine(const dmvs_conv_desc& d, int n, int c, float* gn_s) {
-  const int g = c / (d.C1 / 4);
-  const double s = d.in_stats[(n * 4 + g) * 2 + 0];
-  const double q = d.in_stats[(n * 4 + g) * 2 + 1];
-  const double mean = s * (double)d.in_inv_count;
-  double var = q * (double)d.in_inv_count - mean * mean;
-  var = var < 0.0 ? 0.0 : var;
-  const float rstd = (float)(1.0 / sqrt(var + 1e-5));
-  const float g1 = d.in_g1[c] * rstd;
-  gn_s[c] = g1;
-  gn_s[d.C1 + c] = d.in_g0[c] - (float)mean * g1;
-}
-
-// GroupNorm+SiLU applied to one staged input value.
-__device__ __noinline__ float staged_silu(float v, float scale, float shift) { return siluf_(fmaf(v, scale, shift)); }
+constexpr int kThreads = kConvThreads;
 
 template <int CO_T, int WC, int PX, int S>
 __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
@@ -115,57 +56,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
     for (int j = 0; j < CO_T; ++j) acc[p][j] = 0.0f;
 
   const int ck4 = a.CK >> 2;
-  const int units_per_row = a.in_cols << a.ck4_shift;
   const int w_rows = d.KH * d.KW * a.CK;
   const int w_units = w_rows * N4;
-  const int Ctot = d.C1 + d.C2;
 
   for (int kd = 0; kd < d.KD; ++kd) {
     const int id = od * S + kd - d.pad_d;
     if (id < 0 || id >= d.D) continue;  // zero padding along depth (uniform for the CTA)
     for (int c0 = 0; c0 < a.cin_pad; c0 += a.CK) {
       __syncthreads();  // previous chunk fully consumed (also orders gn_s / stat_s init)
-      // ---- stage the input tile: warps take rows, lanes take (column, channel-quad) units ------
-#pragma unroll 1
-      for (int row = warp; row < a.in_rows; row += 8) {
-        const int iy = iy0 + row;
-        const bool row_ok = iy >= 0 && iy < d.H;
-        const int sy = d.in_up2 ? (iy >> 1) : iy;
-        const int64_t row_pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws;
-        float* row_dst = in_s + row * a.in_cols * a.CKP;
-#pragma unroll 1
-        for (int u = lane; u < units_per_row; u += 32) {
-          const int c4 = u & (ck4 - 1);
-          const int col = u >> a.ck4_shift;
-          const int ix = ix0 + col;
-          const int ch = c0 + c4 * 4;
-          const bool ok = row_ok && ix >= 0 && ix < d.W && ch < Ctot;
-          const int sx = d.in_up2 ? (ix >> 1) : ix;
-          const int64_t pix = row_pix + sx;
-          float* dst = row_dst + col * a.CKP + c4 * 4;
-          if (a.fast_in) {
-            const float* src = d.x;
-            if (ok) src = ch < d.C1 ? d.x + pix * d.x_ps + ch : d.x2 + pix * d.x2_ps + (ch - d.C1);
-            cp_async16(dst, src, ok);
-          } else {
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ok) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = ch + k;
-                if (c < d.C1) {
-                  float v = __ldg(d.x + pix * d.x_ps + c);
-                  if (d.in_stats != nullptr) v = staged_silu(v, gn_s[c], gn_s[d.C1 + c]);
-                  e[k] = v;
-                } else if (c < Ctot) {
-                  e[k] = __ldg(d.x2 + pix * d.x2_ps + (c - d.C1));
-                }
-              }
-            }
-            *reinterpret_cast<float4*>(dst) = make_float4(e[0], e[1], e[2], e[3]);
-          }
-        }
-      }
+      stage_input_tile(a, in_s, gn_s, n, id, iy0, ix0, c0);
       // ---- stage the weight slab [KH*KW][CK][COUT_S] ----------------------------------------
 #pragma unroll 1
       for (int idx = tid; idx < w_units; idx += kThreads) {
@@ -230,80 +129,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
   }
   __syncthreads();
 
-  const int q4 = tid % N4;                 // this thread always handles the same channel quad
-  const int cq = a.co_base + q4 * 4;       // its first absolute output channel
-  float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-  if (cq < d.Cout) {
-    float bias[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (d.bias != nullptr && cq + k < d.Cout) bias[k] = __ldg(d.bias + cq + k);
-    const bool full_quad = cq + 4 <= d.Cout;
-    // Plain epilogues (bias + optional ReLU: > 80 % of all launches) take a branch-free inline path; residuals,
-    // sigmoid/tanh/SiLU and the GRU blends go through the out-of-line generic routine.
-    const bool plain = d.epi == DMVS_EPI_STD && d.res_mode == DMVS_RES_NONE &&
-                       (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
-    const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
-    const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
-#pragma unroll 1
-    for (int pix = tid / N4; pix < TH * kTileW; pix += kThreads / N4) {
-      const int oy = ty0 + (pix >> 5), ox = tx0 + (pix & 31);
-      if (oy >= d.Ho || ox >= d.Wo) continue;
-      const float4 t4 = *reinterpret_cast<const float4*>(out_s + pix * OP + q4 * 4);
-      float v[4] = {t4.x + bias[0], t4.y + bias[1], t4.z + bias[2], t4.w + bias[3]};
-      const int64_t opix = (img_base + oy) * d.Wo + ox;
-      if (plain) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (cq + k >= relu_from) v[k] = fmaxf(v[k], 0.0f);
-      } else {
-        int64_t rpix = opix;
-        if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (cq + k < d.Cout) v[k] = epilogue_value(d, v[k], cq + k, opix, rpix);
-      }
-      if (d.out_stats != nullptr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          gs[k] += v[k];
-          gq[k] += v[k] * v[k];
-        }
-      }
-      float* yp = d.y + opix * d.y_ps + cq;
-      if (a.vec_y && full_quad) {
-        *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (cq + k < d.Cout) yp[k] = v[k];
-      }
-    }
-  }
-  if (d.out_stats != nullptr) {
-    // lanes l, l+N4, l+2*N4, ... of a warp share a channel quad: fold them, then one shared atomic per
-    // (quad, element), then one double atomic per (group, moment) per CTA.
-    const int cpg = d.Cout / 4;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float s = gs[k], q = gq[k];
-      if (N4 < 32) {
-#pragma unroll
-        for (int o = 16; o >= (N4 < 32 ? N4 : 32); o >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-      }
-      const int c = cq + k;
-      if (lane < N4 && c < d.Cout) {
-        const int g = c / cpg;
-        atomicAdd(&stat_s[g * 2 + 0], s);
-        atomicAdd(&stat_s[g * 2 + 1], q);
-      }
-    }
-    __syncthreads();
-    if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
-  }
+  epilogue_tile<TH, COUT_S>(a, out_s, stat_s, n, od, ty0, tx0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,9 +173,6 @@ KernelFn pick_kernel(int chunk, int px, int s, int* co_t, int* wc) {
   }
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-constexpr int kSmemBudget = 100 * 1024;  // two CTAs per SM
 
 }  // namespace
 }  // namespace dmvs
@@ -376,6 +199,11 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
       (d.D + 2 * d.pad_d - d.KD) / d.stride + 1 != d.Do)
     return DMVS_ERR_ARG;
   if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
+  if (d.precision != DMVS_PREC_FP32) {
+    if (d.precision != DMVS_PREC_TF32X3 && d.precision != DMVS_PREC_TF32) return DMVS_ERR_ARG;
+    if (!d.w_t) return DMVS_ERR_ARG;
+    return dispatch_conv_mma(d, static_cast<cudaStream_t>(stream));
+  }
 
   ConvArgs a;
   a.d = d;

@@ -13,8 +13,26 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
+import os
+
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
-                    RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
+                    PREC_FP32, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
+
+# Arithmetic of the convolutions (storage is always fp32):
+#   "tf32x3" (default) tensor cores with hi/lo operand split - fp32-class accuracy (parity-bearing mode)
+#   "fp32"             CUDA-core FFMA kernel
+#   "tf32"             tensor cores, operands rounded to TF32 (torch/cuDNN default numerics; ~5e-4 depth rel-L1)
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+_precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "tf32x3")]
+
+
+def set_precision(name: str) -> None:
+    global _precision
+    _precision = PRECISIONS[name]
+
+
+def get_precision() -> str:
+    return {v: k for k, v in PRECISIONS.items()}[_precision]
 
 Tensor = torch.Tensor
 
@@ -127,10 +145,11 @@ class PackedConv:
     cin: int
     cout: int
     k: Tuple[int, int, int]
+    w_t: Optional[Tensor] = None   # tensor-core layout [KD,KH,KW,cout_pad8,cin_pad8]
 
     def to(self, device) -> "PackedConv":
         return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device), self.cin,
-                          self.cout, self.k)
+                          self.cout, self.k, None if self.w_t is None else self.w_t.to(device))
 
 
 @dataclass
@@ -189,6 +208,8 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         d.in_stats, d.in_g1, d.in_g0 = _ptr(in_gn.stats), _ptr(in_gn.g1), _ptr(in_gn.g0)
         d.in_inv_count = 1.0 / float(D * H * W * (C1 // 4))
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
+    d.w_t = _ptr(pc.w_t)
+    d.precision = _precision if pc.w_t is not None else PREC_FP32
     d.KD, d.KH, d.KW, d.stride = KD, KH, KW, stride
     d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
     d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps

@@ -34,7 +34,10 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedC
     packed = torch.zeros(kd, kh, kw, _pad4(cin), _pad4(cout), dtype=torch.float32)
     packed[:, :, :, :cin, :cout] = w.permute(2, 3, 4, 1, 0)
     b = None if bias is None else bias.detach().float().cpu().contiguous()
-    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw))
+    p8 = lambda n: (n + 7) & ~7
+    w_t = torch.zeros(kd, kh, kw, p8(cout), p8(cin), dtype=torch.float32)   # tensor-core layout, cin contiguous
+    w_t[:, :, :, :cout, :cin] = w.permute(2, 3, 4, 0, 1)
+    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous())
 
 
 def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:

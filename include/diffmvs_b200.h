@@ -43,6 +43,11 @@ extern "C" {
 #define DMVS_RES_PRE_ACT 1  /* y = act(conv + bias + res)   ResidualBlock, module.py:315-319 */
 #define DMVS_RES_POST_ACT 2 /* y = act(conv + bias) + res   CostRegNet skips, module.py:445-446 */
 
+/* arithmetic of dmvs_conv_f32 (storage is always fp32) */
+#define DMVS_PREC_FP32 0   /* CUDA-core FFMA, fp32 products */
+#define DMVS_PREC_TF32X3 1 /* tensor cores, each operand split hi+lo: a*b ~ ah*bh + al*bh + ah*bl (fp32-class) */
+#define DMVS_PREC_TF32 2   /* tensor cores, operands rounded to TF32 (what cuDNN does by torch default) */
+
 /* epilogue kinds */
 #define DMVS_EPI_STD 0
 #define DMVS_EPI_GRU_ZR 1 /* c<hid: z=sigmoid(v); c>=hid: r*h = sigmoid(v)*aux1[c-hid]   module.py:166-168 */
@@ -79,6 +84,9 @@ typedef struct dmvs_conv_desc {
   float in_inv_count;       /* 1 / (elements per (sample, group)) */
   /* weights */
   const float* w;
+  const float* w_t;         /* tensor-core layout [KD][KH][KW][cout_pad8][cin_pad8] (pads to 8, zero filled); may be
+                               NULL when precision == DMVS_PREC_FP32 */
+  int32_t precision;        /* DMVS_PREC_* */
   const float* bias;        /* [Cout] or NULL */
   int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;
   /* output */

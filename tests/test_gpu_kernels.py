@@ -32,6 +32,17 @@ def _nchw(y):  # GPU [N,H,W,C] -> CPU NCHW
     return y.permute(0, 3, 1, 2).contiguous().cpu()
 
 
+PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3}   # max-abs error relative to the output scale
+
+
+@pytest.fixture(params=["fp32", "tf32x3", "tf32"])
+def precision(request):
+    old = ops.get_precision()
+    ops.set_precision(request.param)
+    yield request.param
+    ops.set_precision(old)
+
+
 def _close(got, ref, tol=2e-6, what=""):
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item() + 1e-12
@@ -64,7 +75,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,H,W", CONV_CASES)
-def test_conv2d_matches_torch(cin, cout, k, stride, H, W):
+def test_conv2d_matches_torch(cin, cout, k, stride, H, W, precision):
     N = 2
     x = _rand(N, cin, H, W, seed=1)
     w = _rand(cout, cin, *k, seed=2) * (1.0 / math.sqrt(cin * k[0] * k[1]))
@@ -74,44 +85,47 @@ def test_conv2d_matches_torch(cin, cout, k, stride, H, W):
     pc = packing.pack_weight(w, b).to(DEV)
     y = ops.conv(_nhwc(x), pc, stride=stride, act=ops.ACT_RELU)
     assert tuple(y.shape) == (N, ref.shape[2], ref.shape[3], cout)
-    _close(_nchw(y), ref, what=f"conv {cin}->{cout} k{k} s{stride}")
+    _close(_nchw(y), ref, tol=PREC_TOL[precision], what=f"conv {cin}->{cout} k{k} s{stride} [{precision}]")
 
 
-def test_conv2d_epilogues_and_views():
+def test_conv2d_epilogues_and_views(precision):
+    if precision == "tf32":
+        pytest.skip("epilogue logic is precision independent; covered by fp32 and tf32x3")
     N, H, W = 1, 24, 40
     x1, x2 = _rand(N, 16, H, W, seed=1), _rand(N, 8, H, W, seed=2)
     w, b = _rand(20, 24, 3, 3, seed=3) * 0.1, _rand(20, seed=4)
     res = _rand(N, 20, H, W, seed=5)
     pc = packing.pack_weight(w, b).to(DEV)
     conv = F.conv2d(torch.cat((x1, x2), 1), w, b, padding=1)
+    _c = lambda got, ref, what: _close(got, ref, tol=PREC_TOL[precision], what=what)
     # virtual concat + residual before ReLU (ResidualBlock)
     y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), act=ops.ACT_RELU, res=_nhwc(res), res_mode=ops.RES_PRE_ACT)
-    _close(_nchw(y), F.relu(conv + res), what="concat+res_pre")
+    _c(_nchw(y), F.relu(conv + res), "concat+res_pre")
     # residual after ReLU (CostRegNet skip)
     y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), act=ops.ACT_RELU, res=_nhwc(res), res_mode=ops.RES_POST_ACT)
-    _close(_nchw(y), F.relu(conv) + res, what="res_post")
+    _c(_nchw(y), F.relu(conv) + res, "res_post")
     # activation only from channel 5 on, tanh / sigmoid / silu
     for act, fn in ((ops.ACT_TANH, torch.tanh), (ops.ACT_SIGMOID, torch.sigmoid), (ops.ACT_SILU, F.silu)):
         y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), act=act, act_c0=5)
         ref = conv.clone()
         ref[:, 5:] = fn(conv[:, 5:])
-        _close(_nchw(y), ref, what=f"act {act} from c5")
+        _c(_nchw(y), ref, f"act {act} from c5")
     # channel-sliced input and output inside wider buffers
     wide_in = torch.zeros(N, H, W, 40, device=DEV)
     wide_in[..., 8:24] = _nhwc(x1)
     wide_in[..., 32:40] = _nhwc(x2)
     wide_out = torch.full((N, H, W, 64), 7.0, device=DEV)
     ops.conv(wide_in[..., 8:24], pc, x2=wide_in[..., 32:40], out=wide_out[..., 4:24])
-    _close(_nchw(wide_out[..., 4:24]), conv, what="sliced io")
+    _c(_nchw(wide_out[..., 4:24]), conv, "sliced io")
     assert torch.all(wide_out[..., :4] == 7.0) and torch.all(wide_out[..., 24:] == 7.0)
     # nearest-upsampled residual (FPN lateral, module.py:409-416)
     small = _rand(N, 20, H // 2, W // 2, seed=6)
     y = ops.conv(_nhwc(x1), pc, x2=_nhwc(x2), res=_nhwc(small), res_mode=ops.RES_PRE_ACT, res_up2=True)
-    _close(_nchw(y), conv + F.interpolate(small, scale_factor=2, mode="nearest"), what="res_up2")
+    _c(_nchw(y), conv + F.interpolate(small, scale_factor=2, mode="nearest"), "res_up2")
     # nearest-upsampled input (update.py:38-42)
     xs = _rand(N, 24, H // 2, W // 2, seed=7)
     y = ops.conv(_nhwc(xs), pc, in_up2=True)
-    _close(_nchw(y), F.conv2d(F.interpolate(xs, scale_factor=2, mode="nearest"), w, b, padding=1), what="in_up2")
+    _c(_nchw(y), F.conv2d(F.interpolate(xs, scale_factor=2, mode="nearest"), w, b, padding=1), "in_up2")
 
 
 def test_conv_unshuffle_equals_reference_downsample():
@@ -134,14 +148,14 @@ def test_conv_bn_folding():
 
 
 @pytest.mark.parametrize("cin,cout,stride", [(4, 8, 1), (8, 8, 1), (8, 16, 2), (16, 32, 2), (32, 32, 1), (8, 1, 1)])
-def test_conv3d_matches_torch(cin, cout, stride):
+def test_conv3d_matches_torch(cin, cout, stride, precision):
     N, D, H, W = 2, 8, 12, 20
     x = _rand(N, cin, D, H, W, seed=1)
     w, b = _rand(cout, cin, 3, 3, 3, seed=2) * (1 / math.sqrt(27 * cin)), _rand(cout, seed=3)
     ref = F.relu(F.conv3d(x, w, b, stride=stride, padding=1))
     y = ops.conv(x.permute(0, 2, 3, 4, 1).contiguous().to(DEV), packing.pack_weight(w, b).to(DEV), stride=stride,
                  act=ops.ACT_RELU)
-    _close(y.permute(0, 4, 1, 2, 3).cpu(), ref, what=f"conv3d {cin}->{cout} s{stride}")
+    _close(y.permute(0, 4, 1, 2, 3).cpu(), ref, tol=PREC_TOL[precision], what=f"conv3d {cin}->{cout} s{stride} [{precision}]")
 
 
 @pytest.mark.parametrize("cin,cout", [(32, 16), (16, 8)])
@@ -159,7 +173,9 @@ def test_deconv3d_matches_torch(cin, cout):
     _close(y.permute(0, 4, 1, 2, 3).cpu(), ref, tol=5e-6, what="deconv3d")
 
 
-def test_groupnorm_pipeline_matches_resnet_block():
+def test_groupnorm_pipeline_matches_resnet_block(precision):
+    if precision == "tf32":
+        pytest.skip("covered by fp32 and tf32x3")
     """conv(+stats) -> conv(GN+SiLU prologue, +stats) -> groupnorm_silu_add == oracle resnet_block."""
     from diffmvs_b200 import pipeline
     dim_in, dim_out, H, W, N = 24, 16, 20, 28, 2
@@ -177,8 +193,8 @@ def test_groupnorm_pipeline_matches_resnet_block():
     arena = pipeline.StatsArena(DEV, N, 2)
     xg = _nhwc(x)
     y = plan(xg[..., :16], arena, x2=xg[..., 16:])
-    assert rel_l1(_nchw(y), ref) < 2e-6
-    _close(_nchw(y), ref, tol=2e-5, what="resnet block")
+    assert rel_l1(_nchw(y), ref) < 5e-6
+    _close(_nchw(y), ref, tol=3e-5, what="resnet block")
 
 
 def test_gru_matches_oracle():

@@ -25,7 +25,10 @@ LAYERS = [
     ("unet 32->32 @1/8", 1, 32, 32, 3, 1, 144, 200),
     ("mask3 16->64", 1, 16, 64, 3, 1, 576, 800),
 ]
-only = sys.argv[1] if len(sys.argv) > 1 else None
+only = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] != "all" else None
+if len(sys.argv) > 2:
+    ops.set_precision(sys.argv[2])
+print("precision:", ops.get_precision())
 print(f"{'layer':28s} {'ms':>8s} {'TFLOP/s':>8s} {'GB/s(io)':>9s}")
 for name, N, cin, cout, k, s, H, W in LAYERS:
     if only and only not in name:
