@@ -17,7 +17,7 @@ namespace {
 constexpr int kThreads = kConvThreads;
 
 template <int CO_T, int WC, int PX, int S>
-__global__ void __launch_bounds__(kThreads, 2) conv_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int WP = 8 / WC;           // warps along output rows
   constexpr int TH = WP * PX;          // output rows per CTA
   constexpr int COUT_S = CO_T * WC;    // output channels per CTA

@@ -28,7 +28,7 @@ __device__ __forceinline__ void ldmatrix_x2(unsigned (&r)[2], const float* smem_
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -41,9 +41,20 @@ __device__ __forceinline__ void split_tf32(unsigned x, unsigned& hi, unsigned& l
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(lo) : "f"(rest));
 }
 
-// NT = n8 tiles per warp, WC = warps along output channels, PX = output rows per warp, S = stride
-template <int NT, int WC, int PX, int S>
-__global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const ConvArgs a) {
+// One pipeline stage = one (output tile, depth tap kd, input-channel chunk c0).
+struct Stage {
+  int tile, kd, c0;
+};
+
+// NT = n8 tiles per warp, WC = warps along output channels, PX = output rows per warp, S = stride,
+// PASSES = 1 (TF32) or 3 (3xTF32).
+//
+// Persistent CTAs walk the output tiles round-robin; the cp.async loads of stage s+1 (input halo tile and
+// weight slab, double-buffered in shared memory) are in flight while the tensor cores work on stage s and
+// while the epilogue of a finished tile streams out - loads, math and stores of one SM overlap without
+// relying on a second resident CTA.
+template <int NT, int WC, int PX, int S, int PASSES>
+__global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int WP = 8 / WC;
   constexpr int TH = WP * PX;
   constexpr int COUT_S = NT * 8 * WC;
@@ -51,21 +62,88 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const ConvArg
   const dmvs_conv_desc& d = a.d;
 
   extern __shared__ __align__(16) float smem[];
-  float* in_s = smem;                                          // [in_rows][in_cols][CKP]
-  float* w_s = in_s + a.in_rows * a.in_cols * a.CKP;           // [KH*KW][COUT_S][CKP]
-  float* gn_s = w_s + d.KH * d.KW * COUT_S * a.CKP;            // [2][C1] when in_stats
+  const int in_sz = a.in_rows * a.in_cols * a.CKP;          // floats per input buffer
+  const int w_sz = d.KH * d.KW * COUT_S * a.CKP;            // floats per weight buffer
+  float* in_s0 = smem;                                      // [2][in_rows][in_cols][CKP]
+  float* w_s0 = in_s0 + 2 * in_sz;                          // [2][KH*KW][COUT_S][CKP]
+  float* out_s = w_s0 + 2 * w_sz;                           // [TH*32][OP]
+  float* gn_s = out_s + TH * kTileW * OP;                   // [2][C1] when in_stats
   __shared__ float stat_s[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wc = warp % WC, wp = warp / WC;
-  const int n = blockIdx.z / d.Do;
-  const int od = blockIdx.z - n * d.Do;
-  const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * kTileW;
-  const int iy0 = ty0 * S - d.pad_h, ix0 = tx0 * S - d.pad_w;
+  const int tiles_x = ceil_div(d.Wo, kTileW), tiles_y = ceil_div(d.Ho, TH);
+  const int total_tiles = tiles_x * tiles_y * d.N * d.Do;
 
-  if (tid < 8) stat_s[tid] = 0.0f;
-  if (d.in_stats != nullptr)
-    for (int c = tid; c < d.C1; c += kConvThreads) groupnorm_affine(d, n, c, gn_s);
+  // ldmatrix source rows of this lane.  A: matrices (rows 0-7,k0-3) (rows 8-15,k0-3) (rows 0-7,k4-7) (rows 8-15,k4-7)
+  const int lm = lane >> 3, lr = lane & 7;
+  const int a_row = lr + (lm & 1) * 8;       // pixel within the m16 tile
+  const int a_kofs = (lm >> 1) * 4;          // channel offset within the k8 step
+  // B (x4): matrices (tile j,k0-3) (tile j,k4-7) (tile j+1,k0-3) (tile j+1,k4-7); (x2): first two only
+  const int b_n = (lm >> 1) * 8 + lr;
+  const int b_kofs = (lm & 1) * 4;
+  const int ck4 = a.CK >> 2;
+  const int w_units = d.KH * d.KW * COUT_S * ck4;   // 16-byte units of the weight slab
+  const int ksteps = a.CK >> 3;
+  const int row_pitch = S * a.in_cols * a.CKP;
+
+  auto decode = [&](int tile, int& n, int& od, int& ty0, int& tx0) {
+    const int tx = tile % tiles_x;
+    const int r = tile / tiles_x;
+    const int ty = r % tiles_y;
+    const int z = r / tiles_y;
+    n = z / d.Do;
+    od = z - n * d.Do;
+    ty0 = ty * TH;
+    tx0 = tx * kTileW;
+  };
+  auto kd_first = [&](int od) { const int v = d.pad_d - od * S; return v > 0 ? v : 0; };
+  auto kd_last = [&](int od) { const int v = d.D - 1 + d.pad_d - od * S; return v < d.KD - 1 ? v : d.KD - 1; };
+  auto first_stage = [&](int tile) {
+    Stage s{tile, 0, 0};
+    if (tile < total_tiles) {
+      int n, od, ty0, tx0;
+      decode(tile, n, od, ty0, tx0);
+      s.kd = kd_first(od);
+    }
+    return s;
+  };
+  auto advance = [&](const Stage& c) {
+    Stage s = c;
+    s.c0 += a.CK;
+    if (s.c0 < a.cin_pad) return s;
+    s.c0 = 0;
+    int n, od, ty0, tx0;
+    decode(c.tile, n, od, ty0, tx0);
+    if (++s.kd <= kd_last(od)) return s;
+    return first_stage(c.tile + (int)gridDim.x);
+  };
+  int gn_n = -1;
+  auto issue = [&](const Stage& s, int buf) {
+    int n, od, ty0, tx0;
+    decode(s.tile, n, od, ty0, tx0);
+    if (d.in_stats != nullptr && n != gn_n) {   // GroupNorm affine of the producer is per sample
+      __syncthreads();
+      for (int c = tid; c < d.C1; c += kConvThreads) groupnorm_affine(d, n, c, gn_s);
+      __syncthreads();
+      gn_n = n;
+    }
+    const int id = od * S + s.kd - d.pad_d;
+    stage_input_tile(a, in_s0 + buf * in_sz, gn_s, n, id, ty0 * S - d.pad_h, tx0 * S - d.pad_w, s.c0);
+    float* w_s = w_s0 + buf * w_sz;   // global [kd][tap][cout_pad8][cin_pad8] -> shared [tap][COUT_S][CKP]
+#pragma unroll 1
+    for (int idx = tid; idx < w_units; idx += kConvThreads) {
+      const int c4 = idx & (ck4 - 1);
+      const int r = idx >> a.ck4_shift;            // tap * COUT_S + co
+      const int co = r % COUT_S;
+      const int tap = r / COUT_S;
+      const bool ok = s.c0 + c4 * 4 < a.cin_pad;
+      const int64_t off =
+          ((int64_t)(s.kd * d.KH * d.KW + tap) * a.w_cstride + a.co_base + co) * a.cin_pad + s.c0 + c4 * 4;
+      cp_async16(w_s + r * a.CKP + c4 * 4, ok ? d.w_t + off : d.w_t, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
 
   float acc[PX][2][NT][4];
 #pragma unroll
@@ -77,41 +155,25 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const ConvArg
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[p][mt][j][e] = 0.0f;
 
-  // ldmatrix source rows of this lane.  A: matrices (rows 0-7,k0-3) (rows 8-15,k0-3) (rows 0-7,k4-7) (rows 8-15,k4-7)
-  const int lm = lane >> 3, lr = lane & 7;
-  const int a_row = lr + (lm & 1) * 8;       // pixel within the m16 tile
-  const int a_kofs = (lm >> 1) * 4;          // channel offset within the k8 step
-  // B (x4): matrices (tile j,k0-3) (tile j,k4-7) (tile j+1,k0-3) (tile j+1,k4-7); (x2): first two only
-  const int b_n = (lm >> 1) * 8 + lr;
-  const int b_kofs = (lm & 1) * 4;
+  Stage cur = first_stage((int)blockIdx.x);
+  if (cur.tile >= total_tiles) return;
+  int buf = 0;
+  issue(cur, 0);
+  for (;;) {
+    const Stage nxt = advance(cur);
+    const bool has_next = nxt.tile < total_tiles;
+    if (has_next) {
+      issue(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");   // everything but the newest group has landed
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncthreads();
 
-  const int ck4 = a.CK >> 2;
-  const int w_units = d.KH * d.KW * COUT_S * ck4;   // 16-byte units of the weight slab
-
-  for (int kd = 0; kd < d.KD; ++kd) {
-    const int id = od * S + kd - d.pad_d;
-    if (id < 0 || id >= d.D) continue;
-    for (int c0 = 0; c0 < a.cin_pad; c0 += a.CK) {
-      __syncthreads();
-      stage_input_tile(a, in_s, gn_s, n, id, iy0, ix0, c0);
-      // weight slab: global [kd][tap][cout_pad8][cin_pad8] -> shared [tap][COUT_S][CKP]
-#pragma unroll 1
-      for (int idx = tid; idx < w_units; idx += kConvThreads) {
-        const int c4 = idx & (ck4 - 1);
-        const int r = idx >> a.ck4_shift;            // tap * COUT_S + co
-        const int co = r % COUT_S;
-        const int tap = r / COUT_S;
-        const bool ok = c0 + c4 * 4 < a.cin_pad;
-        const int64_t off = ((int64_t)(kd * d.KH * d.KW + tap) * a.w_cstride + a.co_base + co) * a.cin_pad + c0 + c4 * 4;
-        cp_async16(w_s + r * a.CKP + c4 * 4, ok ? d.w_t + off : d.w_t, ok);
-      }
-      cp_async_wait_all();
-      __syncthreads();
-
-      const float* a_base = in_s + ((wp * PX * S) * a.in_cols + a_row * S) * a.CKP + a_kofs;
-      const float* b_base = w_s + (wc * NT * 8 + b_n) * a.CKP + b_kofs;
-      const int row_pitch = S * a.in_cols * a.CKP;
-      const int ksteps = a.CK >> 3;
+    // ---- tensor-core math on stage `cur` -----------------------------------------------------------
+    {
+      const float* a_base = in_s0 + buf * in_sz + ((wp * PX * S) * a.in_cols + a_row * S) * a.CKP + a_kofs;
+      const float* b_base = w_s0 + buf * w_sz + (wc * NT * 8 + b_n) * a.CKP + b_kofs;
 #pragma unroll 1
       for (int kh = 0; kh < d.KH; ++kh) {
 #pragma unroll 1
@@ -120,7 +182,6 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const ConvArg
           const float* bp = b_base + ((kh * d.KW + kw) * COUT_S) * a.CKP;
 #pragma unroll 1
           for (int ks = 0; ks < ksteps; ++ks) {
-            // ---- B fragments of all NT tiles (hi / lo) ----
             unsigned bh[NT][2], bl[NT][2];
 #pragma unroll
             for (int j = 0; j < NT; j += 2) {
@@ -134,72 +195,99 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const ConvArg
                 bh[j][0] = r2[0]; bh[j][1] = r2[1];
               }
             }
-            if (a.passes == 3) {
+            if (PASSES == 3) {
 #pragma unroll
               for (int j = 0; j < NT; ++j) {
                 split_tf32(bh[j][0], bh[j][0], bl[j][0]);
                 split_tf32(bh[j][1], bh[j][1], bl[j][1]);
               }
             }
-            // ---- A fragments per (row, m16 tile), then the MMAs ----
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
+              // both m16 tiles of the row are loaded up front so their MMA chains interleave
+              unsigned ah[2][4];
+              ldmatrix_x4(ah[0], ap + p * row_pitch + ks * 8);
+              ldmatrix_x4(ah[1], ap + p * row_pitch + 16 * S * a.CKP + ks * 8);
+              if (PASSES == 3) {
+                unsigned al[2][4];
 #pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                unsigned ah[4];
-                ldmatrix_x4(ah, ap + p * row_pitch + mt * 16 * S * a.CKP + ks * 8);
-                if (a.passes == 3) {
-                  unsigned al[4];
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) split_tf32(ah[e], ah[e], al[e]);
-                  // The tensor core adds into its accumulator with truncation; chaining hundreds of k-steps
-                  // through it biases long reductions (7x7x64: ~2e-5).  So each k8 step is formed from a zero
-                  // accumulator and folded into the running sum with a round-to-nearest FADD.
+                  for (int e = 0; e < 4; ++e) split_tf32(ah[mt][e], ah[mt][e], al[mt][e]);
+                // The tensor core adds into its accumulator with truncation; chaining hundreds of k-steps
+                // through it biases long reductions (7x7x64: ~2e-5).  Each k8 step is therefore formed from a
+                // zero accumulator and folded into the running sum with a round-to-nearest FADD.
+                float t4[2][NT][4];
 #pragma unroll
-                  for (int j = 0; j < NT; ++j) {
-                    float t4[4] = {0.f, 0.f, 0.f, 0.f};
-                    mma_tf32(t4, al, bh[j][0], bh[j][1]);
-                    mma_tf32(t4, ah, bl[j][0], bl[j][1]);
-                    mma_tf32(t4, ah, bh[j][0], bh[j][1]);
+                for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[p][mt][j][e] += t4[e];
-                  }
-                } else {
+                  for (int j = 0; j < NT; ++j)
 #pragma unroll
-                  for (int j = 0; j < NT; ++j) mma_tf32(acc[p][mt][j], ah, bh[j][0], bh[j][1]);
-                }
+                    for (int e = 0; e < 4; ++e) t4[mt][j][e] = 0.0f;
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int j = 0; j < NT; ++j) mma_tf32(t4[mt][j], al[mt], bh[j][0], bh[j][1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int j = 0; j < NT; ++j) mma_tf32(t4[mt][j], ah[mt], bl[j][0], bl[j][1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int j = 0; j < NT; ++j) mma_tf32(t4[mt][j], ah[mt], bh[j][0], bh[j][1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int j = 0; j < NT; ++j)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[p][mt][j][e] += t4[mt][j][e];
+              } else {
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                  for (int j = 0; j < NT; ++j) mma_tf32(acc[p][mt][j], ah[mt], bh[j][0], bh[j][1]);
               }
             }
           }
         }
       }
     }
-  }
 
-  // ---- accumulators -> shared output tile -> shared epilogue -------------------------------------
-  __syncthreads();
-  float* out_s = smem;  // [TH*32][OP]
-  const int g = lane >> 2, t = lane & 3;   // C fragment: rows g / g+8, columns 2t, 2t+1
+    // ---- tile finished: accumulators -> shared output tile -> fused epilogue --------------------------
+    if (!has_next || nxt.tile != cur.tile) {
+      int n, od, ty0, tx0;
+      decode(cur.tile, n, od, ty0, tx0);
+      const int g = lane >> 2, t = lane & 3;   // C fragment: rows g / g+8, columns 2t, 2t+1
 #pragma unroll
-  for (int p = 0; p < PX; ++p)
+      for (int p = 0; p < PX; ++p)
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        float* o = out_s + ((wp * PX + p) * kTileW + mt * 16 + g) * OP + (wc * NT + j) * 8 + 2 * t;
-        *reinterpret_cast<float2*>(o) = make_float2(acc[p][mt][j][0], acc[p][mt][j][1]);
-        *reinterpret_cast<float2*>(o + 8 * OP) = make_float2(acc[p][mt][j][2], acc[p][mt][j][3]);
-      }
-  __syncthreads();
-  epilogue_tile<TH, COUT_S>(a, out_s, stat_s, n, od, ty0, tx0);
+          for (int j = 0; j < NT; ++j) {
+            float* o = out_s + ((wp * PX + p) * kTileW + mt * 16 + g) * OP + (wc * NT + j) * 8 + 2 * t;
+            *reinterpret_cast<float2*>(o) = make_float2(acc[p][mt][j][0], acc[p][mt][j][1]);
+            *reinterpret_cast<float2*>(o + 8 * OP) = make_float2(acc[p][mt][j][2], acc[p][mt][j][3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[p][mt][j][e] = 0.0f;
+          }
+      if (tid < 8) stat_s[tid] = 0.0f;
+      __syncthreads();
+      epilogue_tile<TH, COUT_S>(a, out_s, stat_s, n, od, ty0, tx0);
+    }
+    __syncthreads();   // every warp is done with this stage's buffers (and out_s) before they are refilled
+    if (!has_next) break;
+    cur = nxt;
+    buf ^= 1;
+  }
 }
 
 using KernelFn = void (*)(const ConvArgs);
 
-template <int NT, int WC, int PX, int S>
+template <int NT, int WC, int PX, int S, int PASSES>
 KernelFn get_kernel() {
   static bool configured = false;
-  KernelFn fn = conv_mma_kernel<NT, WC, PX, S>;
+  KernelFn fn = conv_mma_kernel<NT, WC, PX, S, PASSES>;
   if (!configured) {
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     configured = true;
@@ -207,17 +295,17 @@ KernelFn get_kernel() {
   return fn;
 }
 
-template <int NT, int WC, int MAXPX>
+template <int NT, int WC, int MAXPX, int PASSES>
 KernelFn pick_px(int px, int s) {
   if (px > MAXPX) px = MAXPX;
   if (s == 1) {
-    if (px >= 4) { if constexpr (MAXPX >= 4) return get_kernel<NT, WC, 4, 1>(); }
-    if (px >= 2) return get_kernel<NT, WC, 2, 1>();
-    return get_kernel<NT, WC, 1, 1>();
+    if (px >= 4) { if constexpr (MAXPX >= 4) return get_kernel<NT, WC, 4, 1, PASSES>(); }
+    if (px >= 2) return get_kernel<NT, WC, 2, 1, PASSES>();
+    return get_kernel<NT, WC, 1, 1, PASSES>();
   }
-  if (px >= 4) { if constexpr (MAXPX >= 4) return get_kernel<NT, WC, 4, 2>(); }
-  if (px >= 2) return get_kernel<NT, WC, 2, 2>();
-  return get_kernel<NT, WC, 1, 2>();
+  if (px >= 4) { if constexpr (MAXPX >= 4) return get_kernel<NT, WC, 4, 2, PASSES>(); }
+  if (px >= 2) return get_kernel<NT, WC, 2, 2, PASSES>();
+  return get_kernel<NT, WC, 1, 2, PASSES>();
 }
 
 struct Config { int wc, max_px; };
@@ -230,14 +318,18 @@ Config config_of(int chunk) {
     default: return {4, 2};
   }
 }
-KernelFn pick_kernel(int chunk, int px, int s) {
+template <int PASSES>
+KernelFn pick_kernel_p(int chunk, int px, int s) {
   switch (chunk) {
-    case 8: return pick_px<1, 1, 4>(px, s);
-    case 16: return pick_px<2, 1, 4>(px, s);
-    case 32: return pick_px<4, 1, 2>(px, s);
-    case 64: return pick_px<4, 2, 2>(px, s);
-    default: return pick_px<4, 4, 2>(px, s);
+    case 8: return pick_px<1, 1, 4, PASSES>(px, s);
+    case 16: return pick_px<2, 1, 4, PASSES>(px, s);
+    case 32: return pick_px<4, 1, 2, PASSES>(px, s);
+    case 64: return pick_px<4, 2, 2, PASSES>(px, s);
+    default: return pick_px<4, 4, 2, PASSES>(px, s);
   }
+}
+KernelFn pick_kernel(int chunk, int px, int s, int passes) {
+  return passes == 3 ? pick_kernel_p<3>(chunk, px, s) : pick_kernel_p<1>(chunk, px, s);
 }
 
 }  // namespace
@@ -277,9 +369,9 @@ int dispatch_conv_mma(const dmvs_conv_desc& d, cudaStream_t st) {
           for (int c = 16; c >= 8; c >>= 1) {
             if (c > a.cin_pad) continue;
             const int ckp = c + 4;
-            size_t need = ((size_t)in_rows * in_cols * ckp + (size_t)d.KH * d.KW * chunk * ckp + 2 * (size_t)d.C1) * 4;
-            const size_t out_tile = (size_t)th * kTileW * (chunk + 4) * 4;
-            if (out_tile > need) need = out_tile;
+            // double-buffered input tile + weight slab, output tile, GroupNorm affine
+            const size_t need = (2 * ((size_t)in_rows * in_cols * ckp + (size_t)d.KH * d.KW * chunk * ckp) +
+                                 (size_t)th * kTileW * (chunk + 4) + 2 * (size_t)d.C1) * 4;
             if (need <= budget) { ck = c; smem = need; break; }
           }
           if (ck) {
@@ -293,7 +385,7 @@ int dispatch_conv_mma(const dmvs_conv_desc& d, cudaStream_t st) {
     }
     if (!ck) return DMVS_ERR_UNSUPPORTED;
     if (px < 1) px = 1;
-    KernelFn fn = pick_kernel(chunk, px, S);
+    KernelFn fn = pick_kernel(chunk, px, S, a.passes);
     const int th = (8 / cfg.wc) * px;
     a.co_base = co_base;
     a.CK = ck;
@@ -301,8 +393,10 @@ int dispatch_conv_mma(const dmvs_conv_desc& d, cudaStream_t st) {
     a.ck4_shift = ck == 8 ? 1 : 2;
     a.in_rows = (th - 1) * S + d.KH;
     a.in_cols = (kTileW - 1) * S + d.KW;
-    dim3 grid(ceil_div(d.Wo, kTileW), ceil_div(d.Ho, th), d.N * d.Do);
-    if (grid.y > 65535 || grid.z > 65535) return DMVS_ERR_UNSUPPORTED;
+    const long tiles = (long)ceil_div(d.Wo, kTileW) * ceil_div(d.Ho, th) * d.N * d.Do;
+    if (tiles > 0x7fffffffL) return DMVS_ERR_UNSUPPORTED;
+    const int ctas_per_sm = smem <= (size_t)kSmemBudget ? 2 : 1;
+    const int grid = (int)(tiles < (long)kNumSMs * ctas_per_sm ? tiles : (long)kNumSMs * ctas_per_sm);
     fn<<<grid, kConvThreads, smem, st>>>(a);
     const int rc = launch_status();
     if (rc) return rc;
