@@ -19,11 +19,11 @@ from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU
                     PREC_FP32, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
 # Arithmetic of the convolutions (storage is always fp32):
-#   "tf32x3" (default) tensor cores with hi/lo operand split - fp32-class accuracy (parity-bearing mode)
-#   "fp32"             CUDA-core FFMA kernel
+#   "tf32x3"           tensor cores with hi/lo operand split - fp32-class accuracy
+#   "fp32"   (default) CUDA-core FFMA kernel (currently the fastest fp32-class back end)
 #   "tf32"             tensor cores, operands rounded to TF32 (torch/cuDNN default numerics; ~5e-4 depth rel-L1)
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
-_precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "tf32x3")]
+_precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "fp32")]
 
 
 def set_precision(name: str) -> None:

@@ -177,6 +177,41 @@ def test_full_size_against_oracle_on_device(workload, monkeypatch):
         assert e < 1e-3, (i, e)
     assert tuple(out["depth"][-1].shape) == (1, imgs[0].shape[2], imgs[0].shape[3])
 
+@pytest.mark.parametrize("mode,tol", [("tf32x3", DEPTH_TOL), ("tf32", 1e-3)])
+@pytest.mark.parametrize("workload", ["cas_small", "cfg2"])
+def test_tensor_core_modes_meet_the_parity_bar(workload, mode, tol, monkeypatch):
+    """The tensor-core convolution modes against the CPU oracle: "tf32x3" (operand split) must stay in the
+    fp32 class; plain "tf32" (torch/cuDNN default numerics) must stay inside the north_star bar of 1e-3."""
+    from diffmvs_b200 import ops
+    args = synth.workload_args(workload)
+    sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
+    imgs, proj, dv = synth.workload_inputs(workload, seed=2)
+
+    def mk():
+        gen = torch.Generator().manual_seed(13)
+        return lambda like: torch.randn(like.shape, generator=gen, dtype=torch.float32)
+
+    taps_ref = {}
+    with torch.no_grad():
+        ref = O.casdiffmvs_forward(sd, args, imgs, proj, dv, randn=mk(), taps=taps_ref)
+    model = _build(args, sd)
+    _patch_noise(monkeypatch, mk())
+    old = ops.get_precision()
+    ops.set_precision(mode)
+    try:
+        taps = {}
+        with torch.no_grad():
+            out = model.plan(DEV).forward(*_to_dev(imgs, proj, dv), taps=taps)
+    finally:
+        ops.set_precision(old)
+    mism = (taps["stage1_floor"].cpu().long() != taps_ref["stage1_floor"][:, 0]).float().mean().item()
+    REPORT.append((workload, f"[{mode}] stage1 floor-index mismatch rate", mism))
+    for i, (d, r) in enumerate(zip(out["depth"], ref["depth"])):
+        e = rel_l1(d, r)
+        REPORT.append((workload, f"[{mode}] depth[{i}]", e))
+        assert e < tol, (workload, mode, i, e)
+
+
 
 def test_zz_report():
     """Prints the collected parity numbers (kept in gpurun_out/ when run on the GPU box)."""
