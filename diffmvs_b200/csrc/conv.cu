@@ -200,7 +200,14 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     return DMVS_ERR_ARG;
   if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
   if (d.precision != DMVS_PREC_FP32) {
-    if (d.precision != DMVS_PREC_TF32X3 && d.precision != DMVS_PREC_TF32) return DMVS_ERR_ARG;
+    if (d.precision < DMVS_PREC_FP32 || d.precision > DMVS_PREC_TC_TF32) return DMVS_ERR_ARG;
+    if (d.precision >= DMVS_PREC_TC_TF32X3) {
+      if (conv_tc_supported(d)) return dispatch_conv_tc(d, static_cast<cudaStream_t>(stream));
+      dmvs_conv_desc alt = d;   // strided layers: legacy tensor-core path with the same arithmetic
+      alt.precision = d.precision == DMVS_PREC_TC_TF32X3 ? DMVS_PREC_TF32X3 : DMVS_PREC_TF32;
+      if (!alt.w_t) return DMVS_ERR_ARG;
+      return dispatch_conv_mma(alt, static_cast<cudaStream_t>(stream));
+    }
     if (!d.w_t) return DMVS_ERR_ARG;
     return dispatch_conv_mma(d, static_cast<cudaStream_t>(stream));
   }

@@ -207,5 +207,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* ou
 
 // tensor-core back end (conv_mma.cu); returns 0 / DMVS_ERR_* / cudaError
 int dispatch_conv_mma(const dmvs_conv_desc& d, cudaStream_t stream);
+// tcgen05 / TMEM back end (conv_tc.cu)
+bool conv_tc_supported(const dmvs_conv_desc& d);
+int dispatch_conv_tc(const dmvs_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmvs

@@ -16,13 +16,14 @@ from . import _cabi
 import os
 
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
-                    PREC_FP32, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
+                    PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
 # Arithmetic of the convolutions (storage is always fp32):
 #   "tf32x3"           tensor cores with hi/lo operand split - fp32-class accuracy
 #   "fp32"   (default) CUDA-core FFMA kernel (currently the fastest fp32-class back end)
 #   "tf32"             tensor cores, operands rounded to TF32 (torch/cuDNN default numerics; ~5e-4 depth rel-L1)
-PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
+              "tc_tf32": PREC_TC_TF32}
 _precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "fp32")]
 
 
@@ -146,10 +147,12 @@ class PackedConv:
     cout: int
     k: Tuple[int, int, int]
     w_t: Optional[Tensor] = None   # tensor-core layout [KD,KH,KW,cout_pad8,cin_pad8]
+    w_tc: Optional[Tensor] = None  # tcgen05 layout [2(hi,lo),KD,KH*KW,cin_pad8/4,cout_pad16,4]
 
     def to(self, device) -> "PackedConv":
         return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device), self.cin,
-                          self.cout, self.k, None if self.w_t is None else self.w_t.to(device))
+                          self.cout, self.k, None if self.w_t is None else self.w_t.to(device),
+                          None if self.w_tc is None else self.w_tc.to(device))
 
 
 @dataclass
@@ -208,8 +211,10 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         d.in_stats, d.in_g1, d.in_g0 = _ptr(in_gn.stats), _ptr(in_gn.g1), _ptr(in_gn.g0)
         d.in_inv_count = 1.0 / float(D * H * W * (C1 // 4))
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
-    d.w_t = _ptr(pc.w_t)
+    d.w_t, d.w_tc = _ptr(pc.w_t), _ptr(pc.w_tc)
     d.precision = _precision if pc.w_t is not None else PREC_FP32
+    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32) and pc.w_tc is None:
+        d.precision = PREC_TF32X3 if d.precision == PREC_TC_TF32X3 else PREC_TF32
     d.KD, d.KH, d.KW, d.stride = KD, KH, KW, stride
     d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
     d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps

@@ -25,6 +25,13 @@ def _pad4(n: int) -> int:
     return (n + 3) & ~3
 
 
+def rna_tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to TF32 (10-bit mantissa), nearest with ties away from zero - bit-identical to PTX
+    `cvt.rna.tf32.f32` for finite values."""
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
 def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedConv:
     """w [Cout,Cin,KH,KW] or [Cout,Cin,KD,KH,KW] -> PackedConv ([KD,KH,KW,cin_pad,cout_pad])."""
     w = w.detach().float().cpu()
@@ -37,7 +44,15 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedC
     p8 = lambda n: (n + 7) & ~7
     w_t = torch.zeros(kd, kh, kw, p8(cout), p8(cin), dtype=torch.float32)   # tensor-core layout, cin contiguous
     w_t[:, :, :, :cout, :cin] = w.permute(2, 3, 4, 0, 1)
-    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous())
+    # tcgen05 layout: hi/lo TF32 planes, [2][KD][KH*KW][cin_pad8/4][cout_pad16][4] (input-channel quad innermost)
+    ci8, co16 = p8(cin), (cout + 15) & ~15
+    full = torch.zeros(kd, kh * kw, ci8, co16, dtype=torch.float32)
+    full[:, :, :cin, :cout] = w.permute(2, 3, 4, 1, 0).reshape(kd, kh * kw, cin, cout)
+    quad = full.view(kd, kh * kw, ci8 // 4, 4, co16).permute(0, 1, 2, 4, 3).contiguous()
+    hi = rna_tf32(quad)
+    lo = rna_tf32(quad - hi)
+    w_tc = torch.stack((hi, lo), 0).contiguous()
+    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc)
 
 
 def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:

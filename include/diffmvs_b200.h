@@ -47,6 +47,8 @@ extern "C" {
 #define DMVS_PREC_FP32 0   /* CUDA-core FFMA, fp32 products */
 #define DMVS_PREC_TF32X3 1 /* tensor cores, each operand split hi+lo: a*b ~ ah*bh + al*bh + ah*bl (fp32-class) */
 #define DMVS_PREC_TF32 2   /* tensor cores, operands rounded to TF32 (what cuDNN does by torch default) */
+#define DMVS_PREC_TC_TF32X3 3 /* as TF32X3 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 1) */
+#define DMVS_PREC_TC_TF32 4   /* as TF32 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 2) */
 
 /* epilogue kinds */
 #define DMVS_EPI_STD 0
@@ -86,6 +88,8 @@ typedef struct dmvs_conv_desc {
   const float* w;
   const float* w_t;         /* tensor-core layout [KD][KH][KW][cout_pad8][cin_pad8] (pads to 8, zero filled); may be
                                NULL when precision == DMVS_PREC_FP32 */
+  const float* w_tc;        /* tcgen05 layout: two planes (hi = rna_tf32(w), lo = rna_tf32(w - hi)), each
+                               [KD][KH*KW][cin_pad8/4][cout_pad16][4]; may be NULL unless precision is DMVS_PREC_TC_* */
   int32_t precision;        /* DMVS_PREC_* */
   const float* bias;        /* [Cout] or NULL */
   int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;

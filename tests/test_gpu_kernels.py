@@ -32,10 +32,10 @@ def _nchw(y):  # GPU [N,H,W,C] -> CPU NCHW
     return y.permute(0, 3, 1, 2).contiguous().cpu()
 
 
-PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3}   # max-abs error relative to the output scale
+PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3, "tc_tf32x3": 2e-5, "tc_tf32": 3e-3}   # max-abs error relative to the output scale
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32"])
+@pytest.fixture(params=["fp32", "tf32x3", "tf32", "tc_tf32x3", "tc_tf32"])
 def precision(request):
     old = ops.get_precision()
     ops.set_precision(request.param)
@@ -89,8 +89,8 @@ def test_conv2d_matches_torch(cin, cout, k, stride, H, W, precision):
 
 
 def test_conv2d_epilogues_and_views(precision):
-    if precision == "tf32":
-        pytest.skip("epilogue logic is precision independent; covered by fp32 and tf32x3")
+    if precision in ("tf32", "tc_tf32"):
+        pytest.skip("epilogue logic is precision independent; covered by the fp32-class modes")
     N, H, W = 1, 24, 40
     x1, x2 = _rand(N, 16, H, W, seed=1), _rand(N, 8, H, W, seed=2)
     w, b = _rand(20, 24, 3, 3, seed=3) * 0.1, _rand(20, seed=4)
@@ -174,8 +174,8 @@ def test_deconv3d_matches_torch(cin, cout):
 
 
 def test_groupnorm_pipeline_matches_resnet_block(precision):
-    if precision == "tf32":
-        pytest.skip("covered by fp32 and tf32x3")
+    if precision in ("tf32", "tc_tf32"):
+        pytest.skip("covered by the fp32-class modes")
     """conv(+stats) -> conv(GN+SiLU prologue, +stats) -> groupnorm_silu_add == oracle resnet_block."""
     from diffmvs_b200 import pipeline
     dim_in, dim_out, H, W, N = 24, 16, 20, 28, 2
