@@ -18,12 +18,14 @@
 //     epilogue with the other's MMAs.  Accumulators leave TMEM through tcgen05.ld into a small shared staging
 //     buffer and the common fused epilogue (bias, residual, activation, GRU blends, GroupNorm statistics,
 //     coalesced 128-bit stores).
+#include <cstdlib>
+
 #include "conv_common.cuh"
 
 namespace dmvs {
 namespace {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;   // warps 0-3 also own the 128 TMEM lanes in the epilogue
 
 struct TcArgs {
   dmvs_conv_desc d;
@@ -53,11 +55,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return v;
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, bool accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
-      "l"(da), "l"(db), "r"(idesc), "r"((uint32_t)accumulate)
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -80,18 +82,21 @@ __device__ __forceinline__ float rna_tf32(float x) {
 
 // N = output channels per CTA (16, 32, 64), PASSES = 1 (TF32) or 3 (3xTF32)
 template <int N, int PASSES>
-__global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   constexpr int OP = N + 4;   // pitch of the epilogue staging rows
   const dmvs_conv_desc& d = a.d;
   extern __shared__ __align__(128) float smem[];
   const int quads = a.CK >> 2;
   const int taps = d.KH * d.KW;
-  float* a_hi = smem;                                         // [quads][plane][4]
-  float* a_lo = a_hi + (PASSES == 3 ? quads * a.plane * 4 : 0);
-  float* w_hi = a_lo + quads * a.plane * 4;                    // [taps][quads][N][4]
-  float* w_lo = w_hi + (PASSES == 3 ? taps * quads * N * 4 : 0);
-  float* gn_s = w_lo + taps * quads * N * 4;                   // [2][C1] when in_stats
-  float* out_s = smem;                                         // [128][OP], aliases a_hi after the MMAs retire
+  const int plane_f = quads * a.plane * 4;                    // floats per operand plane set
+  const int wslab_f = taps * quads * N * 4;                   // floats per weight slab
+  float* a_raw = smem;                                        // [quads][plane][4]  cp.async landing buffer
+  float* a_hi = a_raw + plane_f;                              // split operands read by the tensor core
+  float* a_lo = a_hi + plane_f;
+  float* w_hi0 = a_lo + (PASSES == 3 ? plane_f : 0);          // [2 buffers][taps][quads][N][4]
+  float* w_lo0 = w_hi0 + 2 * wslab_f;
+  float* gn_s = w_lo0 + (PASSES == 3 ? 2 * wslab_f : 0);      // [2][C1] when in_stats
+  float* out_s = a_raw;                                       // [128][OP] epilogue staging (operands are dead by then)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t mbar;
   __shared__ float stat_s[8];
@@ -122,82 +127,92 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
   const int Ctot = d.C1 + d.C2;
   const int units_per_row = a.in_cols * quads;   // 16-byte units per tile row
 
-  uint32_t parity = 0;
-  bool first_stage = true;
-  for (int kd = 0; kd < d.KD; ++kd) {
+  // stage list: every valid depth tap kd x every channel chunk c0
+  const int kd_lo = (d.pad_d - od) > 0 ? (d.pad_d - od) : 0;
+  const int kd_hi = (d.D - 1 + d.pad_d - od) < (d.KD - 1) ? (d.D - 1 + d.pad_d - od) : (d.KD - 1);
+  const int nchunks = ceil_div(a.cin_pad, a.CK);
+  const int nstages = (kd_hi - kd_lo + 1) * nchunks;
+
+  // loads of one stage: halo tile (planar by channel quad) -> a_raw, weights -> w_*[buf]
+  auto issue_loads = [&](int s) {
+    const int kd = kd_lo + s / nchunks;
+    const int c0 = (s % nchunks) * a.CK;
     const int id = od + kd - d.pad_d;
-    if (id < 0 || id >= d.D) continue;
-    for (int c0 = 0; c0 < a.cin_pad; c0 += a.CK) {
-      if (!first_stage) {   // the single operand buffer is free once the previous stage's MMAs have retired
-        mbar_wait(&mbar, parity);
-        parity ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      }
-      // ---- stage the halo tile, planar by channel quad -------------------------------------------------
 #pragma unroll 1
-      for (int row = warp; row < a.in_rows; row += kTcThreads / 32) {
-        const int iy = iy0 + row;
-        const bool row_ok = iy >= 0 && iy < d.H;
-        const int sy = d.in_up2 ? (iy >> 1) : iy;
-        const int64_t row_pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws;
+    for (int row = warp; row < a.in_rows; row += kTcThreads / 32) {
+      const int iy = iy0 + row;
+      const bool row_ok = iy >= 0 && iy < d.H;
+      const int sy = d.in_up2 ? (iy >> 1) : iy;
+      const int64_t row_pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws;
 #pragma unroll 1
-        for (int u = lane; u < units_per_row; u += 32) {
-          const int q = u % quads;
-          const int col = u / quads;
-          const int ix = ix0 + col;
-          const int ch = c0 + q * 4;
-          const bool ok = row_ok && ix >= 0 && ix < d.W && ch < Ctot;
-          const int sx = d.in_up2 ? (ix >> 1) : ix;
-          const int64_t pix = row_pix + sx;
-          const int off = (q * a.plane + row * a.in_cols + col) * 4;
-          if (a.fast_in) {
-            const float* src = d.x;
-            if (ok) src = ch < d.C1 ? d.x + pix * d.x_ps + ch : d.x2 + pix * d.x2_ps + (ch - d.C1);
-            cp_async16(a_hi + off, src, ok);
-          } else {
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ok) {
+      for (int u = lane; u < units_per_row; u += 32) {
+        const int q = u % quads;
+        const int col = u / quads;
+        const int ix = ix0 + col;
+        const int ch = c0 + q * 4;
+        const bool ok = row_ok && ix >= 0 && ix < d.W && ch < Ctot;
+        const int sx = d.in_up2 ? (ix >> 1) : ix;
+        const int64_t pix = row_pix + sx;
+        const int off = (q * a.plane + row * a.in_cols + col) * 4;
+        if (a.fast_in) {
+          const float* src = d.x;
+          if (ok) src = ch < d.C1 ? d.x + pix * d.x_ps + ch : d.x2 + pix * d.x2_ps + (ch - d.C1);
+          cp_async16(a_raw + off, src, ok);
+        } else {
+          float e[4] = {0.f, 0.f, 0.f, 0.f};
+          if (ok) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = ch + k;
-                if (c < d.C1) {
-                  float v = __ldg(d.x + pix * d.x_ps + c);
-                  if (d.in_stats != nullptr) v = staged_silu(v, gn_s[c], gn_s[d.C1 + c]);
-                  e[k] = v;
-                } else if (c < Ctot) {
-                  e[k] = __ldg(d.x2 + pix * d.x2_ps + (c - d.C1));
-                }
+            for (int k = 0; k < 4; ++k) {
+              const int c = ch + k;
+              if (c < d.C1) {
+                float v = __ldg(d.x + pix * d.x_ps + c);
+                if (d.in_stats != nullptr) v = staged_silu(v, gn_s[c], gn_s[d.C1 + c]);
+                e[k] = v;
+              } else if (c < Ctot) {
+                e[k] = __ldg(d.x2 + pix * d.x2_ps + (c - d.C1));
               }
             }
-            *reinterpret_cast<float4*>(a_hi + off) = make_float4(e[0], e[1], e[2], e[3]);
           }
+          *reinterpret_cast<float4*>(a_raw + off) = make_float4(e[0], e[1], e[2], e[3]);
         }
       }
-      // ---- weights of this (kd, channel chunk): global [kd][tap][quad][cout_pad][4] -> [tap][quad][N][4] ----
-      {
-        const int q0 = c0 >> 2;
-        const int qtot = a.cin_pad >> 2;
-        const int w_units = taps * quads * N;
+    }
+    // weights of this (kd, channel chunk): global [kd][tap][quad][cout_pad][4] -> [tap][quad][N][4]
+    const int q0 = c0 >> 2;
+    const int qtot = a.cin_pad >> 2;
+    float* wh = w_hi0 + (s & 1) * wslab_f;
+    float* wl = w_lo0 + (s & 1) * wslab_f;
 #pragma unroll 1
-        for (int idx = tid; idx < w_units; idx += kTcThreads) {
-          const int nn = idx % N;
-          const int r = idx / N;
-          const int q = r % quads;
-          const int tap = r / quads;
-          const bool ok = q0 + q < qtot;
-          const int64_t off = ((((int64_t)kd * taps + tap) * qtot + q0 + q) * a.cout_pad + a.co_base + nn) * 4;
-          cp_async16(w_hi + idx * 4, ok ? d.w_tc + off : d.w_tc, ok);
-          if (PASSES == 3) cp_async16(w_lo + idx * 4, ok ? d.w_tc + a.w_lo_off + off : d.w_tc, ok);
-        }
-      }
-      cp_async_wait_all();
-      __syncthreads();
-      // ---- split once per stage: x -> (hi, lo) planes -------------------------------------------------------
-      if (PASSES == 3) {
-        const int total = quads * a.plane;   // float4 units (slack included: harmless)
+    for (int idx = tid; idx < taps * quads * N; idx += kTcThreads) {
+      const int nn = idx % N;
+      const int r = idx / N;
+      const int q = r % quads;
+      const int tap = r / quads;
+      const bool ok = q0 + q < qtot;
+      const int64_t off = ((((int64_t)kd * taps + tap) * qtot + q0 + q) * a.cout_pad + a.co_base + nn) * 4;
+      cp_async16(wh + idx * 4, ok ? d.w_tc + off : d.w_tc, ok);
+      if (PASSES == 3) cp_async16(wl + idx * 4, ok ? d.w_tc + a.w_lo_off + off : d.w_tc, ok);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+
+  uint32_t parity = 0;
+  issue_loads(0);
+  for (int s = 0; s < nstages; ++s) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();                                   // a_raw and w[s&1] of stage s are visible to every thread
+    if (s > 0) {                                       // MMAs of stage s-1 retired: a_hi / a_lo / w[(s+1)&1] are free
+      mbar_wait(&mbar, parity);
+      parity ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    }
+    // ---- split once per stage: raw -> (hi, lo) operand planes (slack included: harmless) ----------------
+    {
+      const int total = quads * a.plane;
 #pragma unroll 1
-        for (int u = tid; u < total; u += kTcThreads) {
-          const float4 v = *reinterpret_cast<const float4*>(a_hi + u * 4);
+      for (int u = tid; u < total; u += kTcThreads) {
+        const float4 v = *reinterpret_cast<const float4*>(a_raw + u * 4);
+        if (PASSES == 3) {
           float4 h, l;
           h.x = rna_tf32(v.x); l.x = rna_tf32(v.x - h.x);
           h.y = rna_tf32(v.y); l.y = rna_tf32(v.y - h.y);
@@ -205,47 +220,51 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
           h.w = rna_tf32(v.w); l.w = rna_tf32(v.w - h.w);
           *reinterpret_cast<float4*>(a_hi + u * 4) = h;
           *reinterpret_cast<float4*>(a_lo + u * 4) = l;
+        } else {
+          *reinterpret_cast<float4*>(a_hi + u * 4) = v;
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      __syncthreads();
-      // ---- one thread issues every MMA of the stage -------------------------------------------------------
-      if (tid == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo), w_hi_u = smem_u32(w_hi), w_lo_u = smem_u32(w_lo);
-        const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
-        const int ksteps = a.CK >> 3;
-        for (int blk = 0; blk < a.n_blk; ++blk) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(blk * N);
-          bool acc = !first_stage;
-          for (int kh = 0; kh < d.KH; ++kh)
-            for (int kw = 0; kw < d.KW; ++kw) {
-              const uint32_t shift = (uint32_t)(blk * 128 + kh * a.in_cols + kw) * 16u;
-              const int tap = kh * d.KW + kw;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t aoff = (uint32_t)(2 * ks) * lbo_a + shift;
-                const uint32_t boff = (uint32_t)((tap * quads + 2 * ks) * N) * 16u;
-                const uint64_t dah = umma_desc(a_hi_u + aoff, lbo_a, 128);
-                const uint64_t dbh = umma_desc(w_hi_u + boff, lbo_b, 128);
-                if (PASSES == 3) {
-                  const uint64_t dal = umma_desc(a_lo_u + aoff, lbo_a, 128);
-                  const uint64_t dbl = umma_desc(w_lo_u + boff, lbo_b, 128);
-                  umma_tf32(d_tmem, dal, dbh, idesc, acc);
-                  umma_tf32(d_tmem, dah, dbl, idesc, true);
-                  umma_tf32(d_tmem, dah, dbh, idesc, true);
-                } else {
-                  umma_tf32(d_tmem, dah, dbh, idesc, acc);
-                }
-                acc = true;
-              }
-            }
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar))
-                     : "memory");
-      }
-      first_stage = false;
     }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();                                   // operands complete; a_raw may be refilled
+    // ---- one thread issues every MMA of the stage; the next stage's loads go out meanwhile ----------------
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      // Descriptors differ only in their 14-bit start-address field (units of 16 bytes), so they are formed
+      // once per stage and advanced with integer adds; the loop below is ~5 instructions per MMA.
+      const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
+      const uint64_t dah0 = umma_desc(smem_u32(a_hi), lbo_a, 128), dal0 = umma_desc(smem_u32(a_lo), lbo_a, 128);
+      const uint64_t dbh0 = umma_desc(smem_u32(w_hi0 + (s & 1) * wslab_f), lbo_b, 128);
+      const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + (s & 1) * wslab_f), lbo_b, 128);
+      const int ksteps = a.CK >> 3;
+      const uint32_t a_kstep = 2u * (uint32_t)a.plane;        // two channel-quad planes per K=8 step (16-byte units)
+      const uint32_t b_kstep = 2u * (uint32_t)N;
+      for (int blk = 0; blk < a.n_blk; ++blk) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(blk * N);
+        uint32_t acc = s == 0 ? 0u : 1u;
+        uint32_t b_off = 0;                                     // advances by one (tap, kstep) at a time
+        for (int kh = 0; kh < d.KH; ++kh) {
+          uint32_t a_off = (uint32_t)(blk * 128 + kh * a.in_cols);
+          for (int kw = 0; kw < d.KW; ++kw, ++a_off) {
+            uint32_t a_k = a_off;
+            for (int ks = 0; ks < ksteps; ++ks, a_k += a_kstep, b_off += b_kstep) {
+              if (PASSES == 3) {
+                umma_tf32(d_tmem, dal0 + a_k, dbh0 + b_off, idesc, acc);
+                umma_tf32(d_tmem, dah0 + a_k, dbl0 + b_off, idesc, 1u);
+                umma_tf32(d_tmem, dah0 + a_k, dbh0 + b_off, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, dah0 + a_k, dbh0 + b_off, idesc, acc);
+              }
+              acc = 1u;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar))
+                   : "memory");
+    }
+    if (s + 1 < nstages) issue_loads(s + 1);
   }
   // ---- all MMAs retired -> accumulators out of TMEM, block by block -----------------------------------------
   mbar_wait(&mbar, parity);
@@ -265,8 +284,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
   float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
 
   for (int blk = 0; blk < a.n_blk; ++blk) {
-    // TMEM lane = flattened position within the block; this warp owns lanes [32*warp, 32*warp+32)
+    // TMEM lane = flattened position within the block; warp w < 4 owns lanes [32w, 32w+32)
     float* orow = out_s + tid * OP;
+    if (warp < 4) {
 #pragma unroll
     for (int c0 = 0; c0 < N; c0 += 16) {
       uint32_t r[16];
@@ -282,6 +302,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) conv_tc_kernel(const __grid_con
         *reinterpret_cast<float4*>(orow + c0 + j4 * 4) =
             make_float4(__uint_as_float(r[j4 * 4]), __uint_as_float(r[j4 * 4 + 1]), __uint_as_float(r[j4 * 4 + 2]),
                         __uint_as_float(r[j4 * 4 + 3]));
+    }
     }
     __syncthreads();
     // cooperative, coalesced write-out of the 128 positions of this block
@@ -358,7 +379,7 @@ KernelFn get_kernel() {
   static bool configured = false;
   KernelFn fn = conv_tc_kernel<N, PASSES>;
   if (!configured) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     configured = true;
   }
   return fn;
@@ -403,10 +424,12 @@ int dispatch_conv_tc(const dmvs_conv_desc& d, cudaStream_t st) {
     size_t smem = 0;
     // prefer two CTAs per SM (100 KB each); large-kernel layers (7x7) may take one CTA with up to 200 KB
     // (tall tiles first: a 1-row tile of a 7x7 layer would re-read its input seven times)
+    static const int force_th = getenv("DMVS_TC_TH") ? atoi(getenv("DMVS_TC_TH")) : 0;   // tuning aid
     for (int pass = 0; pass < 4 && !CK; ++pass)
     for (int th = (pass < 2 ? 8 : 2); th >= (pass < 2 ? 4 : 1) && !CK; th >>= 1) {
-      const size_t budget = (pass & 1) ? 2 * (size_t)kSmemBudget : (size_t)kSmemBudget;
+      const size_t budget = (pass & 1) ? 216 * (size_t)1024 : (size_t)kSmemBudget;
       if (th > d.Ho && th > 1) continue;
+      if (force_th && th != force_th && pass < 3) continue;
       const int m_total = (th - 1) * in_cols + TW;
       const int nb = ceil_div(m_total, 128);
       if (nb * N > 256) continue;
@@ -414,8 +437,9 @@ int dispatch_conv_tc(const dmvs_conv_desc& d, cudaStream_t st) {
       for (int ck = 16; ck >= 8; ck >>= 1) {
         if (ck > a.cin_pad) continue;
         const int quads = ck / 4;
-        size_t need = ((size_t)(passes == 3 ? 2 : 1) * quads * pl * 4 +
-                       (size_t)(passes == 3 ? 2 : 1) * d.KH * d.KW * quads * N * 4 + 2 * (size_t)d.C1) * 4;
+        // raw landing buffer + hi (+ lo) operand planes, double-buffered hi (+ lo) weight slabs, GroupNorm affine
+        size_t need = ((size_t)(passes == 3 ? 3 : 2) * quads * pl * 4 +
+                       (size_t)(passes == 3 ? 4 : 2) * d.KH * d.KW * quads * N * 4 + 2 * (size_t)d.C1) * 4;
         const size_t stage = (size_t)128 * (N + 4) * 4;
         if (stage > need) need = stage;
         if (need <= budget) { TH = th; CK = ck; n_blk = nb; plane = pl; smem = need; break; }
