@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_PKG, "lib", "libdiffmvs_b200.so")
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4
 RES_NONE, RES_PRE_ACT, RES_POST_ACT = 0, 1, 2
 EPI_STD, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
-PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_TC_TF32X3, PREC_TC_TF32 = 0, 1, 2, 3, 4
+PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_TC_TF32X3, PREC_TC_TF32, PREC_AUTO = 0, 1, 2, 3, 4, 5
 
 f32p = C.c_void_p
 i32 = C.c_int32

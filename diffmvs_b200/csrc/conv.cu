@@ -199,7 +199,15 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
       (d.D + 2 * d.pad_d - d.KD) / d.stride + 1 != d.Do)
     return DMVS_ERR_ARG;
   if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
-  if (d.precision != DMVS_PREC_FP32) {
+  if (d.precision == DMVS_PREC_AUTO) {
+    // fp32-class arithmetic, back end chosen per layer: the tcgen05 kernel wins where one MMA instruction carries
+    // enough work (>= 32 output channels per CTA), the FFMA kernel elsewhere (profiles/r1_conv_backends.txt)
+    if (d.w_tc && conv_tc_supported(d) && d.Cout >= 24) {
+      dmvs_conv_desc alt = d;
+      alt.precision = DMVS_PREC_TC_TF32X3;
+      return dispatch_conv_tc(alt, static_cast<cudaStream_t>(stream));
+    }
+  } else if (d.precision != DMVS_PREC_FP32) {
     if (d.precision < DMVS_PREC_FP32 || d.precision > DMVS_PREC_TC_TF32) return DMVS_ERR_ARG;
     if (d.precision >= DMVS_PREC_TC_TF32X3) {
       if (conv_tc_supported(d)) return dispatch_conv_tc(d, static_cast<cudaStream_t>(stream));

@@ -16,14 +16,14 @@ from . import _cabi
 import os
 
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
-                    PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
+                    PREC_AUTO, PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
 # Arithmetic of the convolutions (storage is always fp32):
 #   "tf32x3"           tensor cores with hi/lo operand split - fp32-class accuracy
 #   "fp32"   (default) CUDA-core FFMA kernel (currently the fastest fp32-class back end)
 #   "tf32"             tensor cores, operands rounded to TF32 (torch/cuDNN default numerics; ~5e-4 depth rel-L1)
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
-              "tc_tf32": PREC_TC_TF32}
+              "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO}
 _precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "fp32")]
 
 

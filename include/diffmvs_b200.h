@@ -48,6 +48,7 @@ extern "C" {
 #define DMVS_PREC_TF32X3 1 /* tensor cores, each operand split hi+lo: a*b ~ ah*bh + al*bh + ah*bl (fp32-class) */
 #define DMVS_PREC_TF32 2   /* tensor cores, operands rounded to TF32 (what cuDNN does by torch default) */
 #define DMVS_PREC_TC_TF32X3 3 /* as TF32X3 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 1) */
+#define DMVS_PREC_AUTO 5      /* fp32-class; per layer: tcgen05 3xTF32 where it is faster, FFMA elsewhere */
 #define DMVS_PREC_TC_TF32 4   /* as TF32 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 2) */
 
 /* epilogue kinds */

@@ -45,16 +45,19 @@ def test_feature_and_context_nets_match_oracle():
     net.load_state_dict(fsd)
     out = net.to(DEV).eval()(imgs[1].to(DEV))
     ref = O.feature_net(sd, "feature", imgs[1], True)
+    from diffmvs_b200 import ops
+    # FFMA (default) agrees to ~1e-7; the tcgen05 modes accumulate in TMEM (truncating adder): ~2e-6
+    tol = 5e-6 if ops.get_precision() in ("fp32", "tf32x3") else 3e-5
     for k in ref:
         assert out[k].shape == ref[k].shape
-        assert rel_l1(out[k], ref[k]) < 5e-6, k
+        assert rel_l1(out[k], ref[k]) < tol, k
     csd = {k[len("context."):]: v for k, v in sd.items() if k.startswith("context.")}
     cnet = ContextNet([32, 64, 36])
     cnet.load_state_dict(csd)
     cout = cnet.to(DEV).eval()(imgs[0].to(DEV))
     cref = O.context_net(sd, "context", imgs[0], True)
     for k in cref:
-        assert rel_l1(cout[k], cref[k]) < 5e-6, k
+        assert rel_l1(cout[k], cref[k]) < tol, k
 
 
 def test_training_mode_and_cpu_are_refused():
