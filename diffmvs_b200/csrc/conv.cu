@@ -16,6 +16,19 @@ namespace {
 
 constexpr int kThreads = kConvThreads;
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// c = a * b + c on both fp32 halves (two independent round-to-nearest FMAs)
+__device__ __forceinline__ void fma2(unsigned long long& c, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+
 template <int CO_T, int WC, int PX, int S>
 __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant__ ConvArgs a) {
   constexpr int WP = 8 / WC;           // warps along output rows
@@ -49,11 +62,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant
     for (int c = tid; c < d.C1; c += kThreads) groupnorm_affine(d, n, c, gn_s);
   }
 
-  float acc[PX][CO_T];
+  // Accumulators are kept as packed fp32x2 pairs {c(2k), c(2k+1)}: Blackwell's FFMA2 (`fma.rn.f32x2`) retires two
+  // IEEE fp32 FMAs per issue slot (same 74 TFLOP/s peak as FFMA, half the instructions -
+  // tools/probes/ffma2_probe.cu), which is what this issue-bound loop needs.
+  unsigned long long acc2[PX][CO_T / 2];
 #pragma unroll
   for (int p = 0; p < PX; ++p)
 #pragma unroll
-    for (int j = 0; j < CO_T; ++j) acc[p][j] = 0.0f;
+    for (int j = 0; j < CO_T / 2; ++j) acc2[p][j] = 0ull;
 
   const int ck4 = a.CK >> 2;
   const int w_rows = d.KH * d.KW * a.CK;
@@ -98,15 +114,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
               const float* wr = wt + (c4 * 4 + ci) * COUT_S;
+              unsigned long long aa[PX];   // {a, a}
+#pragma unroll
+              for (int p = 0; p < PX; ++p) aa[p] = pack2(av[p][ci], av[p][ci]);
 #pragma unroll
               for (int j4 = 0; j4 < CO_T / 4; ++j4) {
                 const float4 wv = *reinterpret_cast<const float4*>(wr + j4 * 4);
+                const unsigned long long w01 = pack2(wv.x, wv.y), w23 = pack2(wv.z, wv.w);
 #pragma unroll
                 for (int p = 0; p < PX; ++p) {
-                  acc[p][j4 * 4 + 0] = fmaf(av[p][ci], wv.x, acc[p][j4 * 4 + 0]);
-                  acc[p][j4 * 4 + 1] = fmaf(av[p][ci], wv.y, acc[p][j4 * 4 + 1]);
-                  acc[p][j4 * 4 + 2] = fmaf(av[p][ci], wv.z, acc[p][j4 * 4 + 2]);
-                  acc[p][j4 * 4 + 3] = fmaf(av[p][ci], wv.w, acc[p][j4 * 4 + 3]);
+                  fma2(acc2[p][j4 * 2 + 0], aa[p], w01);
+                  fma2(acc2[p][j4 * 2 + 1], aa[p], w23);
                 }
               }
             }
@@ -123,9 +141,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant
   for (int p = 0; p < PX; ++p) {
     float* op = out_s + ((wp * PX + p) * kTileW + lane) * OP + wc * CO_T;
 #pragma unroll
-    for (int j4 = 0; j4 < CO_T / 4; ++j4)
-      *reinterpret_cast<float4*>(op + j4 * 4) =
-          make_float4(acc[p][j4 * 4], acc[p][j4 * 4 + 1], acc[p][j4 * 4 + 2], acc[p][j4 * 4 + 3]);
+    for (int j4 = 0; j4 < CO_T / 4; ++j4) {
+      float c0, c1, c2, c3;
+      unpack2(acc2[p][j4 * 2 + 0], c0, c1);
+      unpack2(acc2[p][j4 * 2 + 1], c2, c3);
+      *reinterpret_cast<float4*>(op + j4 * 4) = make_float4(c0, c1, c2, c3);
+    }
   }
   __syncthreads();
 
