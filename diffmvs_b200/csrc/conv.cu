@@ -249,6 +249,7 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
   const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
   a.fast_in = vec_x && vec_x2 && d.in_stats == nullptr;
   a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
+  a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
 

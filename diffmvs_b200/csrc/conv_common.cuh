@@ -21,6 +21,7 @@ struct ConvArgs {
   int in_rows, in_cols;
   int fast_in;     // every staged 4-channel unit is one aligned 16-byte segment and needs no transform
   int vec_y;       // 128-bit stores allowed on y
+  int vec_res;     // 128-bit loads allowed on the residual
   int Hs, Ws;      // stored size of x (H/2, W/2 when in_up2)
   int passes;      // MMA only: 1 = plain TF32, 3 = 3xTF32 split (fp32-class accuracy)
 };
@@ -142,8 +143,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* ou
     const bool full_quad = cq + 4 <= d.Cout;
     // Plain epilogues (bias + optional ReLU: > 80 % of all launches) take a branch-free inline path; residuals,
     // sigmoid/tanh/SiLU and the GRU blends go through the out-of-line generic routine.
-    const bool plain = d.epi == DMVS_EPI_STD && d.res_mode == DMVS_RES_NONE &&
-                       (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
+    const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
     const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
     const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
 #pragma unroll 1
@@ -153,13 +153,29 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* ou
       const float4 t4 = *reinterpret_cast<const float4*>(out_s + pix * OP + q4 * 4);
       float v[4] = {t4.x + bias[0], t4.y + bias[1], t4.z + bias[2], t4.w + bias[3]};
       const int64_t opix = (img_base + oy) * d.Wo + ox;
-      if (plain) {
+      int64_t rpix = opix;
+      if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+      if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+        float r[4] = {0.f, 0.f, 0.f, 0.f};
+        if (d.res_mode != DMVS_RES_NONE) {
+          const float* rp = d.res + rpix * d.res_ps + cq;
+          if (a.vec_res && full_quad) {
+            const float4 r4 = ldg4(rp);
+            r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+          } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (cq + k >= relu_from) v[k] = fmaxf(v[k], 0.0f);
+            for (int k = 0; k < 4; ++k)
+              if (cq + k < d.Cout) r[k] = __ldg(rp + k);
+          }
+        }
+        const bool pre = d.res_mode == DMVS_RES_PRE_ACT;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float x = pre ? v[k] + r[k] : v[k];
+          if (cq + k >= relu_from) x = fmaxf(x, 0.0f);
+          v[k] = pre ? x : x + r[k];
+        }
       } else {
-        int64_t rpix = opix;
-        if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (cq + k < d.Cout) v[k] = epilogue_value(d, v[k], cq + k, opix, rpix);

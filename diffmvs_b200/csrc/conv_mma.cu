@@ -344,6 +344,7 @@ int dispatch_conv_mma(const dmvs_conv_desc& d, cudaStream_t st) {
   const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
   a.fast_in = vec_x && vec_x2 && d.in_stats == nullptr;
   a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
+  a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
   a.passes = d.precision == DMVS_PREC_TF32 ? 1 : 3;

@@ -45,7 +45,7 @@ struct TcArgs {
   int tiles_x, tiles_y, total_tiles;
   int R;            // depth of the raw / weight ring
   int stage_f;      // floats reserved for the (hi, lo) working planes / epilogue staging
-  int fast_in, vec_y;
+  int fast_in, vec_y, vec_res;
   int Hs, Ws;
   int64_t w_lo_off; // offset (floats) of the lo weights inside w_tc
 };
@@ -340,8 +340,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         for (int k = 0; k < 4; ++k)
           if (d.bias != nullptr && cq + k < d.Cout) bias[k] = __ldg(d.bias + cq + k);
         const bool full_quad = cq + 4 <= d.Cout;
-        const bool plain = d.epi == DMVS_EPI_STD && d.res_mode == DMVS_RES_NONE &&
-                           (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
+        const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
         const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
         const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
         float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
@@ -378,13 +377,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               const float4 t4 = *reinterpret_cast<const float4*>(out_s + m * OP + q4 * 4);
               float v[4] = {t4.x + bias[0], t4.y + bias[1], t4.z + bias[2], t4.w + bias[3]};
               const int64_t opix = (img_base + oy) * d.Wo + ox;
-              if (plain) {
+              int64_t rpix = opix;
+              if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+              if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+                float r[4] = {0.f, 0.f, 0.f, 0.f};
+                if (d.res_mode != DMVS_RES_NONE) {
+                  const float* rp = d.res + rpix * d.res_ps + cq;
+                  if (a.vec_res && full_quad) {
+                    const float4 r4 = ldg4(rp);
+                    r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+                  } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (cq + k >= relu_from) v[k] = fmaxf(v[k], 0.0f);
+                    for (int k = 0; k < 4; ++k)
+                      if (cq + k < d.Cout) r[k] = __ldg(rp + k);
+                  }
+                }
+                const bool pre = d.res_mode == DMVS_RES_PRE_ACT;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float x = pre ? v[k] + r[k] : v[k];
+                  if (cq + k >= relu_from) x = fmaxf(x, 0.0f);
+                  v[k] = pre ? x : x + r[k];
+                }
               } else {
-                int64_t rpix = opix;
-                if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   if (cq + k < d.Cout) v[k] = epilogue_value(d, v[k], cq + k, opix, rpix);
@@ -485,6 +500,7 @@ int dispatch_conv_tc(const dmvs_conv_desc& d, cudaStream_t st) {
   const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
   a.fast_in = vec_x && vec_x2 && d.in_stats == nullptr;
   a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
+  a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
   a.w_lo_off = (int64_t)d.KD * d.KH * d.KW * (a.cin_pad / 4) * a.cout_pad * 4;

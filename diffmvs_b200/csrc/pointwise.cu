@@ -162,6 +162,18 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
   }
 }
 
+// C <= 4 (images): one thread per pixel, C coalesced plane reads, one packed write
+__global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, float* __restrict__ y, int y_ps, int C, int HW,
+                                          int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t n = i / HW;
+  const int p = (int)(i - n * HW);
+  const float* xp = x + n * C * HW + p;
+  float* yp = y + i * y_ps;
+  for (int c = 0; c < C; ++c) yp[c] = __ldg(xp + (int64_t)c * HW);
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_ps, float* __restrict__ y, int C, int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -261,6 +273,12 @@ extern "C" int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int
 extern "C" int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t N, int32_t C, int32_t HW,
                                  void* stream) {
   if (!x || !y || N <= 0 || C <= 0 || HW <= 0 || y_ps < C) return DMVS_ERR_ARG;
+  if (C <= 4) {
+    const int64_t total = (int64_t)N * HW;
+    nchw_to_nhwc_small_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, y_ps, C,
+                                                                                                             HW, total);
+    return launch_status();
+  }
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
   if (grid.z > 65535 || grid.y > 65535) return DMVS_ERR_UNSUPPORTED;
   nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, y, y_ps, C, HW);
