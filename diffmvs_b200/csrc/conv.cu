@@ -223,7 +223,12 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
   if (d.precision == DMVS_PREC_AUTO) {
     // fp32-class arithmetic, back end chosen per layer: the tcgen05 kernel wins where one MMA instruction carries
     // enough work (>= 32 output channels per CTA), the FFMA kernel elsewhere (profiles/r1_conv_backends.txt)
-    if (d.w_tc && conv_tc_supported(d) && d.Cout >= 24) {
+    // measured rule (profiles/r1_conv_backends.txt): 3x3-or-larger kernels on maps big enough to fill the persistent grid,
+    // with >= 24 output channels, or >= 16 when the reduction is long (7x7x64)
+    const int taps = d.KD * d.KH * d.KW;
+    const long out_px = (long)d.N * d.Do * d.Ho * d.Wo;
+    const bool wide = d.Cout >= 24 || (d.Cout >= 16 && (long)taps * (d.C1 + d.C2) >= 2048);
+    if (d.w_tc && conv_tc_supported(d) && taps >= 9 && out_px >= 100000 && wide) {
       dmvs_conv_desc alt = d;
       alt.precision = DMVS_PREC_TC_TF32X3;
       return dispatch_conv_tc(alt, static_cast<cudaStream_t>(stream));
