@@ -77,17 +77,17 @@ class ClockSampler:
 
 
 def _best_cpu_threads(cores: int) -> int:
-    """torch's intra-op pools oversubscribe badly on big hosts (128 threads: 221 s/ref-view on the B200 box);
-    pick the thread count that is fastest on a small forward (cfg2-sized) and use it for the baseline."""
+    """torch's intra-op pools oversubscribe badly on big hosts (all 128 threads of the B200 box: 221 s/ref-view,
+    16 threads: 7.5 s); pick the fastest of {32, 16, 8} threads on a small forward (cfg2) for the baseline."""
     import torch
-    cands = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
+    cands = sorted({c for c in (min(cores, 32), 16, 8) if c <= cores}, reverse=True)
     if len(cands) == 1:
         return cands[0]
     best, best_t = cands[0], float("inf")
-    for c in cands:
+    for c in cands:                       # ~1 s per forward at cfg2: the whole sweep stays under ~15 s
         run = _oracle_forward_cpu("cfg2", c)
         run()
-        t = min(run(), run())
+        t = run()
         if t < best_t:
             best, best_t = c, t
     return best
@@ -189,18 +189,45 @@ def run_ours(a):
 
     h_out = {}
 
+    # End-to-end: every step copies its inputs from pinned host memory and returns its results to pinned host
+    # memory.  Like a DataLoader with pin_memory, the H2D copy of step i+1 runs on a copy stream while step i
+    # computes (two device input slots); every byte still moves inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "d2h": 0}
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])      # the forward that read this slot has finished
+            slots[slot] = ([t.to(dev, non_blocking=True) for t in h_imgs],
+                           {k: t.to(dev, non_blocking=True) for k, t in h_proj.items()},
+                           h_dv.to(dev, non_blocking=True))
+            ready[slot].record(copy_stream)
+
     def step_e2e():
-        di = [t.to(dev, non_blocking=True) for t in h_imgs]
-        dp = {k: t.to(dev, non_blocking=True) for k, t in h_proj.items()}
-        dd = h_dv.to(dev, non_blocking=True)
+        i = e2e_state["i"]
+        cur = i & 1
+        if slots[cur] is None:
+            prefetch(cur)                                # first step: its own copy, not overlapped
+        main = torch.cuda.current_stream()
+        main.wait_event(ready[cur])
+        di, dp, dd = slots[cur]
+        for t in list(di) + list(dp.values()) + [dd]:
+            t.record_stream(main)                        # allocated on the copy stream, consumed on the main one
         out = model(di, dp, dd)
+        consumed[cur].record(main)
+        prefetch(cur ^ 1)                                # next step's inputs, overlapped with this forward
         res = [out["depth"][-1]] + list(out["photometric_confidence"])
-        for i, t in enumerate(res):
-            if i not in h_out:
-                h_out[i] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h_out[i].copy_(t, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller holds the result, as test.py:130 does
-        return sum(t.numel() * 4 for t in res)
+        for k, t in enumerate(res):
+            if k not in h_out:
+                h_out[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h_out[k].copy_(t, non_blocking=True)
+        main.synchronize()                               # the caller holds the result, as test.py:130 does
+        e2e_state["i"] = i + 1
+        e2e_state["d2h"] = sum(t.numel() * 4 for t in res)
+        return e2e_state["d2h"]
 
     def barrier():
         if world > 1:
