@@ -288,7 +288,7 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
         // keep at least ~2 waves of CTAs when a smaller tile is possible
         const int th2 = (8 / wcount) * px;
         const long blocks = (long)ceil_div(d.Wo, kTileW) * ceil_div(d.Ho, th2) * d.N * d.Do;
-        if (blocks >= 2 * kNumSMs || px == 1) break;
+        if (blocks >= kNumSMs || px == 1) break;   // one full wave is enough: taller per-thread tiles amortise LDS better
       }
     }
     if (!ck) return DMVS_ERR_UNSUPPORTED;
