@@ -9,6 +9,8 @@
 //     (bank-conflict free), weights as warp-uniform broadcast vectors;
 //   * GroupNorm+SiLU of the producer layer is applied while staging (no extra pass over HBM), and
 //     the GroupNorm statistics of this layer's output are reduced in the epilogue.
+#include <cstdlib>
+
 #include "conv_common.cuh"
 
 namespace dmvs {
@@ -223,12 +225,12 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
   if (d.precision == DMVS_PREC_AUTO) {
     // fp32-class arithmetic, back end chosen per layer: the tcgen05 kernel wins where one MMA instruction carries
     // enough work (>= 32 output channels per CTA), the FFMA kernel elsewhere (profiles/r1_conv_backends.txt)
-    // measured rule (profiles/r1_conv_backends.txt): 3x3-or-larger kernels on maps big enough to fill the persistent grid,
-    // with >= 24 output channels, or >= 16 when the reduction is long (7x7x64)
+    // measured rule (profiles/r1_conv_backends.txt): the persistent tcgen05 kernel pays off on 3x3-or-larger kernels with
+    // >= 5 GMAC of work and >= 24 output channels (or >= 16 when the reduction is long, e.g. 7x7x64)
     const int taps = d.KD * d.KH * d.KW;
-    const long out_px = (long)d.N * d.Do * d.Ho * d.Wo;
+    const double macs = (double)taps * (d.C1 + d.C2) * d.Cout * d.N * d.Do * d.Ho * d.Wo;
     const bool wide = d.Cout >= 24 || (d.Cout >= 16 && (long)taps * (d.C1 + d.C2) >= 2048);
-    if (d.w_tc && conv_tc_supported(d) && taps >= 9 && out_px >= 100000 && wide) {
+    if (d.w_tc && conv_tc_supported(d) && taps >= 9 && macs >= 5e9 && wide) {
       dmvs_conv_desc alt = d;
       alt.precision = DMVS_PREC_TC_TF32X3;
       return dispatch_conv_tc(alt, static_cast<cudaStream_t>(stream));
@@ -288,7 +290,8 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
         // keep at least ~2 waves of CTAs when a smaller tile is possible
         const int th2 = (8 / wcount) * px;
         const long blocks = (long)ceil_div(d.Wo, kTileW) * ceil_div(d.Ho, th2) * d.N * d.Do;
-        if (blocks >= kNumSMs || px == 1) break;   // one full wave is enough: taller per-thread tiles amortise LDS better
+        static const long min_blocks = getenv("DMVS_CONV_MINBLOCKS") ? atol(getenv("DMVS_CONV_MINBLOCKS")) : kNumSMs;
+        if (blocks >= min_blocks || px == 1) break;   // one full wave is enough: taller per-thread tiles amortise LDS better
       }
     }
     if (!ck) return DMVS_ERR_UNSUPPORTED;
