@@ -18,13 +18,16 @@ import os
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
                     PREC_AUTO, PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
-# Arithmetic of the convolutions (storage is always fp32):
-#   "tf32x3"           tensor cores with hi/lo operand split - fp32-class accuracy
-#   "fp32"   (default) CUDA-core FFMA kernel (currently the fastest fp32-class back end)
-#   "tf32"             tensor cores, operands rounded to TF32 (torch/cuDNN default numerics; ~5e-4 depth rel-L1)
+# Arithmetic of the convolutions (storage is always fp32).  fp32-class modes (parity-safe, <= 4e-6 depth rel-L1):
+#   "auto"  (default)  per layer: tcgen05/TMEM 3xTF32 kernel for the FLOP-heavy stride-1 layers, FFMA2 kernel elsewhere
+#   "fp32"             CUDA-core kernel everywhere (packed fp32x2 FMAs)
+#   "tf32x3"           legacy mma.sync tensor cores with hi/lo operand split
+#   "tc_tf32x3"        tcgen05 kernel wherever it applies (stride 1), mma.sync 3xTF32 for strided layers
+# Plain-TF32 modes (NOT parity-safe on the synthetic weights: 1e-3..3e-3 depth rel-L1, 2-6 % index flips):
+#   "tf32", "tc_tf32"  operands rounded to TF32 - the numerics cuDNN uses under torch defaults
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
               "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO}
-_precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "fp32")]
+_precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "auto")]
 
 
 def set_precision(name: str) -> None:
