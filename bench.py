@@ -335,6 +335,12 @@ def run_ours(a):
         "wall_ms_per_step": ms_wall / a.steps,
     }
     print(json.dumps(line), flush=True)
+    if a.dump_tuned:
+        names = {v: k for k, v in ops.PRECISIONS.items()}
+        rows = [{"sig": list(map(int, k)), "choice": names[c], "ms": {names[m]: t for m, t in ts.items()}}
+                for k, (c, ts) in ops.tuned_table().items()]
+        with open(a.dump_tuned, "w") as f:
+            json.dump(rows, f, indent=0)
     if world > 1:
         dist.destroy_process_group()
 
@@ -348,6 +354,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-modes", action="store_true")
+    ap.add_argument("--dump-tuned", default=None, help="write the per-layer autotuning table (JSON) to this path")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -16,6 +16,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4
 RES_NONE, RES_PRE_ACT, RES_POST_ACT = 0, 1, 2
 EPI_STD, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_TC_TF32X3, PREC_TC_TF32, PREC_AUTO = 0, 1, 2, 3, 4, 5
+PREC_WS_TF32X3, PREC_WS_TF32 = 6, 7
 
 f32p = C.c_void_p
 i32 = C.c_int32
@@ -43,6 +44,7 @@ SIGNATURES = {
     "dmvs_build_info": (C.c_char_p, []),
     "dmvs_launch_count": (C.c_uint64, []),
     "dmvs_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "dmvs_conv_backends": (C.c_int, [C.POINTER(ConvDesc)]),
     "dmvs_deconv3d_f32": (C.c_int, [f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_compose_homographies": (C.c_int, [f32p, f32p, i32, i32, C.c_void_p]),
     "dmvs_warp_volume": (C.c_int, [f32p, i32, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]),

@@ -235,6 +235,21 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
       alt.precision = DMVS_PREC_TC_TF32X3;
       return dispatch_conv_tc(alt, static_cast<cudaStream_t>(stream));
     }
+  } else if (d.precision == DMVS_PREC_WS_TF32X3 || d.precision == DMVS_PREC_WS_TF32) {
+    // width-stacked tcgen05 kernel wherever its layout preconditions hold (stride 1, 16-byte channel groups);
+    // DMVS_WS_MIN_K / DMVS_WS_MIN_MACS bound the layers it takes (tuning aids, see dispatch rule below)
+    static const long ws_min_k = getenv("DMVS_WS_MIN_K") ? atol(getenv("DMVS_WS_MIN_K")) : 0;
+    static const double ws_min_macs = getenv("DMVS_WS_MIN_MACS") ? atof(getenv("DMVS_WS_MIN_MACS")) : 0.0;
+    const long kred = (long)d.KD * d.KH * d.KW * (d.C1 + d.C2);
+    const double macs = (double)kred * d.Cout * d.N * d.Do * d.Ho * d.Wo;
+    if (d.w_tc && conv_ws_supported(d) && kred >= ws_min_k && macs >= ws_min_macs)
+      return dispatch_conv_ws(d, static_cast<cudaStream_t>(stream));
+    if (d.precision == DMVS_PREC_WS_TF32 && d.w_t) {
+      dmvs_conv_desc alt = d;
+      alt.precision = DMVS_PREC_TF32;
+      return dispatch_conv_mma(alt, static_cast<cudaStream_t>(stream));
+    }
+    // fall through to the FFMA kernel
   } else if (d.precision != DMVS_PREC_FP32) {
     if (d.precision < DMVS_PREC_FP32 || d.precision > DMVS_PREC_TC_TF32) return DMVS_ERR_ARG;
     if (d.precision >= DMVS_PREC_TC_TF32X3) {
@@ -313,6 +328,16 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     remaining -= chunk;
   }
   return 0;
+}
+
+extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
+  if (dp == nullptr) return DMVS_ERR_ARG;
+  const dmvs_conv_desc& d = *dp;
+  int mask = 1;                                        // bit 0: FFMA kernel (always)
+  if (d.w_t) mask |= 2;                                // bit 1: legacy mma.sync kernel
+  if (d.w_tc && conv_tc_supported(d)) mask |= 4;       // bit 2: tcgen05 kernel, taps as descriptor offsets
+  if (d.w_tc && conv_ws_supported(d)) mask |= 8;       // bit 3: tcgen05 kernel, kernel-row taps stacked along N
+  return mask;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -226,5 +226,8 @@ int dispatch_conv_mma(const dmvs_conv_desc& d, cudaStream_t stream);
 // tcgen05 / TMEM back end (conv_tc.cu)
 bool conv_tc_supported(const dmvs_conv_desc& d);
 int dispatch_conv_tc(const dmvs_conv_desc& d, cudaStream_t stream);
+// width-stacked tcgen05 back end (conv_ws.cu): the KW taps of a kernel row share one MMA (N = KW * Cout)
+bool conv_ws_supported(const dmvs_conv_desc& d);
+int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t stream);
 
 }  // namespace dmvs

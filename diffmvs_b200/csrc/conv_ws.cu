@@ -1,0 +1,634 @@
+// tcgen05 / TMEM implicit-GEMM convolution with the kernel-row taps stacked along N ("ws" = width-stacked),
+// stride 1, 2-D / 3-D, channels-last, for sm_100a.
+//
+// Why a second tcgen05 kernel: with the taps as descriptor offsets (conv_tc.cu) every tap is its own MMA with
+// N = Cout.  The layers of this network have Cout = 8..32, and an SS-mode M=128 x K=8 TF32 MMA has to read its
+// 4 KB A operand from shared memory (128 B/clk => 32 clk) no matter how small N is, while the math needs only
+// N/2 clk.  So at Cout = 16 the tensor pipe idles 75 % of the time and the kernel is no faster than FFMA2.
+//
+// Here the KW taps of one kernel row share ONE MMA:
+//     E[p][kw*CC + c] = sum_{kd,kh,k} A[p + kh*in_cols][k] * W[kd][kh][kw][k][c]          (N = KW*CC columns)
+//     out[p][c]       = sum_{kw} E[p + kw][kw*CC + c]                                      (shift-add epilogue)
+// p = flattened position of the staged (TH+KH-1) x (TW+KW-1) halo tile (pitch in_cols), exactly the planar-by-
+// channel-quad operand layout of conv_tc.cu: a kh tap is still a descriptor offset of kh*in_cols positions, the
+// kw taps become columns.  One A read now feeds KW*CC >= 24..224 columns, MMA count drops KW-fold, and the
+// shift-add costs KW*CC FADDs per pixel (1-10 % of the FMAs it replaces) through a small shared staging ring.
+//
+//   * 3xTF32 (fp32-class): hi = rna_tf32(x), lo = rna_tf32(x - hi), D += Alo*Bhi + Ahi*Blo + Ahi*Bhi; activations
+//     are split once per stage in shared memory (in place), weights are pre-split on the host (w_tc layout).
+//   * GroupNorm(4)+affine+SiLU of the producer (update.py:117-133) is applied inside the split pass, so those
+//     layers keep the asynchronous cp.async landing path.
+//   * Persistent CTAs, two per SM (<= 112 KB shared, <= 256 TMEM columns each): while one CTA drains its
+//     accumulators the other one's MMAs keep the tensor pipe busy - overlap without warp specialisation.
+//   * Stages = (tile, depth tap, 8 input channels) stream through an R-deep cp.async ring exactly as in conv_tc.cu.
+#include <cstdlib>
+
+#include "conv_common.cuh"
+
+namespace dmvs {
+namespace {
+
+constexpr int kWsThreads = 256;
+constexpr int kRingRows = 136;   // epilogue staging ring: one 128-row M block + the <= 8 trailing rows of the previous one
+
+struct WsArgs {
+  dmvs_conv_desc d;
+  int cin_pad;      // (C1+C2) rounded up to 8
+  int cout_pad;     // pitch of the packed weights (Cout rounded up to 16)
+  int co_base;      // first output channel of this launch
+  int CC;           // output channels of this launch (multiple of 8)
+  int CCE;          // output channels per epilogue pass (multiple of 8, KW*CCE <= 64)
+  int N;            // MMA N = KW*CC rounded up to 16
+  int TH, TW, in_rows, in_cols;
+  int m_total;      // TH * in_cols flattened positions carry results
+  int plane;        // positions per channel-quad plane (incl. slack read by the last M block)
+  int n_blk;        // M=128 blocks per tile
+  int tmem_cols;    // allocated TMEM columns (power of two >= 32)
+  int tiles_x, tiles_y, total_tiles;
+  int stage_f;      // floats per ring slot: operand pair [hi | lo]; doubles as epilogue staging
+  int vec_y, vec_res;
+  int Hs, Ws;
+  float inv_in_cols;
+  int64_t w_lo_off; // offset (floats) of the lo weights inside w_tc
+};
+
+struct Stage {
+  int tile, kd, chunk;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// K-major, un-swizzled UMMA shared-memory descriptor (8 rows x 16 bytes core matrices)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t v = 0;
+  v |= (uint64_t)((saddr >> 4) & 0x3fff);
+  v |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  v |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  v |= 1ull << 46;  // descriptor version (Blackwell); layout_type 0 = no swizzle
+  return v;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();   // watchdog: a lost commit must not hang the GPU
+  }
+}
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int R>
+__device__ __forceinline__ void cp_async_wait_ring() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(R - 2) : "memory");
+}
+
+// PASSES = 1 (TF32) or 3 (3xTF32), R = ring depth (2, 3), GN = GroupNorm+SiLU prologue in the split pass
+template <int PASSES, int R, bool GN>
+__global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_constant__ WsArgs a) {
+  const dmvs_conv_desc& d = a.d;
+  extern __shared__ __align__(128) float smem[];
+  const int N = a.N;
+  const int plane_f = 2 * a.plane * 4;                        // floats per operand plane set (two channel quads)
+  const int wslab_f = d.KH * 2 * N * 4;                       // floats per weight slab: [kh][quad][N][4]
+  float* pair0 = smem;                                        // [R][stage_f]: pair = [hi | lo], raw data lands in hi
+  float* w_hi0 = pair0 + R * a.stage_f;                       // [R][wslab_f]
+  float* w_lo0 = w_hi0 + R * wslab_f;
+  float* gn_s = w_lo0 + (PASSES == 3 ? R * wslab_f : 0);      // [2][C1] when GN
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t mbar[2];   // stages alternate barriers: a parity wait may lag by one phase only
+  __shared__ float stat_s[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar[1])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  const int Ctot = d.C1 + d.C2;
+  const int units_per_row = a.in_cols * 2;       // 16-byte units per tile row (two channel quads per stage)
+  const int nchunks = a.cin_pad >> 3;
+  const int taps = d.KH * d.KW;
+  const int qtot = a.cin_pad >> 2;
+
+  auto decode = [&](int tile, int& n, int& od, int& ty0, int& tx0) {
+    const int tx = tile % a.tiles_x;
+    const int r = tile / a.tiles_x;
+    const int ty = r % a.tiles_y;
+    const int z = r / a.tiles_y;
+    n = z / d.Do;
+    od = z - n * d.Do;
+    ty0 = ty * a.TH;
+    tx0 = tx * a.TW;
+  };
+  auto kd_first = [&](int od) { const int v = d.pad_d - od; return v > 0 ? v : 0; };
+  auto kd_last = [&](int od) { const int v = d.D - 1 + d.pad_d - od; return v < d.KD - 1 ? v : d.KD - 1; };
+  auto first_stage_of = [&](int tile) {
+    Stage s{tile, 0, 0};
+    if (tile < a.total_tiles) {
+      int n, od, ty0, tx0;
+      decode(tile, n, od, ty0, tx0);
+      s.kd = kd_first(od);
+    }
+    return s;
+  };
+  auto advance = [&](const Stage& c) {
+    Stage s = c;
+    if (++s.chunk < nchunks) return s;
+    s.chunk = 0;
+    int n, od, ty0, tx0;
+    decode(c.tile, n, od, ty0, tx0);
+    if (++s.kd <= kd_last(od)) return s;
+    return first_stage_of(c.tile + (int)gridDim.x);
+  };
+
+  // loads of one stage into ring slot `slot`: raw halo tile (planar by channel quad) and its weight slab
+  auto issue_loads = [&](const Stage& s, int slot) {
+    if (s.tile < a.total_tiles) {
+      int n, od, ty0, tx0;
+      decode(s.tile, n, od, ty0, tx0);
+      const int c0 = s.chunk * 8;
+      const int id = od + s.kd - d.pad_d;
+      const int iy0 = ty0 - d.pad_h, ix0 = tx0 - d.pad_w;
+      float* a_raw = pair0 + slot * a.stage_f;
+#pragma unroll 1
+      for (int row = warp; row < a.in_rows; row += kWsThreads / 32) {
+        const int iy = iy0 + row;
+        const bool row_ok = iy >= 0 && iy < d.H;
+        const int sy = d.in_up2 ? (iy >> 1) : iy;
+        const int64_t row_pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws;
+        const int row_off = row * a.in_cols;
+#pragma unroll 1
+        for (int u = lane; u < units_per_row; u += 32) {
+          const int q = u & 1;
+          const int col = u >> 1;
+          const int ix = ix0 + col;
+          const int ch = c0 + q * 4;
+          const bool ok = row_ok && ix >= 0 && ix < d.W && ch < Ctot;
+          const int sx = d.in_up2 ? (ix >> 1) : ix;
+          const int64_t pix = row_pix + sx;
+          const float* src = d.x;
+          if (ok) src = ch < d.C1 ? d.x + pix * d.x_ps + ch : d.x2 + pix * d.x2_ps + (ch - d.C1);
+          cp_async16(a_raw + (q * a.plane + row_off + col) * 4, src, ok);
+        }
+      }
+      // weights of this (kd, channel chunk): global [kd][kh*KW+kw][quad][cout_pad][4] -> shared [kh][quad][N][4],
+      // N index = kw*CC + c (columns past KW*CC are zero filled)
+      const int q0 = c0 >> 2;
+      float* wh = w_hi0 + slot * wslab_f;
+      float* wl = w_lo0 + slot * wslab_f;
+      const int wunits = d.KH * 2 * N;
+#pragma unroll 1
+      for (int idx = tid; idx < wunits; idx += kWsThreads) {
+        const int j = idx % N;
+        const int r = idx / N;
+        const int q = r & 1;
+        const int kh = r >> 1;
+        const int kw = j / a.CC;
+        const int c = j - kw * a.CC;
+        const bool ok = kw < d.KW && q0 + q < qtot;
+        const int64_t off =
+            ((((int64_t)s.kd * taps + kh * d.KW + kw) * qtot + q0 + q) * a.cout_pad + a.co_base + c) * 4;
+        cp_async16(wh + idx * 4, ok ? d.w_tc + off : d.w_tc, ok);
+        if (PASSES == 3) cp_async16(wl + idx * 4, ok ? d.w_tc + a.w_lo_off + off : d.w_tc, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");   // always one group per stage slot (possibly empty)
+  };
+
+  Stage cur = first_stage_of((int)blockIdx.x);
+  if (cur.tile < a.total_tiles) {
+    Stage pre = cur;
+#pragma unroll 1
+    for (int i = 0; i < R - 1; ++i) {   // prologue: R-1 stages in flight
+      issue_loads(pre, i);
+      if (pre.tile < a.total_tiles) pre = advance(pre);
+    }
+    int issued = 0, waited = 0;  // stages whose MMAs were committed / whose completion was consumed (in order)
+    bool tile_start = true;
+    int slot = 0;
+    int gn_n = -1;
+    auto wait_one = [&]() {      // stage t commits to mbar[t & 1]; its phase there has parity (t >> 1) & 1
+      mbar_wait(&mbar[waited & 1], (uint32_t)((waited >> 1) & 1));
+      ++waited;
+    };
+    for (;;) {
+      int n, od, ty0, tx0;
+      decode(cur.tile, n, od, ty0, tx0);
+      cp_async_wait_ring<R>();                           // everything but the newest R-2 groups has landed
+      if (GN && n != gn_n) {                             // GroupNorm affine of the producer is per sample
+        for (int c = tid; c < d.C1; c += kWsThreads) groupnorm_affine(d, n, c, gn_s);
+        gn_n = n;
+      }
+      __syncthreads();                                   // raw data of `slot` (and gn_s) visible to every thread
+      float* a_hi = pair0 + slot * a.stage_f;
+      float* a_lo = a_hi + plane_f;
+      // ---- one pass over the staged tile: optional GroupNorm+SiLU, then the (hi, lo) split in place ----------
+      if (PASSES == 3 || GN) {
+        const int total = 2 * a.plane;
+        const int iy0 = ty0 - d.pad_h, ix0 = tx0 - d.pad_w;
+        const int c0 = cur.chunk * 8;
+#pragma unroll 1
+        for (int u = tid; u < total; u += kWsThreads) {
+          float4 v = *reinterpret_cast<const float4*>(a_hi + u * 4);
+          if (GN) {
+            const int q = u >= a.plane ? 1 : 0;
+            const int p = u - q * a.plane;
+            const int row = (int)(((float)p + 0.5f) * a.inv_in_cols);
+            const int col = p - row * a.in_cols;
+            const int iy = iy0 + row, ix = ix0 + col;
+            const int ch = c0 + q * 4;
+            if (row < a.in_rows && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W && ch < d.C1) {   // padding stays zero
+              const float4 g1 = *reinterpret_cast<const float4*>(gn_s + ch);
+              const float4 g0 = *reinterpret_cast<const float4*>(gn_s + d.C1 + ch);
+              v.x = siluf_(fmaf(v.x, g1.x, g0.x));
+              v.y = siluf_(fmaf(v.y, g1.y, g0.y));
+              v.z = siluf_(fmaf(v.z, g1.z, g0.z));
+              v.w = siluf_(fmaf(v.w, g1.w, g0.w));
+            } else {
+              v = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          if (PASSES == 3) {
+            float4 h, l;
+            h.x = rna_tf32(v.x); l.x = rna_tf32(v.x - h.x);
+            h.y = rna_tf32(v.y); l.y = rna_tf32(v.y - h.y);
+            h.z = rna_tf32(v.z); l.z = rna_tf32(v.z - h.z);
+            h.w = rna_tf32(v.w); l.w = rna_tf32(v.w - h.w);
+            *reinterpret_cast<float4*>(a_hi + u * 4) = h;
+            *reinterpret_cast<float4*>(a_lo + u * 4) = l;
+          } else {
+            *reinterpret_cast<float4*>(a_hi + u * 4) = v;
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      __syncthreads();                                   // operands of this stage complete
+      // ---- one thread issues the MMAs: per M block and kernel row, all KW taps in one instruction -----------
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
+        const uint64_t dah0 = umma_desc(smem_u32(a_hi), lbo_a, 128), dal0 = umma_desc(smem_u32(a_lo), lbo_a, 128);
+        const uint64_t dbh0 = umma_desc(smem_u32(w_hi0 + slot * wslab_f), lbo_b, 128);
+        const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + slot * wslab_f), lbo_b, 128);
+        const uint32_t b_step = 2u * (uint32_t)N;              // one kernel row of weights, in 16-byte units
+        for (int blk = 0; blk < a.n_blk; ++blk) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(blk * N);
+          uint32_t acc = tile_start ? 0u : 1u;
+          uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
+          for (int kh = 0; kh < d.KH; ++kh, a_off += (uint32_t)a.in_cols, b_off += b_step) {
+            if (PASSES == 3) {
+              umma_tf32(d_tmem, dal0 + a_off, dbh0 + b_off, idesc, acc);
+              umma_tf32(d_tmem, dah0 + a_off, dbl0 + b_off, idesc, 1u);
+              umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, acc);
+            }
+            acc = 1u;
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                         smem_u32(&mbar[issued & 1]))
+                     : "memory");
+      }
+      ++issued;
+      // ---- keep the ring full: stage s+R-1 reuses the pair of stage s-1, whose MMAs must have retired ----------
+      if (issued - waited > 1) {
+        wait_one();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      }
+      issue_loads(pre, (slot + R - 1) % R);
+      if (pre.tile < a.total_tiles) pre = advance(pre);
+
+      const Stage nxt = advance(cur);
+      const bool tile_done = nxt.tile != cur.tile;
+      tile_start = tile_done;
+      if (tile_done) {
+        // ---- all MMAs of the tile retired -> shift-add epilogue ------------------------------------------------
+        while (waited < issued) wait_one();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        float* ring = pair0 + slot * a.stage_f;   // this stage's pair is dead now: [kRingRows][SP] staging ring
+        const int CCE = a.CCE;
+        const int SP = d.KW * CCE + 4;            // ring row pitch (odd number of 16-byte units: conflict-free)
+        const int N4 = CCE >> 2;                  // channel quads per epilogue pass (2, 4, ... 16)
+        const int g_per_kw = CCE >> 3;            // 8-column TMEM groups per tap
+        const int groups = d.KW * g_per_kw;
+        const int quadrant = warp & 3, half = warp >> 2;
+        const int q4 = tid % N4;                  // fixed channel quad per thread (256 % N4 == 0)
+        const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
+        const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
+        const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
+#pragma unroll 1
+        for (int e0 = 0; e0 < a.CC; e0 += CCE) {
+          const int cq = a.co_base + e0 + q4 * 4;   // first absolute output channel of this thread's quad
+          if (a.co_base + e0 >= d.Cout) break;      // block-uniform: the whole pass is channel padding
+          float bias[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (d.bias != nullptr && cq + k < d.Cout) bias[k] = __ldg(d.bias + cq + k);
+          const bool full_quad = cq + 4 <= d.Cout;
+          float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
+          if (tid < 8) stat_s[tid] = 0.0f;
+#pragma unroll 1
+          for (int blk = 0; blk < a.n_blk; ++blk) {
+            // phase A: TMEM rows of this block -> ring rows (lane quadrant = warp % 4; the two warp halves split the groups)
+            {
+              const int m = quadrant * 32 + lane;
+              float* rrow = ring + ((blk * 128 + m) % kRingRows) * SP;
+              const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + e0);
+#pragma unroll 1
+              for (int g = half; g < groups; g += 2) {
+                const int kw = g / g_per_kw;
+                const int sub = g - kw * g_per_kw;
+                float v[8];
+                tmem_ld8(trow + (uint32_t)(kw * a.CC + sub * 8), v);
+                float* dst = rrow + kw * CCE + sub * 8;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+            }
+            __syncthreads();
+            // phase B: positions [blk*128 - (KW-1), blk*128 + 128 - (KW-1)) have all their KW rows in the ring now
+            if (cq < d.Cout) {
+#pragma unroll 1
+              for (int m = tid / N4; m < 128; m += kWsThreads / N4) {
+                const int p = blk * 128 - (d.KW - 1) + m;
+                if (p < 0) continue;
+                const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
+                const int px = p - py * a.in_cols;
+                const int oy = ty0 + py, ox = tx0 + px;
+                if (px >= a.TW || py >= a.TH || oy >= d.Ho || ox >= d.Wo) continue;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int kw = 0; kw < d.KW; ++kw) {
+                  const float4 t4 =
+                      *reinterpret_cast<const float4*>(ring + ((p + kw) % kRingRows) * SP + kw * CCE + q4 * 4);
+                  v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] += bias[k];
+                const int64_t opix = (img_base + oy) * d.Wo + ox;
+                int64_t rpix = opix;
+                if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+                if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+                  float r[4] = {0.f, 0.f, 0.f, 0.f};
+                  if (d.res_mode != DMVS_RES_NONE) {
+                    const float* rp = d.res + rpix * d.res_ps + cq;
+                    if (a.vec_res && full_quad) {
+                      const float4 r4 = ldg4(rp);
+                      r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
+                    } else {
+#pragma unroll
+                      for (int k = 0; k < 4; ++k)
+                        if (cq + k < d.Cout) r[k] = __ldg(rp + k);
+                    }
+                  }
+                  const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    float x = pre_act ? v[k] + r[k] : v[k];
+                    if (cq + k >= relu_from) x = fmaxf(x, 0.0f);
+                    v[k] = pre_act ? x : x + r[k];
+                  }
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (cq + k < d.Cout) v[k] = epilogue_value(d, v[k], cq + k, opix, rpix);
+                }
+                if (d.out_stats != nullptr) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    gs[k] += v[k];
+                    gq[k] += v[k] * v[k];
+                  }
+                }
+                float* yp = d.y + opix * d.y_ps + cq;
+                if (a.vec_y && full_quad) {
+                  *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    if (cq + k < d.Cout) yp[k] = v[k];
+                }
+              }
+            }
+            __syncthreads();   // ring rows are rewritten by the next block / the next pass / the next stage's loads
+          }
+          if (d.out_stats != nullptr) {
+            const int cpg = d.Cout / 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float s = gs[k], q = gq[k];
+              for (int o = 16; o >= N4; o >>= 1) {   // lanes l, l+N4, ... of a warp share a channel quad
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+              }
+              const int c = cq + k;
+              if (lane < N4 && c < d.Cout) {
+                const int g = c / cpg;
+                atomicAdd(&stat_s[g * 2 + 0], s);
+                atomicAdd(&stat_s[g * 2 + 1], q);
+              }
+            }
+            __syncthreads();
+            if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+            __syncthreads();
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads done before the next tile's MMAs
+      }
+      if (nxt.tile >= a.total_tiles) break;
+      cur = nxt;
+      slot = (slot + 1) % R;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(a.tmem_cols));
+}
+
+using KernelFn = void (*)(const WsArgs);
+
+template <int PASSES, int R, bool GN>
+KernelFn get_kernel() {
+  static bool configured = false;
+  KernelFn fn = conv_ws_kernel<PASSES, R, GN>;
+  if (!configured) {
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    configured = true;
+  }
+  return fn;
+}
+
+template <int PASSES>
+KernelFn pick_r(int r, bool gn) {
+  if (gn) return r >= 3 ? get_kernel<PASSES, 3, true>() : get_kernel<PASSES, 2, true>();
+  return r >= 3 ? get_kernel<PASSES, 3, false>() : get_kernel<PASSES, 2, false>();
+}
+
+struct TileCfg {
+  int TH = 0, TW = 0, in_cols = 0, n_blk = 0, plane = 0, R = 0, stage_f = 0;
+  size_t smem = 0;
+  double score = 0.0;
+};
+
+// Tile search: maximise useful output pixels per unit of (MMA rows + staged positions) under the shared-memory
+// and TMEM budget of `ctas_per_sm` co-resident CTAs.
+TileCfg choose_tile(const dmvs_conv_desc& d, int N, int CCE, int passes, int ctas_per_sm) {
+  const size_t smem_limit = ctas_per_sm == 2 ? 112 * 1024 : 216 * 1024;
+  const int tmem_limit = ctas_per_sm == 2 ? 256 : 512;
+  const int max_blk = tmem_limit / N;
+  TileCfg best;
+  static const int force_th = getenv("DMVS_WS_TH") ? atoi(getenv("DMVS_WS_TH")) : 0;   // tuning aids
+  static const int force_r = getenv("DMVS_WS_R") ? atoi(getenv("DMVS_WS_R")) : 0;
+  for (int th = 16; th >= 1; th >>= 1) {
+    if (th > 1 && th / 2 >= d.Ho) continue;          // a shorter tile already covers the image height
+    if (force_th && th != force_th) continue;
+    for (int nb = max_blk; nb >= 1; --nb) {
+      const int cols_max = nb * 128 / th;            // in_cols such that th*in_cols <= nb*128
+      const int tw_max = cols_max - (d.KW - 1);
+      if (tw_max < 8 && tw_max < d.Wo) continue;
+      if (tw_max < 1) continue;
+      const int ntx = ceil_div(d.Wo, tw_max);
+      const int TW = ceil_div(d.Wo, ntx);
+      const int in_cols = TW + d.KW - 1;
+      const int m_total = th * in_cols;
+      const int n_blk = ceil_div(m_total, 128);
+      if (n_blk > max_blk) continue;
+      const int plane = (n_blk * 128 + (d.KH - 1) * in_cols + 8 + 7) & ~7;
+      size_t work_f = (size_t)(passes == 3 ? 2 : 1) * 2 * plane * 4;
+      const size_t ring_f = (size_t)kRingRows * (d.KW * CCE + 4);
+      if (work_f < ring_f) work_f = ring_f;
+      work_f = (work_f + 31) & ~(size_t)31;
+      const size_t wslab_f = (size_t)d.KH * 2 * N * 4;
+      for (int r = 3; r >= 2; --r) {
+        if (force_r && r != force_r) continue;
+        const size_t need = (r * work_f + (passes == 3 ? 2 : 1) * r * wslab_f + 2 * (size_t)d.C1 + 8) * 4;
+        if (need > smem_limit) continue;
+        const double useful = (double)th * TW;
+        const double cost = (double)n_blk * 128 * (1.0 + 0.15 * d.KH) + 0.6 * (double)(th + d.KH - 1) * in_cols +
+                            (r == 2 ? 0.08 : 0.0) * n_blk * 128 + 96.0;   // + fixed per-tile overhead
+        const double score = useful / cost;
+        if (score > best.score) {
+          best.TH = th; best.TW = TW; best.in_cols = in_cols; best.n_blk = n_blk; best.plane = plane; best.R = r;
+          best.stage_f = (int)work_f; best.smem = need; best.score = score;
+        }
+        break;   // deepest ring that fits for this shape
+      }
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+bool conv_ws_supported(const dmvs_conv_desc& d) {
+  if (d.w_tc == nullptr || d.stride != 1 || d.KH > 16 || d.KW > 8) return false;
+  const bool vec_x = aligned16(d.x) && (d.x_ps % 4 == 0) && (d.C1 % 4 == 0);
+  const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
+  if (!vec_x || !vec_x2) return false;
+  if (d.in_stats != nullptr && (d.in_up2 || d.C2 != 0 || !aligned16(d.in_g1) || !aligned16(d.in_g0))) return false;
+  return true;
+}
+
+int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
+  if (!aligned16(d.w_tc)) return DMVS_ERR_ALIGN;
+  if (!conv_ws_supported(d)) return DMVS_ERR_UNSUPPORTED;
+  const int passes = d.precision == DMVS_PREC_WS_TF32 ? 1 : 3;
+  WsArgs a;
+  a.d = d;
+  a.cin_pad = (d.C1 + d.C2 + 7) & ~7;
+  a.cout_pad = (d.Cout + 15) & ~15;
+  a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
+  a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
+  a.Hs = d.in_up2 ? d.H / 2 : d.H;
+  a.Ws = d.in_up2 ? d.W / 2 : d.W;
+  a.w_lo_off = (int64_t)d.KD * d.KH * d.KW * (a.cin_pad / 4) * a.cout_pad * 4;
+
+  int cc_max = (256 / d.KW) & ~7;
+  if (cc_max > 64) cc_max = 64;
+  if (cc_max < 8) return DMVS_ERR_UNSUPPORTED;
+  int remaining = (d.Cout + 7) & ~7, co_base = 0;
+  while (remaining > 0) {
+    const int CC = remaining < cc_max ? remaining : cc_max;
+    const int N = (d.KW * CC + 15) & ~15;
+    int CCE = CC;
+    if (d.KW * CC > 64) CCE = (d.KW * 16 <= 64 && CC % 16 == 0) ? 16 : 8;
+    if (256 % (CCE / 4) != 0) CCE = 8;   // a thread keeps one channel quad: quads per pass must divide the block
+    TileCfg t = choose_tile(d, N, CCE, passes, 2);
+    if (!t.TH) t = choose_tile(d, N, CCE, passes, 1);
+    if (!t.TH) return DMVS_ERR_UNSUPPORTED;
+    a.co_base = co_base;
+    a.CC = CC;
+    a.CCE = CCE;
+    a.N = N;
+    a.TH = t.TH;
+    a.TW = t.TW;
+    a.in_rows = t.TH + d.KH - 1;
+    a.in_cols = t.in_cols;
+    a.m_total = t.TH * t.in_cols;
+    a.plane = t.plane;
+    a.n_blk = t.n_blk;
+    a.stage_f = t.stage_f;
+    a.inv_in_cols = 1.0f / (float)t.in_cols;
+    int cols = 32;
+    while (cols < t.n_blk * N) cols <<= 1;
+    a.tmem_cols = cols;
+    a.tiles_x = ceil_div(d.Wo, t.TW);
+    a.tiles_y = ceil_div(d.Ho, t.TH);
+    const long tiles = (long)a.tiles_x * a.tiles_y * d.N * d.Do;
+    if (tiles > 0x7fffffffL) return DMVS_ERR_UNSUPPORTED;
+    a.total_tiles = (int)tiles;
+    const int per_sm = (t.smem <= 112 * 1024 && cols <= 256) ? 2 : 1;
+    const long max_grid = (long)kNumSMs * per_sm;
+    const int grid = (int)(tiles < max_grid ? tiles : max_grid);
+    KernelFn fn = passes == 3 ? pick_r<3>(t.R, d.in_stats != nullptr) : pick_r<1>(t.R, d.in_stats != nullptr);
+    fn<<<grid, kWsThreads, t.smem, st>>>(a);
+    const int rc = launch_status();
+    if (rc) return rc;
+    co_base += CC;
+    remaining -= CC;
+  }
+  return 0;
+}
+
+}  // namespace dmvs

@@ -16,7 +16,8 @@ from . import _cabi
 import os
 
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
-                    PREC_AUTO, PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
+                    PREC_AUTO, PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, PREC_WS_TF32, PREC_WS_TF32X3,
+                    RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
 # Arithmetic of the convolutions (storage is always fp32).  fp32-class modes (parity-safe, <= 4e-6 depth rel-L1):
 #   "auto"  (default)  per layer: tcgen05/TMEM 3xTF32 kernel for the FLOP-heavy stride-1 layers, FFMA2 kernel elsewhere
@@ -26,13 +27,71 @@ from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU
 # Plain-TF32 modes (NOT parity-safe on the synthetic weights: 1e-3..3e-3 depth rel-L1, 2-6 % index flips):
 #   "tf32", "tc_tf32"  operands rounded to TF32 - the numerics cuDNN uses under torch defaults
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
-              "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO}
+              "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO, "ws_tf32x3": PREC_WS_TF32X3, "ws_tf32": PREC_WS_TF32}
 _precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "auto")]
 
 
 def set_precision(name: str) -> None:
     global _precision
     _precision = PRECISIONS[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# Per-layer back-end autotuning ("auto" precision only).  The reference runs with `cudnn.benchmark = True`
+# (test.py:18): cuDNN times its algorithms the first time it sees a layer shape and keeps the fastest.  Same
+# here: the first call of a new convolution signature times every fp32-class back end that can run it (FFMA2,
+# tcgen05 tap-offset, tcgen05 width-stacked) on the live buffers and caches the winner for the process.  All
+# candidates meet the same parity class, so the choice only affects speed.  DMVS_AUTOTUNE=0 falls back to the
+# static rule inside dmvs_conv_f32.
+# ------------------------------------------------------------------------------------------------
+_AUTOTUNE = os.environ.get("DMVS_AUTOTUNE", "1") != "0"
+_AUTOTUNE_WS = os.environ.get("DMVS_AUTO_WS", "1") != "0"
+_TUNED: dict = {}
+_BACKEND_BITS = ((1, PREC_FP32), (4, PREC_TC_TF32X3), (8, PREC_WS_TF32X3))
+
+
+def set_autotune(enabled: bool, use_ws: Optional[bool] = None) -> None:
+    global _AUTOTUNE, _AUTOTUNE_WS
+    _AUTOTUNE = bool(enabled)
+    if use_ws is not None:
+        _AUTOTUNE_WS = bool(use_ws)
+    _TUNED.clear()
+
+
+def tuned_table() -> dict:
+    """signature -> (chosen precision code, {code: ms}) of every convolution tuned so far."""
+    return dict(_TUNED)
+
+
+def _tune(d: "ConvDesc", key) -> int:
+    lib = _cabi.lib()
+    mask = lib.dmvs_conv_backends(C.byref(d))
+    cands = [code for bit, code in _BACKEND_BITS if mask & bit and (code != PREC_WS_TF32X3 or _AUTOTUNE_WS)]
+    if torch.cuda.is_current_stream_capturing() or len(cands) < 2:
+        return PREC_AUTO if len(cands) >= 2 else cands[0]
+    stream = _stream()
+    stats, d.out_stats = d.out_stats, None        # accumulating statistics must not see the trial runs
+    times = {}
+    try:
+        for code in cands:
+            d.precision = code
+            if lib.dmvs_conv_f32(C.byref(d), stream) != 0:
+                continue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = float("inf")
+            for _ in range(3):
+                e0.record()
+                lib.dmvs_conv_f32(C.byref(d), stream)
+                e1.record()
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            times[code] = best
+    finally:
+        d.out_stats = stats
+    choice = min(times, key=times.get) if times else PREC_FP32
+    _TUNED[key] = (choice, times)
+    return choice
+
 
 
 def get_precision() -> str:
@@ -216,8 +275,8 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
     d.w_t, d.w_tc = _ptr(pc.w_t), _ptr(pc.w_tc)
     d.precision = _precision if pc.w_t is not None else PREC_FP32
-    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32) and pc.w_tc is None:
-        d.precision = PREC_TF32X3 if d.precision == PREC_TC_TF32X3 else PREC_TF32
+    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32) and pc.w_tc is None:
+        d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3) else PREC_TF32
     d.KD, d.KH, d.KW, d.stride = KD, KH, KW, stride
     d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
     d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps
@@ -233,6 +292,11 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     if aux2 is not None:
         d.aux2, d.aux2_ps = _ptr(aux2), pixel_stride(aux2, "conv aux2")
     d.out_stats = _ptr(out_stats)
+    if d.precision == PREC_AUTO and _AUTOTUNE:
+        key = (N, D, H, W, C1, C2, pc.cout, KD, KH, KW, stride, pd, ph, pw, int(in_up2), in_gn is not None, epi,
+               res_mode, int(res_up2), x_ps, x2_ps, y_ps)
+        hit = _TUNED.get(key)
+        d.precision = hit[0] if hit is not None else _tune(d, key)
     check(_cabi.lib().dmvs_conv_f32(C.byref(d), _stream()), "dmvs_conv_f32")
     return out
 

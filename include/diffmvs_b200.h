@@ -50,6 +50,8 @@ extern "C" {
 #define DMVS_PREC_TC_TF32X3 3 /* as TF32X3 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 1) */
 #define DMVS_PREC_AUTO 5      /* fp32-class; per layer: tcgen05 3xTF32 where it is faster, FFMA elsewhere */
 #define DMVS_PREC_TC_TF32 4   /* as TF32 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 2) */
+#define DMVS_PREC_WS_TF32X3 6 /* 3xTF32 on the width-stacked tcgen05 back end (conv_ws.cu) wherever it applies, FFMA elsewhere */
+#define DMVS_PREC_WS_TF32 7   /* plain TF32 on the width-stacked tcgen05 back end, legacy TF32 elsewhere */
 
 /* epilogue kinds */
 #define DMVS_EPI_STD 0
@@ -111,6 +113,11 @@ typedef struct dmvs_conv_desc {
 } dmvs_conv_desc;
 
 int dmvs_conv_f32(const dmvs_conv_desc* desc, void* stream);
+
+/* Which arithmetic back ends can run `desc` (bit 0: FFMA, bit 1: mma.sync, bit 2: tcgen05 with taps as descriptor
+ * offsets, bit 3: tcgen05 width-stacked).  Used by the host-side per-layer autotuner (the counterpart of the
+ * reference's `cudnn.benchmark = True`, test.py:18).  Launches nothing. */
+int dmvs_conv_backends(const dmvs_conv_desc* desc);
 
 /* ConvTranspose3d(k=3, s=2, p=1, output_padding=1) + folded BN + ReLU + skip add
  * (module.Deconv3d as used by CostRegNet_small, module.py:110-144,436-437,445-446).

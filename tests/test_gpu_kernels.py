@@ -32,10 +32,11 @@ def _nchw(y):  # GPU [N,H,W,C] -> CPU NCHW
     return y.permute(0, 3, 1, 2).contiguous().cpu()
 
 
-PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3, "tc_tf32x3": 2e-5, "tc_tf32": 3e-3, "auto": 2e-5}   # max-abs error relative to the output scale
+PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3, "tc_tf32x3": 2e-5, "tc_tf32": 3e-3, "auto": 2e-5,
+            "ws_tf32x3": 2e-5, "ws_tf32": 3e-3}   # max-abs error relative to the output scale
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32", "tc_tf32x3", "tc_tf32", "auto"])
+@pytest.fixture(params=["fp32", "tf32x3", "tf32", "tc_tf32x3", "tc_tf32", "auto", "ws_tf32x3", "ws_tf32"])
 def precision(request):
     old = ops.get_precision()
     ops.set_precision(request.param)
@@ -71,6 +72,13 @@ CONV_CASES = [
     (52, 20, (5, 1), 1, 16, 20),
     (16, 2, (1, 1), 1, 32, 40),
     (4, 1, (3, 3), 1, 17, 19),
+    # multi-tile / multi-block shapes for the persistent tcgen05 kernels
+    (16, 16, (3, 3), 1, 70, 150),
+    (8, 8, (3, 3), 1, 100, 260),
+    (64, 16, (3, 3), 1, 40, 200),
+    (32, 32, (3, 3), 1, 36, 100),
+    (64, 64, (1, 5), 1, 18, 50),
+    (64, 32, (5, 1), 1, 18, 50),
 ]
 
 
@@ -89,7 +97,7 @@ def test_conv2d_matches_torch(cin, cout, k, stride, H, W, precision):
 
 
 def test_conv2d_epilogues_and_views(precision):
-    if precision in ("tf32", "tc_tf32"):
+    if precision in ("tf32", "tc_tf32", "ws_tf32"):
         pytest.skip("epilogue logic is precision independent; covered by the fp32-class modes")
     N, H, W = 1, 24, 40
     x1, x2 = _rand(N, 16, H, W, seed=1), _rand(N, 8, H, W, seed=2)
@@ -174,7 +182,7 @@ def test_deconv3d_matches_torch(cin, cout):
 
 
 def test_groupnorm_pipeline_matches_resnet_block(precision):
-    if precision in ("tf32", "tc_tf32"):
+    if precision in ("tf32", "tc_tf32", "ws_tf32"):
         pytest.skip("covered by the fp32-class modes")
     """conv(+stats) -> conv(GN+SiLU prologue, +stats) -> groupnorm_silu_add == oracle resnet_block."""
     from diffmvs_b200 import pipeline

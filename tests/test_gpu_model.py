@@ -180,7 +180,7 @@ def test_full_size_against_oracle_on_device(workload, monkeypatch):
         assert e < 1e-3, (i, e)
     assert tuple(out["depth"][-1].shape) == (1, imgs[0].shape[2], imgs[0].shape[3])
 
-@pytest.mark.parametrize("mode,tol", [("tf32x3", DEPTH_TOL), ("tf32", 1e-2)])
+@pytest.mark.parametrize("mode,tol", [("tf32x3", DEPTH_TOL), ("ws_tf32x3", DEPTH_TOL), ("tf32", 1e-2)])
 @pytest.mark.parametrize("workload", ["cas_small", "cfg2"])
 def test_tensor_core_modes_meet_the_parity_bar(workload, mode, tol, monkeypatch):
     """The tensor-core convolution modes against the CPU oracle.  "tf32x3" (operand split) must stay in the
