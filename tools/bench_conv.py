@@ -41,11 +41,12 @@ LAYERS = [
     ("reg 8->8 3d", 1, 8, 8, (3, 3, 3), 1, (48, 144, 200)),
     ("reg 16->16 3d", 1, 16, 16, (3, 3, 3), 1, (24, 72, 100)),
 ]
-only = sys.argv[1] if len(sys.argv) > 1 and sys.argv[1] != "all" else None
+REPS = int(os.environ.get("BENCH_CONV_REPS", "10"))   # 1 under ncu: two launches per (layer, mode)
+only = sys.argv[1].split(",") if len(sys.argv) > 1 and sys.argv[1] != "all" else None
 modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["fp32", "tc_tf32x3", "ws_tf32x3"]
 print(f"{'layer':28s} " + " ".join(f"{m + ' ms':>13s}" for m in modes) + f" {'best':>10s} {'TFLOP/s':>8s} {'GB/s(io)':>9s}")
 for name, N, cin, cout, k, s, dims in LAYERS:
-    if only and only not in name:
+    if only and not any(o in name for o in only):
         continue
     g = torch.Generator().manual_seed(0)
     three_d = k[0] > 1 or dims[0] > 1
@@ -60,10 +61,10 @@ for name, N, cin, cout, k, s, dims in LAYERS:
         ops.set_precision(mode)
         try:
             y = ops.conv(x, pc, stride=s, act=ops.ACT_RELU)
-            for _ in range(2):
+            for _ in range(2 if REPS > 1 else 0):
                 ops.conv(x, pc, stride=s, act=ops.ACT_RELU, out=y)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 10
+            reps = REPS
             torch.cuda.synchronize()
             e0.record()
             for _ in range(reps):

@@ -23,5 +23,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"get_cost|plane_sweep|depth_regression|upsample_depth|aggregate" -c 8 \
    -o $O/warp_full -f python bench.py --steps 1 --warmup 3 --no-alt-modes --no-cpu-baseline > $O/ncu_warp.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_ws|conv_kernel|conv_tc" -c 12 \
-   -o $O/conv_full -f python tools/bench_conv.py "feat.out3" fp32,tc_tf32x3,ws_tf32x3 > $O/ncu_conv.log 2>&1
+   -o $O/conv_full -f env BENCH_CONV_REPS=1 python tools/bench_conv.py "feat.conv1.1,feat.out3,feat.conv0.1" fp32,ws_tf32x3 > $O/ncu_conv.log 2>&1
 ls -la $O
