@@ -169,6 +169,8 @@ def run_ours(a):
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
     model.load_state_dict(synth.synth_state_dict(shapes, 123), strict=False)
     model.to(dev).eval()
+    if not a.no_graph:
+        model.use_cuda_graph(True)   # public switch: the forward is captured once and replayed as one CUDA graph
 
     # each rank owns its own reference views (weak scaling: one ref-view per step per GPU)
     imgs, proj, dv = synth.workload_inputs(a.workload, seed=rank)
@@ -255,19 +257,21 @@ def run_ours(a):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        l0 = lib.dmvs_launch_count()
+        l0 = ops.launch_count()
         ms_dev, ms_wall = timed(step_resident, a.steps)
-        launches = lib.dmvs_launch_count() - l0
+        launches = ops.launch_count() - l0   # direct launches + kernels inside replayed graphs
         clocks = sampler.stop() if rank == 0 else None
         # end to end through the public API with host buffers
         d2h = step_e2e()
         step_e2e()
         _, e2e_wall = timed(step_e2e, a.steps)
         # per-kernel-family device time over one more step (CUDA events on the launch stream)
+        model.use_cuda_graph(False)          # per-call events need the eager path
         prof = ops.Profiler()
         ops.set_profiler(prof)
         step_resident()
         ops.set_profiler(None)
+        model.use_cuda_graph(not a.no_graph)
         summ = prof.summary() if rank == 0 else {}
         # the other arithmetic modes of the convolutions, device-resident timing only (same storage: fp32)
         alt = {}
@@ -323,7 +327,7 @@ def run_ours(a):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "precision": ops.get_precision(), "alt_modes": alt,
+        "data": "synthetic", "precision": ops.get_precision(), "cuda_graph": not a.no_graph, "alt_modes": alt,
         "config": {"workload": a.workload, "variant": variant, "image": [W, H], "views": V, "numdepth_initial": D0,
                    "numdepth": 384, "batch": 1, "l2": "inputs (155 MB at cfg3) and per-step working set exceed L2",
                    "parallelism": f"ref-views sharded, {world} GPU(s), no data-path collective"},
@@ -354,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-modes", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")
     ap.add_argument("--dump-tuned", default=None, help="write the per-layer autotuning table (JSON) to this path")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -174,6 +174,17 @@ __global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, float* __
   for (int c = 0; c < C; ++c) yp[c] = __ldg(xp + (int64_t)c * HW);
 }
 
+// RGB image planes [N][3][HW] -> [N][HW][4] with a zero fourth channel: one aligned 16-byte store per pixel, so
+// the first convolution of FeatureNet / ContextNet can stage its input with 128-bit asynchronous copies.
+__global__ void image_to_nhwc4_kernel(const float* __restrict__ x, float4* __restrict__ y, int HW, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t n = i / HW;
+  const int p = (int)(i - n * HW);
+  const float* xp = x + n * 3 * HW + p;
+  y[i] = make_float4(__ldg(xp), __ldg(xp + HW), __ldg(xp + 2 * (int64_t)HW), 0.0f);
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_ps, float* __restrict__ y, int C, int HW) {
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
@@ -282,6 +293,15 @@ extern "C" int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
   if (grid.z > 65535 || grid.y > 65535) return DMVS_ERR_UNSUPPORTED;
   nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, y, y_ps, C, HW);
+  return launch_status();
+}
+
+extern "C" int dmvs_image_to_nhwc4(const float* x, float* y, int32_t N, int32_t HW, void* stream) {
+  if (!x || !y || N <= 0 || HW <= 0) return DMVS_ERR_ARG;
+  if (!aligned16(y)) return DMVS_ERR_ALIGN;
+  const int64_t total = (int64_t)N * HW;
+  image_to_nhwc4_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<float4*>(y), HW, total);
   return launch_status();
 }
 

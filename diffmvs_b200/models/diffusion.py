@@ -68,6 +68,12 @@ class CasDiffMVS(_PlannedModule):
     def _build_plan(self, sd, device):
         return pipeline.CasDiffMVSPlan(sd, self.args, device, test=self.test)
 
+    def use_cuda_graph(self, enabled: bool = True) -> "CasDiffMVS":
+        """Replay the forward as one CUDA graph per input signature (captured on first use).  Results and
+        RNG consumption are those of the eager path; inputs must be CUDA tensors of a fixed shape."""
+        self._use_graph = bool(enabled)
+        return self
+
     def forward(self, imgs, proj_matrices, depth_values, depth_gt_ms=None):
         """`imgs`: list of V `[B,3,H,W]`; `proj_matrices`: dict stage1..4 -> `[B,V,2,4,4]`; `depth_values [B,N]`
         -> {"depth": [...], "conf": [], "photometric_confidence": [...]} (diffusion.py:139-295, test mode)."""
@@ -75,4 +81,7 @@ class CasDiffMVS(_PlannedModule):
             raise NotImplementedError("training-mode outputs (per-iteration lists, ground-truth injection) are out of "
                                       "scope: build with test=True (SURVEY.md section 2)")
         with torch.no_grad():
-            return self.plan(imgs[0].device).forward(imgs, proj_matrices, depth_values)
+            plan = self.plan(imgs[0].device)
+            if getattr(self, "_use_graph", False):
+                return plan.forward_graphed(imgs, proj_matrices, depth_values)
+            return plan.forward(imgs, proj_matrices, depth_values)

@@ -99,6 +99,19 @@ def get_precision() -> str:
 
 Tensor = torch.Tensor
 
+_replayed_launches = 0
+
+
+def count_replayed_launches(n: int) -> None:
+    """Kernels executed through CUDA-graph replays (the library's own counter only sees direct launches)."""
+    global _replayed_launches
+    _replayed_launches += n
+
+
+def launch_count() -> int:
+    """Kernels of libdiffmvs_b200.so run so far in this process: direct launches + graph-replayed ones."""
+    return int(_cabi.lib().dmvs_launch_count()) + _replayed_launches
+
 
 class Profiler:
     """Optional per-call CUDA-event timing of the kernel entry points (used by bench.py / tools; off by default).
@@ -488,6 +501,21 @@ def to_nhwc(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     xc = x.contiguous()
     check(_cabi.lib().dmvs_nchw_to_nhwc(_ptr(xc), _ptr(out), pixel_stride(out, "out"), N, Cc, H * W, _stream()),
           "dmvs_nchw_to_nhwc")
+    return out
+
+
+@_profiled("to_nhwc")
+def image_to_nhwc4(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """RGB image batch [N,3,H,W] -> [N,H,W,4] (fourth channel zero)."""
+    _req_cuda_f32(x, "image")
+    N, Cc, H, W = x.shape
+    if Cc != 3:
+        raise ValueError(f"image_to_nhwc4: expected 3 channels, got {Cc}")
+    if out is None:
+        out = torch.empty((N, H, W, 4), device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != (N, H, W, 4) or not out.is_contiguous():
+        raise ValueError("image_to_nhwc4: out must be a dense [N,H,W,4] tensor")
+    check(_cabi.lib().dmvs_image_to_nhwc4(_ptr(x.contiguous()), _ptr(out), N, H * W, _stream()), "dmvs_image_to_nhwc4")
     return out
 
 

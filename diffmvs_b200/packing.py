@@ -32,11 +32,14 @@ def rna_tf32(x: torch.Tensor) -> torch.Tensor:
     return ((bits + 0x1000) & -8192).view(torch.float32)
 
 
-def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None) -> PackedConv:
-    """w [Cout,Cin,KH,KW] or [Cout,Cin,KD,KH,KW] -> PackedConv ([KD,KH,KW,cin_pad,cout_pad])."""
+def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None, pad_cin: int = 0) -> PackedConv:
+    """w [Cout,Cin,KH,KW] or [Cout,Cin,KD,KH,KW] -> PackedConv ([KD,KH,KW,cin_pad,cout_pad]).
+    `pad_cin` > Cin appends zero input channels (RGB images are staged with a zero fourth channel)."""
     w = w.detach().float().cpu()
     if w.dim() == 4:
         w = w.unsqueeze(2)
+    if pad_cin > w.shape[1]:
+        w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, pad_cin - w.shape[1]))
     cout, cin, kd, kh, kw = w.shape
     packed = torch.zeros(kd, kh, kw, _pad4(cin), _pad4(cout), dtype=torch.float32)
     packed[:, :, :, :cin, :cout] = w.permute(2, 3, 4, 1, 0)
@@ -61,14 +64,14 @@ def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:
     return scale, shift
 
 
-def pack_conv_bn(sd: SD, p: str) -> PackedConv:
+def pack_conv_bn(sd: SD, p: str, pad_cin: int = 0) -> PackedConv:
     """`module.Conv2d/Conv3d/ConvBnReLU/ConvBn`: conv (no bias) followed by eval BN."""
     w = sd[p + ".conv.weight"].float()
     scale, shift = bn_scale_shift(sd, p + ".bn")
     w = w * scale.view(-1, *([1] * (w.dim() - 1)))
     if (p + ".conv.bias") in sd:
         shift = shift + sd[p + ".conv.bias"].float() * scale
-    return pack_weight(w, shift)
+    return pack_weight(w, shift, pad_cin)
 
 
 def pack_conv(sd: SD, p: str, gain: float = 1.0, rows: Optional[slice] = None) -> PackedConv:

@@ -53,6 +53,7 @@ class FeatureNetPlan:
         self.cas = cas
         up = lambda pc: pc.to(device)
         self.c0 = [up(packing.pack_conv_bn(sd, f"conv0.{i}")) for i in range(2)]
+        self.c0_rgb0 = up(packing.pack_conv_bn(sd, "conv0.0", pad_cin=4))   # for [N,H,W,4] zero-padded RGB input
         self.lv = [[up(packing.pack_conv_bn(sd, f"conv{l}.{i}")) for i in range(3)] for l in (1, 2, 3)]
         self.out1 = up(packing.pack_conv(sd, "out1"))
         self.inner1 = up(packing.pack_conv(sd, "inner1"))
@@ -62,8 +63,9 @@ class FeatureNetPlan:
             self.out3 = up(packing.pack_conv(sd, "out3"))
 
     def __call__(self, x: Tensor) -> Dict[str, Tensor]:
-        """x [N,H,W,3] -> {"stage1": [N,H/8,W/8,48], "stage2": [N,H/4,W/4,32], ["stage3": [N,H/2,W/2,16]]}."""
-        x = ops.conv(x, self.c0[0], act=ACT_RELU)
+        """x [N,H,W,3] (or [N,H,W,4] with a zero fourth channel) -> {"stage1": [N,H/8,W/8,48],
+        "stage2": [N,H/4,W/4,32], ["stage3": [N,H/2,W/2,16]]}."""
+        x = ops.conv(x, self.c0_rgb0 if x.shape[-1] == 4 else self.c0[0], act=ACT_RELU)
         x = ops.conv(x, self.c0[1], act=ACT_RELU)
         levels = []
         for l in range(3):
@@ -93,6 +95,7 @@ class ContextNetPlan:
         self.out_dim = list(out_dim)
         self.hidden_dim = list(hidden_dim)
         self.conv1 = up(packing.pack_conv_bn(sd, "conv1"))
+        self.conv1_rgb0 = up(packing.pack_conv_bn(sd, "conv1", pad_cin=4))
         self.layers = []
         for li in (1, 2, 3):
             blocks = []
@@ -122,7 +125,7 @@ class ContextNetPlan:
         return ops.conv(y, blk["c2"], act=ACT_RELU, res=x, res_mode=RES_PRE_ACT)
 
     def trunk(self, x: Tensor) -> Dict[int, Tensor]:
-        x = ops.conv(x, self.conv1, act=ACT_RELU)
+        x = ops.conv(x, self.conv1_rgb0 if x.shape[-1] == 4 else self.conv1, act=ACT_RELU)
         feats = {}
         for li, blocks in enumerate(self.layers):
             x = self._block(x, blocks[0], 2)
@@ -428,10 +431,10 @@ class CasDiffMVSPlan:
         interval0 = 1.0 / depth_values.size(1)
 
         # all views through FeatureNet as one batch (the reference loops, diffusion.py:156-157)
-        x_all = torch.empty((V, B, H, W, 3), device=dev, dtype=torch.float32)
+        x_all = torch.empty((V, B, H, W, 4), device=dev, dtype=torch.float32)   # RGB + one zero channel
         for v, im in enumerate(imgs):
-            ops.to_nhwc(im.float(), out=x_all[v])
-        feats = self.feature(x_all.view(V * B, H, W, 3))
+            ops.image_to_nhwc4(im.float(), out=x_all[v])
+        feats = self.feature(x_all.view(V * B, H, W, 4))
         ctx_feats = self.context.trunk(x_all[0])
 
         slots = sum(b.stats_slots() for b in self.blocks.values())
@@ -489,3 +492,59 @@ class CasDiffMVSPlan:
                     taps[f"{key}_mask"] = mask
                     taps[f"{key}_hidden0"] = hidden
         return {"depth": depths, "conf": [], "photometric_confidence": confs}
+
+    # --------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the whole forward: ~800 kernel launches per
+    # reference view become one graph launch, so the refinement loop runs with no host involvement.
+    # --------------------------------------------------------------------------------------------
+    def forward_graphed(self, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor
+                        ) -> Dict[str, List[Tensor]]:
+        key = (tuple(imgs[0].shape), len(imgs), tuple((k, tuple(v.shape)) for k, v in sorted(proj_matrices.items())),
+               tuple(depth_values.shape), ops.get_precision())
+        graphs = self.__dict__.setdefault("_graphs", {})
+        g = graphs.get(key)
+        if g is None:
+            g = graphs[key] = GraphedForward(self, imgs, proj_matrices, depth_values)
+        return g(imgs, proj_matrices, depth_values)
+
+
+class GraphedForward:
+    """One captured `CasDiffMVSPlan.forward` for a fixed input signature.  Inputs are copied into static
+    buffers, the graph is replayed, results are returned as fresh tensors (the caller owns them, as with the
+    eager path).  `torch.randn_like` inside the graph keeps drawing from the default CUDA generator (torch
+    advances its Philox offset per replay), so noise semantics are those of the eager path."""
+
+    def __init__(self, plan: "CasDiffMVSPlan", imgs, proj_matrices, depth_values):
+        dev = imgs[0].device
+        self.imgs = [torch.empty(i.shape, device=dev, dtype=torch.float32) for i in imgs]
+        self.proj = {k: torch.empty(v.shape, device=dev, dtype=torch.float32) for k, v in proj_matrices.items()}
+        self.dv = torch.empty(depth_values.shape, device=dev, dtype=torch.float32)
+        self._load(imgs, proj_matrices, depth_values)
+        rng = torch.cuda.get_rng_state(dev)  # the warm-up must not consume the caller's noise stream
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):       # eager warm-up: autotunes every layer, fills the allocator
+            for _ in range(2):
+                plan.forward(self.imgs, self.proj, self.dv)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        torch.cuda.set_rng_state(rng, dev)
+        from . import _cabi
+        before = _cabi.lib().dmvs_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = plan.forward(self.imgs, self.proj, self.dv)
+        self.launches = int(_cabi.lib().dmvs_launch_count() - before)
+
+    def _load(self, imgs, proj_matrices, depth_values):
+        for dst, src in zip(self.imgs, imgs):
+            dst.copy_(src, non_blocking=True)
+        for k, dst in self.proj.items():
+            dst.copy_(proj_matrices[k], non_blocking=True)
+        self.dv.copy_(depth_values, non_blocking=True)
+
+    def __call__(self, imgs, proj_matrices, depth_values):
+        self._load(imgs, proj_matrices, depth_values)
+        self.graph.replay()
+        ops.count_replayed_launches(self.launches)
+        return {k: [t.clone() for t in v] for k, v in self.out.items()}

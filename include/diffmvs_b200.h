@@ -208,6 +208,10 @@ int dmvs_ddim_step(float* img, const float* delta, const float* noise, float k_r
 int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int32_t B, int32_t H, int32_t W, int32_t factor,
                           void* stream);
 
+/* Input images (datasets/mvs.py:93-97: [N][3][H][W], RGB in [0,1]) -> channels-last [N][HW][4] with a zero
+ * fourth channel, the layout the first convolutions (module.py:332,364) stage with 128-bit copies. */
+int dmvs_image_to_nhwc4(const float* x, float* y, int32_t N, int32_t HW, void* stream);
+
 /* layout transposes between the reference's NCHW operator surface and channels-last */
 int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t N, int32_t C, int32_t HW, void* stream);
 int dmvs_nhwc_to_nchw(const float* x, int32_t x_ps, float* y, int32_t N, int32_t C, int32_t HW, void* stream);
