@@ -29,7 +29,7 @@ class ConvDesc(C.Structure):
         ("N", i32), ("D", i32), ("H", i32), ("W", i32),
         ("C1", i32), ("C2", i32), ("x_ps", i32), ("x2_ps", i32), ("in_up2", i32),
         ("in_stats", C.c_void_p), ("in_g1", f32p), ("in_g0", f32p), ("in_inv_count", C.c_float),
-        ("w", f32p), ("w_t", f32p), ("w_tc", f32p), ("precision", i32), ("bias", f32p),
+        ("w", f32p), ("w_t", f32p), ("w_tc", f32p), ("w_ws", f32p), ("precision", i32), ("bias", f32p),
         ("KD", i32), ("KH", i32), ("KW", i32), ("stride", i32), ("pad_d", i32), ("pad_h", i32), ("pad_w", i32),
         ("y", f32p), ("Do", i32), ("Ho", i32), ("Wo", i32), ("Cout", i32), ("y_ps", i32),
         ("act", i32), ("act_c0", i32), ("res_mode", i32), ("res", f32p), ("res_ps", i32), ("res_up2", i32),
@@ -86,7 +86,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.dmvs_abi_version() != 1:
+        if handle.dmvs_abi_version() != 2:
             raise KernelLibraryError("ABI version mismatch between _cabi.py and the built library")
         _LIB = handle
     return _LIB

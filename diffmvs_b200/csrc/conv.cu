@@ -242,7 +242,7 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     static const double ws_min_macs = getenv("DMVS_WS_MIN_MACS") ? atof(getenv("DMVS_WS_MIN_MACS")) : 0.0;
     const long kred = (long)d.KD * d.KH * d.KW * (d.C1 + d.C2);
     const double macs = (double)kred * d.Cout * d.N * d.Do * d.Ho * d.Wo;
-    if (d.w_tc && conv_ws_supported(d) && kred >= ws_min_k && macs >= ws_min_macs)
+    if (conv_ws_supported(d) && kred >= ws_min_k && macs >= ws_min_macs)
       return dispatch_conv_ws(d, static_cast<cudaStream_t>(stream));
     if (d.precision == DMVS_PREC_WS_TF32 && d.w_t) {
       dmvs_conv_desc alt = d;
@@ -336,7 +336,7 @@ extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   int mask = 1;                                        // bit 0: FFMA kernel (always)
   if (d.w_t) mask |= 2;                                // bit 1: legacy mma.sync kernel
   if (d.w_tc && conv_tc_supported(d)) mask |= 4;       // bit 2: tcgen05 kernel, taps as descriptor offsets
-  if (d.w_tc && conv_ws_supported(d)) mask |= 8;       // bit 3: tcgen05 kernel, kernel-row taps stacked along N
+  if (conv_ws_supported(d)) mask |= 8;       // bit 3: tcgen05 kernel, kernel-row taps stacked along N
   return mask;
 }
 

@@ -49,11 +49,14 @@ struct WsArgs {
   int vec_y, vec_res;
   int Hs, Ws;
   float inv_in_cols;
-  int64_t w_lo_off; // offset (floats) of the lo weights inside w_tc
+  int lanes_row;    // threads that share one tile row in the loader (32..256, power of two >= 2*in_cols when possible)
+  int64_t w_off;    // offset (floats) of this launch's hi slabs inside w_ws
+  int64_t w_plane;  // distance (floats) from a hi slab to its lo twin
 };
 
 struct Stage {
   int tile, kd, chunk;
+  int n, od, ty0, tx0;   // decoded once per tile (the divisions are not free in a loop that runs per 8 channels)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -103,6 +106,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-byte asynchronous copy without the src-size operand (the zero-fill form costs ~10 extra instructions of
+// pointer fix-ups per copy in SASS); padding is written with a plain shared store instead.
+__device__ __forceinline__ void cp_async16_full(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
 template <int R>
 __device__ __forceinline__ void cp_async_wait_ring() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(R - 2) : "memory");
@@ -145,8 +154,6 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
   const int Ctot = d.C1 + d.C2;
   const int units_per_row = a.in_cols * 2;       // 16-byte units per tile row (two channel quads per stage)
   const int nchunks = a.cin_pad >> 3;
-  const int taps = d.KH * d.KW;
-  const int qtot = a.cin_pad >> 2;
 
   auto decode = [&](int tile, int& n, int& od, int& ty0, int& tx0) {
     const int tx = tile % a.tiles_x;
@@ -161,11 +168,10 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
   auto kd_first = [&](int od) { const int v = d.pad_d - od; return v > 0 ? v : 0; };
   auto kd_last = [&](int od) { const int v = d.D - 1 + d.pad_d - od; return v < d.KD - 1 ? v : d.KD - 1; };
   auto first_stage_of = [&](int tile) {
-    Stage s{tile, 0, 0};
+    Stage s{tile, 0, 0, 0, 0, 0, 0};
     if (tile < a.total_tiles) {
-      int n, od, ty0, tx0;
-      decode(tile, n, od, ty0, tx0);
-      s.kd = kd_first(od);
+      decode(tile, s.n, s.od, s.ty0, s.tx0);
+      s.kd = kd_first(s.od);
     }
     return s;
   };
@@ -173,61 +179,61 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
     Stage s = c;
     if (++s.chunk < nchunks) return s;
     s.chunk = 0;
-    int n, od, ty0, tx0;
-    decode(c.tile, n, od, ty0, tx0);
-    if (++s.kd <= kd_last(od)) return s;
+    if (++s.kd <= kd_last(c.od)) return s;
     return first_stage_of(c.tile + (int)gridDim.x);
   };
 
-  // loads of one stage into ring slot `slot`: raw halo tile (planar by channel quad) and its weight slab
+  // loads of one stage into ring slot `slot`: raw halo tile (planar by channel quad) and its weight slab.
+  // A thread owns a fixed (column, channel quad) unit of the tile and walks down the rows, so the per-copy work is
+  // a row predicate, one 64-bit multiply-add and the cp.async itself (the loader used to dominate the
+  // instruction stream: profiles/r1b_ncu_conv_ffma_vs_ws_v1.txt).
+  const int ld_u0 = tid & (a.lanes_row - 1);
+  const int ld_r0 = tid / a.lanes_row;
+  const int ld_rstep = kWsThreads / a.lanes_row;
   auto issue_loads = [&](const Stage& s, int slot) {
     if (s.tile < a.total_tiles) {
-      int n, od, ty0, tx0;
-      decode(s.tile, n, od, ty0, tx0);
       const int c0 = s.chunk * 8;
-      const int id = od + s.kd - d.pad_d;
-      const int iy0 = ty0 - d.pad_h, ix0 = tx0 - d.pad_w;
+      const int id = s.od + s.kd - d.pad_d;
+      const int iy0 = s.ty0 - d.pad_h, ix0 = s.tx0 - d.pad_w;
       float* a_raw = pair0 + slot * a.stage_f;
+      const int64_t img = (int64_t)(s.n * d.D + id) * a.Hs;
 #pragma unroll 1
-      for (int row = warp; row < a.in_rows; row += kWsThreads / 32) {
-        const int iy = iy0 + row;
-        const bool row_ok = iy >= 0 && iy < d.H;
-        const int sy = d.in_up2 ? (iy >> 1) : iy;
-        const int64_t row_pix = ((int64_t)(n * d.D + id) * a.Hs + sy) * a.Ws;
-        const int row_off = row * a.in_cols;
-#pragma unroll 1
-        for (int u = lane; u < units_per_row; u += 32) {
-          const int q = u & 1;
-          const int col = u >> 1;
-          const int ix = ix0 + col;
-          const int ch = c0 + q * 4;
-          const bool ok = row_ok && ix >= 0 && ix < d.W && ch < Ctot;
-          const int sx = d.in_up2 ? (ix >> 1) : ix;
-          const int64_t pix = row_pix + sx;
-          const float* src = d.x;
-          if (ok) src = ch < d.C1 ? d.x + pix * d.x_ps + ch : d.x2 + pix * d.x2_ps + (ch - d.C1);
-          cp_async16(a_raw + (q * a.plane + row_off + col) * 4, src, ok);
+      for (int u = ld_u0; u < units_per_row; u += a.lanes_row) {
+        const int q = u & 1;
+        const int col = u >> 1;
+        const int ix = ix0 + col;
+        const int ch = c0 + q * 4;
+        const bool col_ok = ix >= 0 && ix < d.W && ch < Ctot;
+        const int sx = d.in_up2 ? (ix >> 1) : ix;
+        // pointer to (image row 0, column sx, channel ch) of this stage's depth slice; rows add sy * row_stride
+        const bool from_x = ch < d.C1;
+        const int ps = from_x ? d.x_ps : d.x2_ps;
+        const float* base = from_x ? d.x + ch : d.x2 + (ch - d.C1);
+        if (!col_ok) base = d.x;
+        const float* colp = base + (col_ok ? (img * a.Ws + sx) * ps : 0);
+        const int row_stride = a.Ws * ps;            // one image plane stays below 2^31 floats (checked on the host)
+        float* dst = a_raw + (q * a.plane + ld_r0 * a.in_cols + col) * 4;
+        const int dst_step = ld_rstep * a.in_cols * 4;
+        const int up = d.in_up2 ? 1 : 0;
+#pragma unroll 2
+        for (int row = ld_r0; row < a.in_rows; row += ld_rstep, dst += dst_step) {
+          const int iy = iy0 + row;
+          if (col_ok && iy >= 0 && iy < d.H) {
+            cp_async16_full(dst, colp + (iy >> up) * row_stride);
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // zero padding
+          }
         }
       }
-      // weights of this (kd, channel chunk): global [kd][kh*KW+kw][quad][cout_pad][4] -> shared [kh][quad][N][4],
-      // N index = kw*CC + c (columns past KW*CC are zero filled)
-      const int q0 = c0 >> 2;
+      // weights of this (kd, channel chunk): the host packed every slab [kh][quad][N][4] contiguously (w_ws)
       float* wh = w_hi0 + slot * wslab_f;
       float* wl = w_lo0 + slot * wslab_f;
-      const int wunits = d.KH * 2 * N;
-#pragma unroll 1
+      const float* src = d.w_ws + a.w_off + (int64_t)(s.kd * nchunks + s.chunk) * wslab_f;
+      const int wunits = wslab_f >> 2;
+#pragma unroll 2
       for (int idx = tid; idx < wunits; idx += kWsThreads) {
-        const int j = idx % N;
-        const int r = idx / N;
-        const int q = r & 1;
-        const int kh = r >> 1;
-        const int kw = j / a.CC;
-        const int c = j - kw * a.CC;
-        const bool ok = kw < d.KW && q0 + q < qtot;
-        const int64_t off =
-            ((((int64_t)s.kd * taps + kh * d.KW + kw) * qtot + q0 + q) * a.cout_pad + a.co_base + c) * 4;
-        cp_async16(wh + idx * 4, ok ? d.w_tc + off : d.w_tc, ok);
-        if (PASSES == 3) cp_async16(wl + idx * 4, ok ? d.w_tc + a.w_lo_off + off : d.w_tc, ok);
+        cp_async16_full(wh + idx * 4, src + idx * 4);
+        if (PASSES == 3) cp_async16_full(wl + idx * 4, src + a.w_plane + idx * 4);
       }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");   // always one group per stage slot (possibly empty)
@@ -250,8 +256,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
       ++waited;
     };
     for (;;) {
-      int n, od, ty0, tx0;
-      decode(cur.tile, n, od, ty0, tx0);
+      const int n = cur.n, od = cur.od, ty0 = cur.ty0, tx0 = cur.tx0;
       cp_async_wait_ring<R>();                           // everything but the newest R-2 groups has landed
       if (GN && n != gn_n) {                             // GroupNorm affine of the producer is per sample
         for (int c = tid; c < d.C1; c += kWsThreads) groupnorm_affine(d, n, c, gn_s);
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
         const int total = 2 * a.plane;
         const int iy0 = ty0 - d.pad_h, ix0 = tx0 - d.pad_w;
         const int c0 = cur.chunk * 8;
-#pragma unroll 1
+#pragma unroll 2
         for (int u = tid; u < total; u += kWsThreads) {
           float4 v = *reinterpret_cast<const float4*>(a_hi + u * 4);
           if (GN) {
@@ -506,73 +511,94 @@ KernelFn pick_r(int r, bool gn) {
 }
 
 struct TileCfg {
-  int TH = 0, TW = 0, in_cols = 0, n_blk = 0, plane = 0, R = 0, stage_f = 0;
+  int TH = 0, TW = 0, in_cols = 0, n_blk = 0, plane = 0, R = 0, stage_f = 0, ctas = 0;
   size_t smem = 0;
-  double score = 0.0;
+  double est = 1e30;   // modelled cycles for the whole launch
 };
 
-// Tile search: maximise useful output pixels per unit of (MMA rows + staged positions) under the shared-memory
-// and TMEM budget of `ctas_per_sm` co-resident CTAs.
-TileCfg choose_tile(const dmvs_conv_desc& d, int N, int CCE, int passes, int ctas_per_sm) {
-  const size_t smem_limit = ctas_per_sm == 2 ? 112 * 1024 : 216 * 1024;
-  const int tmem_limit = ctas_per_sm == 2 ? 256 : 512;
-  const int max_blk = tmem_limit / N;
-  TileCfg best;
+// Tile search.  For every (tile height, M blocks, CTAs per SM) that fits shared memory and TMEM, a rough cycle
+// model of one tile (MMA time, split pass, copy issue, exposed latency, epilogue) times the number of tile waves
+// is evaluated and the cheapest configuration wins.  The model only has to rank shapes; constants are from the
+// ncu captures under profiles/.
+void choose_tile(const dmvs_conv_desc& d, int N, int CC, int CCE, int passes, int cin_pad, TileCfg& best) {
   static const int force_th = getenv("DMVS_WS_TH") ? atoi(getenv("DMVS_WS_TH")) : 0;   // tuning aids
   static const int force_r = getenv("DMVS_WS_R") ? atoi(getenv("DMVS_WS_R")) : 0;
-  for (int th = 16; th >= 1; th >>= 1) {
-    if (th > 1 && th / 2 >= d.Ho) continue;          // a shorter tile already covers the image height
-    if (force_th && th != force_th) continue;
-    for (int nb = max_blk; nb >= 1; --nb) {
-      const int cols_max = nb * 128 / th;            // in_cols such that th*in_cols <= nb*128
-      const int tw_max = cols_max - (d.KW - 1);
-      if (tw_max < 8 && tw_max < d.Wo) continue;
-      if (tw_max < 1) continue;
-      const int ntx = ceil_div(d.Wo, tw_max);
-      const int TW = ceil_div(d.Wo, ntx);
-      const int in_cols = TW + d.KW - 1;
-      const int m_total = th * in_cols;
-      const int n_blk = ceil_div(m_total, 128);
-      if (n_blk > max_blk) continue;
-      const int plane = (n_blk * 128 + (d.KH - 1) * in_cols + 8 + 7) & ~7;
-      size_t work_f = (size_t)(passes == 3 ? 2 : 1) * 2 * plane * 4;
-      const size_t ring_f = (size_t)kRingRows * (d.KW * CCE + 4);
-      if (work_f < ring_f) work_f = ring_f;
-      work_f = (work_f + 31) & ~(size_t)31;
-      const size_t wslab_f = (size_t)d.KH * 2 * N * 4;
-      for (int r = 3; r >= 2; --r) {
-        if (force_r && r != force_r) continue;
-        const size_t need = (r * work_f + (passes == 3 ? 2 : 1) * r * wslab_f + 2 * (size_t)d.C1 + 8) * 4;
-        if (need > smem_limit) continue;
-        const double useful = (double)th * TW;
-        const double cost = (double)n_blk * 128 * (1.0 + 0.15 * d.KH) + 0.6 * (double)(th + d.KH - 1) * in_cols +
-                            (r == 2 ? 0.08 : 0.0) * n_blk * 128 + 96.0;   // + fixed per-tile overhead
-        const double score = useful / cost;
-        if (score > best.score) {
-          best.TH = th; best.TW = TW; best.in_cols = in_cols; best.n_blk = n_blk; best.plane = plane; best.R = r;
-          best.stage_f = (int)work_f; best.smem = need; best.score = score;
+  static const int force_ctas = getenv("DMVS_WS_CTAS") ? atoi(getenv("DMVS_WS_CTAS")) : 0;
+  const int nchunks = cin_pad >> 3;
+  for (int ctas = 2; ctas >= 1; --ctas) {
+    if (force_ctas && ctas != force_ctas) continue;
+    const size_t smem_limit = ctas == 2 ? 112 * 1024 : 216 * 1024;
+    const int max_blk = (ctas == 2 ? 256 : 512) / N;
+    for (int th = 16; th >= 1; th >>= 1) {
+      if (th > 1 && th / 2 >= d.Ho) continue;          // a shorter tile already covers the image height
+      if (force_th && th != force_th) continue;
+      for (int nb = max_blk; nb >= 1; --nb) {
+        const int cols_max = nb * 128 / th;            // in_cols such that th*in_cols <= nb*128
+        int tw_max = cols_max - (d.KW - 1);
+        if (tw_max > 250) tw_max = 250;
+        if (tw_max < 1 || (tw_max < 8 && tw_max < d.Wo)) continue;
+        const int ntx = ceil_div(d.Wo, tw_max);
+        const int TW = ceil_div(d.Wo, ntx);
+        const int in_cols = TW + d.KW - 1;
+        const int in_rows = th + d.KH - 1;
+        const int n_blk = ceil_div(th * in_cols, 128);
+        if (n_blk > max_blk) continue;
+        const int plane = (n_blk * 128 + (d.KH - 1) * in_cols + 8 + 7) & ~7;
+        size_t work_f = (size_t)(passes == 3 ? 2 : 1) * 2 * plane * 4;
+        const size_t ring_f = (size_t)kRingRows * (d.KW * CCE + 4);
+        if (work_f < ring_f) work_f = ring_f;
+        work_f = (work_f + 31) & ~(size_t)31;
+        const size_t wslab_f = (size_t)d.KH * 2 * N * 4;
+        for (int r = 3; r >= 2; --r) {
+          if (force_r && r != force_r) continue;
+          const size_t need = (r * work_f + (passes == 3 ? 2 : 1) * r * wslab_f + 2 * (size_t)d.C1 + 8) * 4;
+          if (need > smem_limit) continue;
+          // ---- cycle model ------------------------------------------------------------------------
+          const double mma = (double)n_blk * d.KH * passes * (N / 2 > 32 ? N / 2 : 32);   // A read 32 clk or math N/2
+          const double split = passes == 3 || d.in_stats ? 2.0 * plane / kWsThreads * (d.in_stats ? 45.0 : 24.0) : 0.0;
+          const double copies = (2.0 * in_rows * in_cols * 10.0 + wslab_f / 4.0 * passes * 6.0) / kWsThreads;
+          const double issue = (split + copies) * 8.0 / 4.0 + 200.0;        // 8 warps over 4 schedulers + barriers
+          const double latency = r == 3 ? 600.0 : 1500.0;                    // exposed copy latency per stage
+          double stage = (mma > latency ? mma : latency) + issue;
+          if (ctas == 2) stage = stage * 0.5 > mma + 0.5 * issue ? stage * 0.5 : mma + 0.5 * issue;   // two CTAs interleave
+          const int stages = nchunks * d.KD;
+          const double epi = (double)n_blk * (CC / CCE) * (250.0 + 128.0 * (CCE / 4) / kWsThreads * (60.0 + 8.0 * d.KW) * 2.0);
+          const double tile = stages * stage + (ctas == 2 ? 0.6 : 1.0) * epi + 300.0;
+          const long tiles = (long)ntx * ceil_div(d.Ho, th) * d.N * d.Do;
+          const double waves = (double)ceil_div64(tiles, (int64_t)kNumSMs);   // per SM
+          const double est = waves * tile;
+          if (est < best.est) {
+            best.TH = th; best.TW = TW; best.in_cols = in_cols; best.n_blk = n_blk; best.plane = plane; best.R = r;
+            best.stage_f = (int)work_f; best.smem = need; best.est = est; best.ctas = ctas;
+          }
         }
-        break;   // deepest ring that fits for this shape
       }
     }
   }
-  return best;
+}
+
+// Output-channel chunking shared with the host packer (packing.py::pack_ws): chunks of at most cc_max channels.
+inline int ws_cc_max(int KW) {
+  int cc = (256 / KW) & ~7;
+  return cc > 64 ? 64 : cc;
 }
 
 }  // namespace
 
 bool conv_ws_supported(const dmvs_conv_desc& d) {
-  if (d.w_tc == nullptr || d.stride != 1 || d.KH > 16 || d.KW > 8) return false;
+  if (d.w_ws == nullptr || d.stride != 1 || d.KH > 16 || d.KW > 8) return false;
   const bool vec_x = aligned16(d.x) && (d.x_ps % 4 == 0) && (d.C1 % 4 == 0);
   const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
   if (!vec_x || !vec_x2) return false;
   if (d.in_stats != nullptr && (d.in_up2 || d.C2 != 0 || !aligned16(d.in_g1) || !aligned16(d.in_g0))) return false;
+  const int64_t ps_max = d.x_ps > d.x2_ps ? d.x_ps : d.x2_ps;
+  if ((int64_t)d.H * d.W * ps_max >= (1ll << 31)) return false;   // 32-bit row offsets inside one image plane
   return true;
 }
 
 int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
-  if (!aligned16(d.w_tc)) return DMVS_ERR_ALIGN;
   if (!conv_ws_supported(d)) return DMVS_ERR_UNSUPPORTED;
+  if (!aligned16(d.w_ws)) return DMVS_ERR_ALIGN;
   const int passes = d.precision == DMVS_PREC_WS_TF32 ? 1 : 3;
   WsArgs a;
   a.d = d;
@@ -582,20 +608,19 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
   a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
-  a.w_lo_off = (int64_t)d.KD * d.KH * d.KW * (a.cin_pad / 4) * a.cout_pad * 4;
 
-  int cc_max = (256 / d.KW) & ~7;
-  if (cc_max > 64) cc_max = 64;
+  const int cc_max = ws_cc_max(d.KW);
   if (cc_max < 8) return DMVS_ERR_UNSUPPORTED;
   int remaining = (d.Cout + 7) & ~7, co_base = 0;
+  int64_t w_off = 0;
   while (remaining > 0) {
     const int CC = remaining < cc_max ? remaining : cc_max;
     const int N = (d.KW * CC + 15) & ~15;
     int CCE = CC;
     if (d.KW * CC > 64) CCE = (d.KW * 16 <= 64 && CC % 16 == 0) ? 16 : 8;
     if (256 % (CCE / 4) != 0) CCE = 8;   // a thread keeps one channel quad: quads per pass must divide the block
-    TileCfg t = choose_tile(d, N, CCE, passes, 2);
-    if (!t.TH) t = choose_tile(d, N, CCE, passes, 1);
+    TileCfg t;
+    choose_tile(d, N, CC, CCE, passes, a.cin_pad, t);
     if (!t.TH) return DMVS_ERR_UNSUPPORTED;
     a.co_base = co_base;
     a.CC = CC;
@@ -610,6 +635,13 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
     a.n_blk = t.n_blk;
     a.stage_f = t.stage_f;
     a.inv_in_cols = 1.0f / (float)t.in_cols;
+    int lanes = 32;
+    while (lanes < 2 * t.in_cols && lanes < kWsThreads) lanes <<= 1;
+    a.lanes_row = lanes;
+    // packed slabs of this chunk: [hi | lo][KD][cin_pad/8][KH][2][N][4]
+    const int64_t plane_w = (int64_t)d.KD * (a.cin_pad >> 3) * d.KH * 2 * N * 4;
+    a.w_off = w_off;
+    a.w_plane = plane_w;
     int cols = 32;
     while (cols < t.n_blk * N) cols <<= 1;
     a.tmem_cols = cols;
@@ -618,8 +650,7 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
     const long tiles = (long)a.tiles_x * a.tiles_y * d.N * d.Do;
     if (tiles > 0x7fffffffL) return DMVS_ERR_UNSUPPORTED;
     a.total_tiles = (int)tiles;
-    const int per_sm = (t.smem <= 112 * 1024 && cols <= 256) ? 2 : 1;
-    const long max_grid = (long)kNumSMs * per_sm;
+    const long max_grid = (long)kNumSMs * t.ctas;
     const int grid = (int)(tiles < max_grid ? tiles : max_grid);
     KernelFn fn = passes == 3 ? pick_r<3>(t.R, d.in_stats != nullptr) : pick_r<1>(t.R, d.in_stats != nullptr);
     fn<<<grid, kWsThreads, t.smem, st>>>(a);
@@ -627,6 +658,7 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
     if (rc) return rc;
     co_base += CC;
     remaining -= CC;
+    w_off += 2 * plane_w;
   }
   return 0;
 }

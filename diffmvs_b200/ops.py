@@ -223,11 +223,12 @@ class PackedConv:
     k: Tuple[int, int, int]
     w_t: Optional[Tensor] = None   # tensor-core layout [KD,KH,KW,cout_pad8,cin_pad8]
     w_tc: Optional[Tensor] = None  # tcgen05 layout [2(hi,lo),KD,KH*KW,cin_pad8/4,cout_pad16,4]
+    w_ws: Optional[Tensor] = None  # width-stacked tcgen05 slabs (packing.pack_ws)
 
     def to(self, device) -> "PackedConv":
-        return PackedConv(self.w.to(device), None if self.bias is None else self.bias.to(device), self.cin,
-                          self.cout, self.k, None if self.w_t is None else self.w_t.to(device),
-                          None if self.w_tc is None else self.w_tc.to(device))
+        mv = lambda t: None if t is None else t.to(device)
+        return PackedConv(self.w.to(device), mv(self.bias), self.cin, self.cout, self.k, mv(self.w_t), mv(self.w_tc),
+                          mv(self.w_ws))
 
 
 @dataclass
@@ -286,7 +287,7 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         d.in_stats, d.in_g1, d.in_g0 = _ptr(in_gn.stats), _ptr(in_gn.g1), _ptr(in_gn.g0)
         d.in_inv_count = 1.0 / float(D * H * W * (C1 // 4))
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
-    d.w_t, d.w_tc = _ptr(pc.w_t), _ptr(pc.w_tc)
+    d.w_t, d.w_tc, d.w_ws = _ptr(pc.w_t), _ptr(pc.w_tc), _ptr(pc.w_ws)
     d.precision = _precision if pc.w_t is not None else PREC_FP32
     if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32) and pc.w_tc is None:
         d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3) else PREC_TF32

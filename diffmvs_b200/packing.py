@@ -55,7 +55,38 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None, pad_cin: i
     hi = rna_tf32(quad)
     lo = rna_tf32(quad - hi)
     w_tc = torch.stack((hi, lo), 0).contiguous()
-    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc)
+    w_ws = pack_ws(full.view(kd, kh, kw, ci8, co16), cout) if kw <= 8 else None
+    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc, w_ws)
+
+
+def ws_cc_max(kw: int) -> int:
+    """Output channels per launch of the width-stacked kernel (mirrors `ws_cc_max` in csrc/conv_ws.cu)."""
+    return min(64, (256 // kw) & ~7)
+
+
+def pack_ws(full: torch.Tensor, cout: int) -> torch.Tensor:
+    """full [KD,KH,KW,cin_pad8,cout_pad16] -> flat width-stacked slabs (include/diffmvs_b200.h, `w_ws`): for every
+    output-channel chunk (CC channels, N = KW*CC rounded up to 16) the planes hi = rna_tf32(w), lo = rna_tf32(w - hi),
+    each [KD][cin_pad8/8][KH][2][N][4]; column kw*CC + c holds tap kw of output channel co_base + c."""
+    kd, kh, kw, ci8, co16 = full.shape
+    cc_max = ws_cc_max(kw)
+    remaining, co_base, parts = (cout + 7) & ~7, 0, []
+    while remaining > 0:
+        cc = min(remaining, cc_max)
+        n = (kw * cc + 15) & ~15
+        blk = torch.zeros(kd, kh, kw, ci8, cc, dtype=torch.float32)
+        avail = min(cc, co16 - co_base)
+        blk[..., :avail] = full[..., co_base:co_base + avail]
+        # [kd][kh][kw][chunk][quad][4][cc] -> [kd][chunk][kh][quad][kw][cc][4]
+        blk = blk.view(kd, kh, kw, ci8 // 8, 2, 4, cc).permute(0, 3, 1, 4, 2, 6, 5).reshape(kd, ci8 // 8, kh, 2, kw * cc, 4)
+        slab = torch.zeros(kd, ci8 // 8, kh, 2, n, 4, dtype=torch.float32)
+        slab[..., :kw * cc, :] = blk
+        hi = rna_tf32(slab)
+        lo = rna_tf32(slab - hi)
+        parts += [hi.reshape(-1), lo.reshape(-1)]
+        co_base += cc
+        remaining -= cc
+    return torch.cat(parts).contiguous()
 
 
 def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:

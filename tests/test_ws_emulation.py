@@ -1,7 +1,7 @@
 """CPU emulation of the index arithmetic of the width-stacked tcgen05 convolution (csrc/conv_ws.cu).
 
 The kernel cannot run without a GPU, but everything that is easy to get wrong in it is integer bookkeeping:
-the planar-by-channel-quad operand layout, the weight slab gathered from the packed `w_tc` layout, the
+the planar-by-channel-quad operand layout, the host-packed weight slabs (`w_ws`), the
 kernel-row descriptor offsets, the N = KW*CC column order, the 136-row staging ring and the shift-add
 windows of the epilogue.  This test replays exactly that bookkeeping with numpy (one "MMA" = one matmul of a
 128-row operand slice) and checks the result against `F.conv2d`.  It mirrors the kernel's variable names.
@@ -29,10 +29,20 @@ def emulate_ws_conv(x, pc, TH, TW, CC, CCE, co_base=0):
     cout_pad = (Cout + 15) & ~15
     qtot = cin_pad // 4
     taps = KH * KW
-    w_tc = pc.w_tc.numpy()                       # [2][KD][taps][qtot][cout_pad][4]
-    assert w_tc.shape == (2, 1, taps, qtot, cout_pad, 4)
-    w_flat = w_tc.reshape(2, -1)
     N = (KW * CC + 15) & ~15
+    # this launch's packed slabs: the chunks before co_base come first in w_ws (packing.pack_ws)
+    w_ws = pc.w_ws.numpy()
+    nchunks = cin_pad // 8
+    cc_max = packing.ws_cc_max(KW)
+    w_off, rem, base = 0, (Cout + 7) & ~7, 0
+    while base < co_base:
+        cc = min(rem, cc_max)
+        w_off += 2 * KD * nchunks * KH * 2 * ((KW * cc + 15) & ~15) * 4
+        base += cc
+        rem -= cc
+    assert base == co_base and CC == min(rem, cc_max), "test case must follow the kernel's channel chunking"
+    wslab_f = KH * 2 * N * 4
+    w_plane = KD * nchunks * wslab_f
     in_rows, in_cols = TH + KH - 1, TW + KW - 1
     m_total = TH * in_cols
     n_blk = -(-m_total // 128)
@@ -60,19 +70,8 @@ def emulate_ws_conv(x, pc, TH, TW, CC, CCE, co_base=0):
                                 v[:len(seg)] = seg
                             A[q, row * in_cols + col] = v
                 # ---- weight slab [kh][quad][N][4] from the packed global layout ---------------------------
-                q0 = c0 >> 2
-                slab = np.zeros((KH * 2 * N, 4))
-                for idx in range(KH * 2 * N):
-                    j = idx % N
-                    r = idx // N
-                    q = r & 1
-                    kh = r >> 1
-                    kw = j // CC
-                    c = j - kw * CC
-                    ok = kw < KW and q0 + q < qtot
-                    if ok:
-                        off = ((((0 * taps + kh * KW + kw) * qtot + q0 + q) * cout_pad + co_base + c) * 4)
-                        slab[idx] = w_flat[0, off:off + 4] + w_flat[1, off:off + 4]      # hi + lo
+                src = w_off + (0 * nchunks + chunk) * wslab_f
+                slab = (w_ws[src:src + wslab_f] + w_ws[src + w_plane:src + w_plane + wslab_f]).astype(np.float64)  # hi + lo
                 slab = slab.reshape(KH, 2, N, 4)
                 # ---- MMAs: per block and kernel row one instruction, N columns ---------------------------
                 for blk in range(n_blk):
@@ -140,4 +139,20 @@ def test_ws_bookkeeping_matches_conv2d(cin, cout, k, H, W, TH, TW, CC, CCE):
     got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, TH, TW, CC, CCE)
     assert not np.isnan(got).any(), "some output was never written"
     # hi + lo of the packed weights reproduces the fp32 weights to ~2^-22 relative
+    assert np.abs(got - ref).max() < 1e-6
+
+
+def test_ws_output_channel_chunks():
+    """Cout = 80 with a 3-wide kernel runs as two launches (64 + 16 channels) over consecutive `w_ws` chunks."""
+    g = torch.Generator().manual_seed(2)
+    cin, cout, k, H, W = 8, 80, (3, 3), 9, 20
+    x = torch.rand(1, cin, H, W, generator=g) - 0.5
+    w = (torch.rand(cout, cin, *k, generator=g) - 0.5) / math.sqrt(cin * 9)
+    pc = packing.pack_weight(w, None)
+    ref = F.conv2d(x.double(), w.double(), padding=1)[0].permute(1, 2, 0).numpy()
+    xin = x[0].permute(1, 2, 0).double().numpy()
+    lo = emulate_ws_conv(xin, pc, 4, 20, 64, 16, co_base=0)
+    hi = emulate_ws_conv(xin, pc, 4, 20, 16, 16, co_base=64)
+    assert np.isnan(lo[..., 64:]).all() and np.isnan(hi[..., :64]).all()
+    got = np.where(np.isnan(lo), hi, lo)
     assert np.abs(got - ref).max() < 1e-6

@@ -1,0 +1,21 @@
+#!/usr/bin/env bash
+# GPU call: ws kernel v2 (cheap loaders), CUDA-graph forward, per-layer comparison, ncu of the ws kernel.
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 400 python -m pytest tests/test_gpu_kernels.py -k "ws_tf32 or auto" -q --tb=short -p no:cacheprovider > $O/pytest_ws.log 2>&1
+echo "pytest_ws rc=$?" >> $O/pytest_ws.log
+tail -4 $O/pytest_ws.log
+timeout 400 python tools/bench_conv.py all fp32,tc_tf32x3,ws_tf32x3,ws_tf32 > $O/bench_conv.log 2>&1
+echo "bench_conv rc=$?" >> $O/bench_conv.log
+timeout 500 python -m pytest tests/test_gpu_model.py -k "ws_tf32x3 or golden or graph or feature" -q --tb=short -p no:cacheprovider > $O/pytest_model.log 2>&1
+echo "pytest_model rc=$?" >> $O/pytest_model.log
+tail -4 $O/pytest_model.log
+timeout 500 python bench.py --steps 10 --warmup 3 --no-alt-modes --dump-tuned $O/tuned.json > $O/bench.log 2>&1
+echo "bench rc=$?" >> $O/bench.log
+tail -2 $O/bench.log | cut -c1-400
+timeout 300 python bench.py --steps 10 --warmup 3 --no-alt-modes --no-cpu-baseline --no-graph > $O/bench_nograph.log 2>&1
+echo "bench_nograph rc=$?" >> $O/bench_nograph.log
+tail -2 $O/bench_nograph.log | cut -c1-400
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_ws" -c 6 \
+   -o $O/ws_full -f env BENCH_CONV_REPS=1 python tools/bench_conv.py "feat.conv1.1,feat.out3,feat.conv0.1" ws_tf32x3 > $O/ncu_ws.log 2>&1
+ls -la $O
