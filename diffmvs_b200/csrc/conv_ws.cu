@@ -29,7 +29,6 @@ namespace dmvs {
 namespace {
 
 constexpr int kWsThreads = 256;
-constexpr int kRingRows = 136;   // epilogue staging ring: one 128-row M block + the <= 8 trailing rows of the previous one
 
 struct WsArgs {
   dmvs_conv_desc d;
@@ -37,7 +36,6 @@ struct WsArgs {
   int cout_pad;     // pitch of the packed weights (Cout rounded up to 16)
   int co_base;      // first output channel of this launch
   int CC;           // output channels of this launch (multiple of 8)
-  int CCE;          // output channels per epilogue pass (multiple of 8, KW*CCE <= 64)
   int N;            // MMA N = KW*CC rounded up to 16
   int TH, TW, in_rows, in_cols;
   int m_total;      // TH * in_cols flattened positions carry results
@@ -45,7 +43,7 @@ struct WsArgs {
   int n_blk;        // M=128 blocks per tile
   int tmem_cols;    // allocated TMEM columns (power of two >= 32)
   int tiles_x, tiles_y, total_tiles;
-  int stage_f;      // floats per ring slot: operand pair [hi | lo]; doubles as epilogue staging
+  int stage_f;      // floats per ring slot: operand pair [hi | lo]; doubles as the epilogue's halo exchange buffer
   int vec_y, vec_res;
   int Hs, Ws;
   float inv_in_cols;
@@ -94,6 +92,15 @@ __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+
+// x = hi + lo + r with hi, lo exactly representable in TF32 and |r| < 2^-21 |x|.  hi is x rounded to nearest
+// (integer add of half an ulp, then mask - the same result as cvt.rna.tf32.f32 for finite values, which ptxas expands
+// to four instructions on sm_100a); lo = x - hi is exact in fp32 and is truncated to TF32 explicitly, so the
+// result does not depend on what the tensor core does with the 13 low mantissa bits.  4 instructions per value.
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -293,10 +300,10 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
           }
           if (PASSES == 3) {
             float4 h, l;
-            h.x = rna_tf32(v.x); l.x = rna_tf32(v.x - h.x);
-            h.y = rna_tf32(v.y); l.y = rna_tf32(v.y - h.y);
-            h.z = rna_tf32(v.z); l.z = rna_tf32(v.z - h.z);
-            h.w = rna_tf32(v.w); l.w = rna_tf32(v.w - h.w);
+            split_tf32(v.x, h.x, l.x);
+            split_tf32(v.y, h.y, l.y);
+            split_tf32(v.z, h.z, l.z);
+            split_tf32(v.w, h.w, l.w);
             *reinterpret_cast<float4*>(a_hi + u * 4) = h;
             *reinterpret_cast<float4*>(a_lo + u * 4) = l;
           } else {
@@ -350,132 +357,148 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
         // ---- all MMAs of the tile retired -> shift-add epilogue ------------------------------------------------
         while (waited < issued) wait_one();
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        float* ring = pair0 + slot * a.stage_f;   // this stage's pair is dead now: [kRingRows][SP] staging ring
-        const int CCE = a.CCE;
-        const int SP = d.KW * CCE + 4;            // ring row pitch (odd number of 16-byte units: conflict-free)
-        const int N4 = CCE >> 2;                  // channel quads per epilogue pass (2, 4, ... 16)
-        const int g_per_kw = CCE >> 3;            // 8-column TMEM groups per tap
-        const int groups = d.KW * g_per_kw;
+        // A lane owns one accumulator row (position p) and 8 output channels: tap kw of its output lives in row
+        // p + kw, i.e. in lane + kw of the same warp (a shuffle) or, for the last KW-1 lanes, in the first rows of
+        // the next lane quadrant / next M block (a small shared "halo" written in a first pass).  Work items are
+        // (M block, channel octet) pairs, split between the two warp halves (warp % 4 = TMEM lane quadrant).
+        float* halo = pair0 + slot * a.stage_f;   // this stage's pair is dead now: [item][quadrant][kw-1][lane][8]
+        const int ncg = a.CC >> 3;
+        const int n_items = a.n_blk * ncg;
         const int quadrant = warp & 3, half = warp >> 2;
-        const int q4 = tid % N4;                  // fixed channel quad per thread (256 % N4 == 0)
+        const int KWm1 = d.KW - 1;
+        const int halo_q = KWm1 * KWm1 * 8;       // floats per (item, quadrant)
         const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
         const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
         const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
+        if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
+        if (KWm1 > 0) {
 #pragma unroll 1
-        for (int e0 = 0; e0 < a.CC; e0 += CCE) {
-          const int cq = a.co_base + e0 + q4 * 4;   // first absolute output channel of this thread's quad
-          if (a.co_base + e0 >= d.Cout) break;      // block-uniform: the whole pass is channel padding
-          float bias[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (d.bias != nullptr && cq + k < d.Cout) bias[k] = __ldg(d.bias + cq + k);
-          const bool full_quad = cq + 4 <= d.Cout;
-          float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};
-          if (tid < 8) stat_s[tid] = 0.0f;
+          for (int it = half; it < n_items; it += 2) {          // pass 1: rows other quadrants will need
+            const int blk = it / ncg, cg = it - blk * ncg;
+            const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
+            float* hq = halo + (it * 4 + quadrant) * halo_q;
 #pragma unroll 1
-          for (int blk = 0; blk < a.n_blk; ++blk) {
-            // phase A: TMEM rows of this block -> ring rows (lane quadrant = warp % 4; the two warp halves split the groups)
-            {
-              const int m = quadrant * 32 + lane;
-              float* rrow = ring + ((blk * 128 + m) % kRingRows) * SP;
-              const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + e0);
-#pragma unroll 1
-              for (int g = half; g < groups; g += 2) {
-                const int kw = g / g_per_kw;
-                const int sub = g - kw * g_per_kw;
-                float v[8];
-                tmem_ld8(trow + (uint32_t)(kw * a.CC + sub * 8), v);
-                float* dst = rrow + kw * CCE + sub * 8;
+            for (int kw = 1; kw < d.KW; ++kw) {
+              float v[8];
+              tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
+              if (lane < kw) {
+                float* dst = hq + ((kw - 1) * KWm1 + lane) * 8;
                 *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
               }
             }
-            __syncthreads();
-            // phase B: positions [blk*128 - (KW-1), blk*128 + 128 - (KW-1)) have all their KW rows in the ring now
-            if (cq < d.Cout) {
+          }
+        }
+        __syncthreads();
 #pragma unroll 1
-              for (int m = tid / N4; m < 128; m += kWsThreads / N4) {
-                const int p = blk * 128 - (d.KW - 1) + m;
-                if (p < 0) continue;
-                const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
-                const int px = p - py * a.in_cols;
-                const int oy = ty0 + py, ox = tx0 + px;
-                if (px >= a.TW || py >= a.TH || oy >= d.Ho || ox >= d.Wo) continue;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int kw = 0; kw < d.KW; ++kw) {
-                  const float4 t4 =
-                      *reinterpret_cast<const float4*>(ring + ((p + kw) % kRingRows) * SP + kw * CCE + q4 * 4);
-                  v[0] += t4.x; v[1] += t4.y; v[2] += t4.z; v[3] += t4.w;
-                }
+        for (int it = half; it < n_items; it += 2) {            // pass 2: shift-add, fused epilogue, store
+          const int blk = it / ncg, cg = it - blk * ncg;
+          const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
+          const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
+          const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
+          float acc[8];
+          tmem_ld8(trow, acc);
+#pragma unroll 1
+          for (int kw = 1; kw < d.KW; ++kw) {
+            float v[8];
+            tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] += bias[k];
-                const int64_t opix = (img_base + oy) * d.Wo + ox;
-                int64_t rpix = opix;
-                if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
-                if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
-                  float r[4] = {0.f, 0.f, 0.f, 0.f};
-                  if (d.res_mode != DMVS_RES_NONE) {
-                    const float* rp = d.res + rpix * d.res_ps + cq;
-                    if (a.vec_res && full_quad) {
-                      const float4 r4 = ldg4(rp);
-                      r[0] = r4.x; r[1] = r4.y; r[2] = r4.z; r[3] = r4.w;
-                    } else {
+            for (int j = 0; j < 8; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
+            if (lane + kw >= 32) {                              // the row lives in the next quadrant / block
+              if (have_next) {
+                const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * 8;
+                const float4 h0 = *reinterpret_cast<const float4*>(src), h1 = *reinterpret_cast<const float4*>(src + 4);
+                v[0] = h0.x; v[1] = h0.y; v[2] = h0.z; v[3] = h0.w;
+                v[4] = h1.x; v[5] = h1.y; v[6] = h1.z; v[7] = h1.w;
+              } else {
 #pragma unroll
-                      for (int k = 0; k < 4; ++k)
-                        if (cq + k < d.Cout) r[k] = __ldg(rp + k);
-                    }
-                  }
-                  const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    float x = pre_act ? v[k] + r[k] : v[k];
-                    if (cq + k >= relu_from) x = fmaxf(x, 0.0f);
-                    v[k] = pre_act ? x : x + r[k];
-                  }
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (cq + k < d.Cout) v[k] = epilogue_value(d, v[k], cq + k, opix, rpix);
-                }
-                if (d.out_stats != nullptr) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) {
-                    gs[k] += v[k];
-                    gq[k] += v[k] * v[k];
-                  }
-                }
-                float* yp = d.y + opix * d.y_ps + cq;
-                if (a.vec_y && full_quad) {
-                  *reinterpret_cast<float4*>(yp) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    if (cq + k < d.Cout) yp[k] = v[k];
-                }
+                for (int j = 0; j < 8; ++j) v[j] = 0.0f;        // past the last block: never a valid output
               }
             }
-            __syncthreads();   // ring rows are rewritten by the next block / the next pass / the next stage's loads
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+          }
+          const int c0 = a.co_base + cg * 8;                    // first absolute output channel of this lane
+          const int p = blk * 128 + quadrant * 32 + lane;
+          const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
+          const int px = p - py * a.in_cols;
+          const int oy = ty0 + py, ox = tx0 + px;
+          const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};   // per channel pair: sum, sum of squares
+          if (valid) {
+            const bool full8 = c0 + 8 <= d.Cout;
+            if (d.bias != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (full8 || c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
+            }
+            const int64_t opix = (img_base + oy) * d.Wo + ox;
+            int64_t rpix = opix;
+            if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+            if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+              float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+              if (d.res_mode != DMVS_RES_NONE) {
+                const float* rp = d.res + rpix * d.res_ps + c0;
+                if (a.vec_res && full8) {
+                  const float4 r0 = ldg4(rp), r1 = ldg4(rp + 4);
+                  r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
+                  r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k)
+                    if (c0 + k < d.Cout) r[k] = __ldg(rp + k);
+                }
+              }
+              const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float x = pre_act ? acc[k] + r[k] : acc[k];
+                if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
+                acc[k] = pre_act ? x : x + r[k];
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (c0 + k < d.Cout) acc[k] = epilogue_value(d, acc[k], c0 + k, opix, rpix);
+            }
+            float* yp = d.y + opix * d.y_ps + c0;
+            if (a.vec_y && full8) {
+              *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+              *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (c0 + k < d.Cout) yp[k] = acc[k];
+            }
+            if (d.out_stats != nullptr) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float x = c0 + k < d.Cout ? acc[k] : 0.0f;
+                ps[k >> 1] += x;
+                pq[k >> 1] += x * x;
+              }
+            }
           }
           if (d.out_stats != nullptr) {
-            const int cpg = d.Cout / 4;
+            // GroupNorm statistics: Cout/4 channels per group is 2, 4 or a multiple of 8 (checked on the host), so a
+            // channel pair never straddles two groups
+            const int cpg = d.Cout >> 2;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float s = gs[k], q = gq[k];
-              for (int o = 16; o >= N4; o >>= 1) {   // lanes l, l+N4, ... of a warp share a channel quad
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                q += __shfl_xor_sync(0xffffffffu, q, o);
-              }
-              const int c = cq + k;
-              if (lane < N4 && c < d.Cout) {
+            for (int j = 0; j < 4; ++j) {
+              const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
+              const int c = c0 + 2 * j;
+              if (lane == 0 && c < d.Cout) {
                 const int g = c / cpg;
                 atomicAdd(&stat_s[g * 2 + 0], s);
                 atomicAdd(&stat_s[g * 2 + 1], q);
               }
             }
-            __syncthreads();
-            if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
-            __syncthreads();
           }
+        }
+        __syncthreads();   // halo reads done before the next stage's loads land here; statistics complete
+        if (d.out_stats != nullptr) {
+          if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+          __syncthreads();
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads done before the next tile's MMAs
       }
@@ -520,7 +543,7 @@ struct TileCfg {
 // model of one tile (MMA time, split pass, copy issue, exposed latency, epilogue) times the number of tile waves
 // is evaluated and the cheapest configuration wins.  The model only has to rank shapes; constants are from the
 // ncu captures under profiles/.
-void choose_tile(const dmvs_conv_desc& d, int N, int CC, int CCE, int passes, int cin_pad, TileCfg& best) {
+void choose_tile(const dmvs_conv_desc& d, int N, int CC, int passes, int cin_pad, TileCfg& best) {
   static const int force_th = getenv("DMVS_WS_TH") ? atoi(getenv("DMVS_WS_TH")) : 0;   // tuning aids
   static const int force_r = getenv("DMVS_WS_R") ? atoi(getenv("DMVS_WS_R")) : 0;
   static const int force_ctas = getenv("DMVS_WS_CTAS") ? atoi(getenv("DMVS_WS_CTAS")) : 0;
@@ -545,8 +568,8 @@ void choose_tile(const dmvs_conv_desc& d, int N, int CC, int CCE, int passes, in
         if (n_blk > max_blk) continue;
         const int plane = (n_blk * 128 + (d.KH - 1) * in_cols + 8 + 7) & ~7;
         size_t work_f = (size_t)(passes == 3 ? 2 : 1) * 2 * plane * 4;
-        const size_t ring_f = (size_t)kRingRows * (d.KW * CCE + 4);
-        if (work_f < ring_f) work_f = ring_f;
+        const size_t halo_f = (size_t)n_blk * (CC / 8) * 4 * (d.KW - 1) * (d.KW - 1) * 8;   // epilogue halo exchange
+        if (work_f < halo_f) work_f = halo_f;
         work_f = (work_f + 31) & ~(size_t)31;
         const size_t wslab_f = (size_t)d.KH * 2 * N * 4;
         for (int r = 3; r >= 2; --r) {
@@ -562,7 +585,7 @@ void choose_tile(const dmvs_conv_desc& d, int N, int CC, int CCE, int passes, in
           double stage = (mma > latency ? mma : latency) + issue;
           if (ctas == 2) stage = stage * 0.5 > mma + 0.5 * issue ? stage * 0.5 : mma + 0.5 * issue;   // two CTAs interleave
           const int stages = nchunks * d.KD;
-          const double epi = (double)n_blk * (CC / CCE) * (250.0 + 128.0 * (CCE / 4) / kWsThreads * (60.0 + 8.0 * d.KW) * 2.0);
+          const double epi = (double)n_blk * (CC / 8) * (60.0 + 37.0 * d.KW) + 200.0;
           const double tile = stages * stage + (ctas == 2 ? 0.6 : 1.0) * epi + 300.0;
           const long tiles = (long)ntx * ceil_div(d.Ho, th) * d.N * d.Do;
           const double waves = (double)ceil_div64(tiles, (int64_t)kNumSMs);   // per SM
@@ -593,6 +616,10 @@ bool conv_ws_supported(const dmvs_conv_desc& d) {
   if (d.in_stats != nullptr && (d.in_up2 || d.C2 != 0 || !aligned16(d.in_g1) || !aligned16(d.in_g0))) return false;
   const int64_t ps_max = d.x_ps > d.x2_ps ? d.x_ps : d.x2_ps;
   if ((int64_t)d.H * d.W * ps_max >= (1ll << 31)) return false;   // 32-bit row offsets inside one image plane
+  if (d.out_stats != nullptr) {   // the epilogue reduces GroupNorm statistics per channel pair
+    const int cpg = d.Cout / 4;
+    if ((d.Cout % 4) != 0 || !(cpg == 2 || cpg == 4 || cpg % 8 == 0)) return false;
+  }
   return true;
 }
 
@@ -616,15 +643,11 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
   while (remaining > 0) {
     const int CC = remaining < cc_max ? remaining : cc_max;
     const int N = (d.KW * CC + 15) & ~15;
-    int CCE = CC;
-    if (d.KW * CC > 64) CCE = (d.KW * 16 <= 64 && CC % 16 == 0) ? 16 : 8;
-    if (256 % (CCE / 4) != 0) CCE = 8;   // a thread keeps one channel quad: quads per pass must divide the block
     TileCfg t;
-    choose_tile(d, N, CC, CCE, passes, a.cin_pad, t);
+    choose_tile(d, N, CC, passes, a.cin_pad, t);
     if (!t.TH) return DMVS_ERR_UNSUPPORTED;
     a.co_base = co_base;
     a.CC = CC;
-    a.CCE = CCE;
     a.N = N;
     a.TH = t.TH;
     a.TW = t.TW;

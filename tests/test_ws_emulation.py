@@ -2,8 +2,7 @@
 
 The kernel cannot run without a GPU, but everything that is easy to get wrong in it is integer bookkeeping:
 the planar-by-channel-quad operand layout, the host-packed weight slabs (`w_ws`), the
-kernel-row descriptor offsets, the N = KW*CC column order, the 136-row staging ring and the shift-add
-windows of the epilogue.  This test replays exactly that bookkeeping with numpy (one "MMA" = one matmul of a
+kernel-row descriptor offsets, the N = KW*CC column order and the shuffle / halo shift-add of the epilogue.  This test replays exactly that bookkeeping with numpy (one "MMA" = one matmul of a
 128-row operand slice) and checks the result against `F.conv2d`.  It mirrors the kernel's variable names.
 """
 import math
@@ -15,10 +14,7 @@ import torch.nn.functional as F
 
 from diffmvs_b200 import packing
 
-RING = 136
-
-
-def emulate_ws_conv(x, pc, TH, TW, CC, CCE, co_base=0):
+def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0):
     """x [H,W,Cin] (numpy), pc PackedConv (2-D) -> y [H,W,Cout] via the kernel's data movement."""
     H, W, Cin = x.shape
     KD, KH, KW = pc.k
@@ -47,7 +43,6 @@ def emulate_ws_conv(x, pc, TH, TW, CC, CCE, co_base=0):
     m_total = TH * in_cols
     n_blk = -(-m_total // 128)
     plane = (n_blk * 128 + (KH - 1) * in_cols + 8 + 7) & ~7
-    SP = KW * CCE + 4
     y = np.full((H, W, Cout), np.nan, dtype=np.float64)
     rng = np.random.default_rng(0)
     for ty0 in range(0, H, TH):
@@ -80,63 +75,67 @@ def emulate_ws_conv(x, pc, TH, TW, CC, CCE, co_base=0):
                         a_op = np.concatenate([A[0, a_off:a_off + 128], A[1, a_off:a_off + 128]], axis=1)   # [128][8]
                         b_op = np.concatenate([slab[kh, 0], slab[kh, 1]], axis=1)                          # [N][8]
                         E[blk * 128:(blk + 1) * 128] += a_op @ b_op.T
-            # ---- shift-add epilogue through the ring --------------------------------------------------------
-            N4 = CCE // 4
-            for e0 in range(0, CC, CCE):
-                if co_base + e0 >= Cout:
-                    break
-                ring = np.full((RING, SP), np.nan)
-                for blk in range(n_blk):
-                    for m in range(128):                      # phase A
-                        rrow = (blk * 128 + m) % RING
-                        for g in range(KW * (CCE // 8)):
-                            kw = g // (CCE // 8)
-                            sub = g - kw * (CCE // 8)
-                            col = kw * CC + e0 + sub * 8
-                            ring[rrow, kw * CCE + sub * 8: kw * CCE + sub * 8 + 8] = E[blk * 128 + m, col:col + 8]
-                    for m in range(128):                      # phase B
-                        p = blk * 128 - (KW - 1) + m
-                        if p < 0:
-                            continue
+            # ---- shift-add epilogue: lane = accumulator row, shuffles inside a warp, halo across warps ---------
+            ncg = CC // 8
+            n_items = n_blk * ncg
+            halo = {}
+            for it in range(n_items):                          # pass 1
+                blk, cg = divmod(it, ncg)
+                for quadrant in range(4):
+                    for kw in range(1, KW):
+                        for lane in range(kw):
+                            row = blk * 128 + quadrant * 32 + lane
+                            halo[(it, quadrant, kw, lane)] = E[row, kw * CC + cg * 8: kw * CC + cg * 8 + 8].copy()
+            for it in range(n_items):                          # pass 2
+                blk, cg = divmod(it, ncg)
+                c0 = co_base + cg * 8
+                for quadrant in range(4):
+                    have_next = quadrant < 3 or blk + 1 < n_blk
+                    itn, qn = (it if quadrant < 3 else it + ncg), (quadrant + 1) & 3
+                    for lane in range(32):
+                        p = blk * 128 + quadrant * 32 + lane
+                        acc = E[p, cg * 8: cg * 8 + 8].copy()
+                        for kw in range(1, KW):
+                            if lane + kw < 32:                  # __shfl_down_sync(v, kw): the row of lane + kw
+                                v = E[p + kw, kw * CC + cg * 8: kw * CC + cg * 8 + 8]
+                            elif have_next:
+                                v = halo[(itn, qn, kw, lane + kw - 32)]
+                            else:
+                                v = np.zeros(8)
+                            acc = acc + v
                         py = int((np.float32(p) + np.float32(0.5)) * np.float32(1.0 / in_cols))
                         px = p - py * in_cols
                         oy, ox = ty0 + py, tx0 + px
-                        if px >= TW or py >= TH or oy >= H or ox >= W:
+                        if not (px < TW and py < TH and oy < H and ox < W and c0 < Cout):
                             continue
-                        for q4 in range(N4):
-                            cq = co_base + e0 + q4 * 4
-                            if cq >= Cout:
-                                continue
-                            v = np.zeros(4)
-                            for kw in range(KW):
-                                v += ring[(p + kw) % RING, kw * CCE + q4 * 4: kw * CCE + q4 * 4 + 4]
-                            for k in range(4):
-                                if cq + k < Cout:
-                                    assert np.isnan(y[oy, ox, cq + k]), "output written twice"
-                                    y[oy, ox, cq + k] = v[k]
+                        for k in range(8):
+                            if c0 + k < Cout:
+                                assert np.isnan(y[oy, ox, c0 + k]), "output written twice"
+                                y[oy, ox, c0 + k] = acc[k]
     return y
 
 
 CASES = [
-    # cin, cout, (kh,kw), H, W, TH, TW, CC, CCE
-    (8, 8, (3, 3), 20, 37, 8, 16, 8, 8),
-    (16, 16, (3, 3), 17, 40, 4, 30, 16, 16),
-    (12, 20, (3, 3), 16, 24, 8, 24, 24, 8),
-    (8, 16, (7, 7), 18, 30, 4, 26, 16, 8),
-    (8, 40, (1, 5), 9, 33, 2, 33, 40, 8),
-    (8, 20, (5, 1), 12, 20, 4, 20, 24, 8),
-    (16, 32, (3, 3), 10, 22, 2, 22, 32, 16),
+    # cin, cout, (kh,kw), H, W, TH, TW, CC
+    (8, 8, (3, 3), 20, 37, 8, 16, 8),
+    (16, 16, (3, 3), 17, 40, 4, 30, 16),
+    (12, 20, (3, 3), 16, 24, 8, 24, 24),
+    (8, 16, (7, 7), 18, 30, 4, 26, 16),
+    (8, 40, (1, 5), 9, 33, 2, 33, 40),
+    (8, 20, (5, 1), 12, 20, 4, 20, 24),
+    (16, 32, (3, 3), 10, 22, 2, 22, 32),
+    (8, 8, (3, 3), 40, 70, 8, 62, 8),
 ]
 
 
-@pytest.mark.parametrize("cin,cout,k,H,W,TH,TW,CC,CCE", CASES)
-def test_ws_bookkeeping_matches_conv2d(cin, cout, k, H, W, TH, TW, CC, CCE):
+@pytest.mark.parametrize("cin,cout,k,H,W,TH,TW,CC", CASES)
+def test_ws_bookkeeping_matches_conv2d(cin, cout, k, H, W, TH, TW, CC):
     g = torch.Generator().manual_seed(1)
     x = torch.rand(1, cin, H, W, generator=g) - 0.5
     w = (torch.rand(cout, cin, *k, generator=g) - 0.5) / math.sqrt(cin * k[0] * k[1])
     pc = packing.pack_weight(w, None)
     ref = F.conv2d(x.double(), w.double(), padding=(k[0] // 2, k[1] // 2))[0].permute(1, 2, 0).numpy()
-    got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, TH, TW, CC, CCE)
+    got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, TH, TW, CC)
     assert not np.isnan(got).any(), "some output was never written"
     # hi + lo of the packed weights reproduces the fp32 weights to ~2^-22 relative
     assert np.abs(got - ref).max() < 1e-6
@@ -151,8 +150,8 @@ def test_ws_output_channel_chunks():
     pc = packing.pack_weight(w, None)
     ref = F.conv2d(x.double(), w.double(), padding=1)[0].permute(1, 2, 0).numpy()
     xin = x[0].permute(1, 2, 0).double().numpy()
-    lo = emulate_ws_conv(xin, pc, 4, 20, 64, 16, co_base=0)
-    hi = emulate_ws_conv(xin, pc, 4, 20, 16, 16, co_base=64)
+    lo = emulate_ws_conv(xin, pc, 4, 20, 64, co_base=0)
+    hi = emulate_ws_conv(xin, pc, 4, 20, 16, co_base=64)
     assert np.isnan(lo[..., 64:]).all() and np.isnan(hi[..., :64]).all()
     got = np.where(np.isnan(lo), hi, lo)
     assert np.abs(got - ref).max() < 1e-6

@@ -2,7 +2,7 @@
 # GPU call: ws kernel v2 (cheap loaders), CUDA-graph forward, per-layer comparison, ncu of the ws kernel.
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 400 python -m pytest tests/test_gpu_kernels.py -k "ws_tf32 or auto" -q --tb=short -p no:cacheprovider > $O/pytest_ws.log 2>&1
+timeout 400 python -m pytest tests/test_gpu_kernels.py -k "ws_tf32 or auto or groupnorm or epilogues" -q --tb=short -p no:cacheprovider > $O/pytest_ws.log 2>&1
 echo "pytest_ws rc=$?" >> $O/pytest_ws.log
 tail -4 $O/pytest_ws.log
 timeout 400 python tools/bench_conv.py all fp32,tc_tf32x3,ws_tf32x3,ws_tf32 > $O/bench_conv.log 2>&1
