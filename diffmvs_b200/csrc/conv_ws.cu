@@ -37,6 +37,9 @@ struct WsArgs {
   int co_base;      // first output channel of this launch
   int CC;           // output channels of this launch (multiple of 8)
   int N;            // MMA N = KW*CC rounded up to 16
+  int S;            // stride (1 or 2); a stride-2 convolution runs as S*S stride-1 phases over decimated input planes
+  int KHe, KWe;     // kernel extent in phase-plane shifts (== KH, KW for stride 1)
+  int smin_h, smin_w;   // smallest shift (== -pad for stride 1)
   int TH, TW, in_rows, in_cols;
   int m_total;      // TH * in_cols flattened positions carry results
   int plane;        // positions per channel-quad plane (incl. slack read by the last M block)
@@ -44,7 +47,7 @@ struct WsArgs {
   int tmem_cols;    // allocated TMEM columns (power of two >= 32)
   int tiles_x, tiles_y, total_tiles;
   int stage_f;      // floats per ring slot: operand pair [hi | lo]; doubles as the epilogue's halo exchange buffer
-  int vec_y, vec_res;
+  int vec_y, vec_res, vec_bias;
   int Hs, Ws;
   float inv_in_cols;
   int lanes_row;    // threads that share one tile row in the loader (32..256, power of two >= 2*in_cols when possible)
@@ -53,7 +56,7 @@ struct WsArgs {
 };
 
 struct Stage {
-  int tile, kd, chunk;
+  int tile, kd, phase, chunk;
   int n, od, ty0, tx0;   // decoded once per tile (the divisions are not free in a loop that runs per 8 channels)
 };
 
@@ -126,12 +129,12 @@ __device__ __forceinline__ void cp_async_wait_ring() {
 
 // PASSES = 1 (TF32) or 3 (3xTF32), R = ring depth (2, 3), GN = GroupNorm+SiLU prologue in the split pass
 template <int PASSES, int R, bool GN>
-__global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_constant__ WsArgs a) {
+__global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_constant__ WsArgs a) {
   const dmvs_conv_desc& d = a.d;
   extern __shared__ __align__(128) float smem[];
   const int N = a.N;
   const int plane_f = 2 * a.plane * 4;                        // floats per operand plane set (two channel quads)
-  const int wslab_f = d.KH * 2 * N * 4;                       // floats per weight slab: [kh][quad][N][4]
+  const int wslab_f = a.KHe * 2 * N * 4;                      // floats per weight slab: [kh'][quad][N][4]
   float* pair0 = smem;                                        // [R][stage_f]: pair = [hi | lo], raw data lands in hi
   float* w_hi0 = pair0 + R * a.stage_f;                       // [R][wslab_f]
   float* w_lo0 = w_hi0 + R * wslab_f;
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
   const int Ctot = d.C1 + d.C2;
   const int units_per_row = a.in_cols * 2;       // 16-byte units per tile row (two channel quads per stage)
   const int nchunks = a.cin_pad >> 3;
+  const int nphase = a.S * a.S;
 
   auto decode = [&](int tile, int& n, int& od, int& ty0, int& tx0) {
     const int tx = tile % a.tiles_x;
@@ -172,10 +176,10 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
     ty0 = ty * a.TH;
     tx0 = tx * a.TW;
   };
-  auto kd_first = [&](int od) { const int v = d.pad_d - od; return v > 0 ? v : 0; };
-  auto kd_last = [&](int od) { const int v = d.D - 1 + d.pad_d - od; return v < d.KD - 1 ? v : d.KD - 1; };
+  auto kd_first = [&](int od) { const int v = d.pad_d - od * a.S; return v > 0 ? v : 0; };
+  auto kd_last = [&](int od) { const int v = d.D - 1 + d.pad_d - od * a.S; return v < d.KD - 1 ? v : d.KD - 1; };
   auto first_stage_of = [&](int tile) {
-    Stage s{tile, 0, 0, 0, 0, 0, 0};
+    Stage s{tile, 0, 0, 0, 0, 0, 0, 0};
     if (tile < a.total_tiles) {
       decode(tile, s.n, s.od, s.ty0, s.tx0);
       s.kd = kd_first(s.od);
@@ -186,6 +190,8 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
     Stage s = c;
     if (++s.chunk < nchunks) return s;
     s.chunk = 0;
+    if (++s.phase < nphase) return s;
+    s.phase = 0;
     if (++s.kd <= kd_last(c.od)) return s;
     return first_stage_of(c.tile + (int)gridDim.x);
   };
@@ -200,15 +206,17 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
   auto issue_loads = [&](const Stage& s, int slot) {
     if (s.tile < a.total_tiles) {
       const int c0 = s.chunk * 8;
-      const int id = s.od + s.kd - d.pad_d;
-      const int iy0 = s.ty0 - d.pad_h, ix0 = s.tx0 - d.pad_w;
+      const int id = s.od * a.S + s.kd - d.pad_d;
+      // phase (pa, pb): tile row r / column c hold input pixel (S*(ty0 + r + smin_h) + pa, S*(tx0 + c + smin_w) + pb)
+      const int pa = a.S == 2 ? (s.phase >> 1) : 0, pb = a.S == 2 ? (s.phase & 1) : 0;
+      const int iy0 = a.S * (s.ty0 + a.smin_h) + pa, ix0 = a.S * (s.tx0 + a.smin_w) + pb;
       float* a_raw = pair0 + slot * a.stage_f;
       const int64_t img = (int64_t)(s.n * d.D + id) * a.Hs;
 #pragma unroll 1
       for (int u = ld_u0; u < units_per_row; u += a.lanes_row) {
         const int q = u & 1;
         const int col = u >> 1;
-        const int ix = ix0 + col;
+        const int ix = ix0 + a.S * col;
         const int ch = c0 + q * 4;
         const bool col_ok = ix >= 0 && ix < d.W && ch < Ctot;
         const int sx = d.in_up2 ? (ix >> 1) : ix;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
         const int up = d.in_up2 ? 1 : 0;
 #pragma unroll 2
         for (int row = ld_r0; row < a.in_rows; row += ld_rstep, dst += dst_step) {
-          const int iy = iy0 + row;
+          const int iy = iy0 + a.S * row;
           if (col_ok && iy >= 0 && iy < d.H) {
             cp_async16_full(dst, colp + (iy >> up) * row_stride);
           } else {
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
       // weights of this (kd, channel chunk): the host packed every slab [kh][quad][N][4] contiguously (w_ws)
       float* wh = w_hi0 + slot * wslab_f;
       float* wl = w_lo0 + slot * wslab_f;
-      const float* src = d.w_ws + a.w_off + (int64_t)(s.kd * nchunks + s.chunk) * wslab_f;
+      const float* src = d.w_ws + a.w_off + (int64_t)((s.kd * nphase + s.phase) * nchunks + s.chunk) * wslab_f;
       const int wunits = wslab_f >> 2;
 #pragma unroll 2
       for (int idx = tid; idx < wunits; idx += kWsThreads) {
@@ -322,11 +330,14 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
         const uint64_t dbh0 = umma_desc(smem_u32(w_hi0 + slot * wslab_f), lbo_b, 128);
         const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + slot * wslab_f), lbo_b, 128);
         const uint32_t b_step = 2u * (uint32_t)N;              // one kernel row of weights, in 16-byte units
+        const int pa = a.S == 2 ? (cur.phase >> 1) : 0;
         for (int blk = 0; blk < a.n_blk; ++blk) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(blk * N);
           uint32_t acc = tile_start ? 0u : 1u;
           uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
-          for (int kh = 0; kh < d.KH; ++kh, a_off += (uint32_t)a.in_cols, b_off += b_step) {
+          for (int khe = 0; khe < a.KHe; ++khe, a_off += (uint32_t)a.in_cols, b_off += b_step) {
+            const int kh = a.S * (khe + a.smin_h) + pa + d.pad_h;   // kernel row behind shift khe in this phase
+            if (kh < 0 || kh >= d.KH) continue;
             if (PASSES == 3) {
               umma_tf32(d_tmem, dal0 + a_off, dbh0 + b_off, idesc, acc);
               umma_tf32(d_tmem, dah0 + a_off, dbl0 + b_off, idesc, 1u);
@@ -365,20 +376,21 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
         const int ncg = a.CC >> 3;
         const int n_items = a.n_blk * ncg;
         const int quadrant = warp & 3, half = warp >> 2;
-        const int KWm1 = d.KW - 1;
+        const int KWm1 = a.KWe - 1;
         const int halo_q = KWm1 * KWm1 * 8;       // floats per (item, quadrant)
         const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
         const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
         const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
         if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
         if (KWm1 > 0) {
+          int blk = 0, cg = half;                                // items half, half + 2, ... as (block, octet)
+          while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
           for (int it = half; it < n_items; it += 2) {          // pass 1: rows other quadrants will need
-            const int blk = it / ncg, cg = it - blk * ncg;
             const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
             float* hq = halo + (it * 4 + quadrant) * halo_q;
 #pragma unroll 1
-            for (int kw = 1; kw < d.KW; ++kw) {
+            for (int kw = 1; kw < a.KWe; ++kw) {
               float v[8];
               tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
               if (lane < kw) {
@@ -387,19 +399,22 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
               }
             }
+            cg += 2;
+            while (cg >= ncg) { cg -= ncg; ++blk; }
           }
         }
         __syncthreads();
+        int blk = 0, cg = half;
+        while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
         for (int it = half; it < n_items; it += 2) {            // pass 2: shift-add, fused epilogue, store
-          const int blk = it / ncg, cg = it - blk * ncg;
           const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
           const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
           const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
           float acc[8];
           tmem_ld8(trow, acc);
 #pragma unroll 1
-          for (int kw = 1; kw < d.KW; ++kw) {
+          for (int kw = 1; kw < a.KWe; ++kw) {
             float v[8];
             tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
 #pragma unroll
@@ -428,9 +443,15 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
           if (valid) {
             const bool full8 = c0 + 8 <= d.Cout;
             if (d.bias != nullptr) {
+              if (a.vec_bias && full8) {
+                const float4 b0 = ldg4(d.bias + c0), b1 = ldg4(d.bias + c0 + 4);
+                acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
+                acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+              } else {
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (full8 || c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
+                for (int k = 0; k < 8; ++k)
+                  if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
+              }
             }
             const int64_t opix = (img_base + oy) * d.Wo + ox;
             int64_t rpix = opix;
@@ -450,11 +471,19 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
                 }
               }
               const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+              if (relu_from <= c0) {          // the common case: ReLU on every channel of the octet
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                float x = pre_act ? acc[k] + r[k] : acc[k];
-                if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
-                acc[k] = pre_act ? x : x + r[k];
+                for (int k = 0; k < 8; ++k) {
+                  const float x = fmaxf(pre_act ? acc[k] + r[k] : acc[k], 0.0f);
+                  acc[k] = pre_act ? x : x + r[k];
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  float x = pre_act ? acc[k] + r[k] : acc[k];
+                  if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
+                  acc[k] = pre_act ? x : x + r[k];
+                }
               }
             } else {
 #pragma unroll
@@ -494,6 +523,8 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
               }
             }
           }
+          cg += 2;
+          while (cg >= ncg) { cg -= ncg; ++blk; }
         }
         __syncthreads();   // halo reads done before the next stage's loads land here; statistics complete
         if (d.out_stats != nullptr) {
@@ -543,50 +574,55 @@ struct TileCfg {
 // model of one tile (MMA time, split pass, copy issue, exposed latency, epilogue) times the number of tile waves
 // is evaluated and the cheapest configuration wins.  The model only has to rank shapes; constants are from the
 // ncu captures under profiles/.
-void choose_tile(const dmvs_conv_desc& d, int N, int CC, int passes, int cin_pad, TileCfg& best) {
+void choose_tile(const dmvs_conv_desc& d, int KHe, int KWe, int N, int CC, int passes, int cin_pad, TileCfg& best) {
   static const int force_th = getenv("DMVS_WS_TH") ? atoi(getenv("DMVS_WS_TH")) : 0;   // tuning aids
   static const int force_r = getenv("DMVS_WS_R") ? atoi(getenv("DMVS_WS_R")) : 0;
   static const int force_ctas = getenv("DMVS_WS_CTAS") ? atoi(getenv("DMVS_WS_CTAS")) : 0;
   const int nchunks = cin_pad >> 3;
-  for (int ctas = 2; ctas >= 1; --ctas) {
+  static const int max_ctas = getenv("DMVS_WS_MAXCTAS") ? atoi(getenv("DMVS_WS_MAXCTAS")) : 3;
+  for (int ctas = max_ctas; ctas >= 1; --ctas) {
     if (force_ctas && ctas != force_ctas) continue;
-    const size_t smem_limit = ctas == 2 ? 112 * 1024 : 216 * 1024;
-    const int max_blk = (ctas == 2 ? 256 : 512) / N;
+    // co-resident CTAs share 227 KB of shared memory and 512 TMEM columns (allocations are powers of two)
+    const size_t smem_limit = ctas >= 4 ? 55 * 1024 : (ctas == 3 ? 74 * 1024 : (ctas == 2 ? 112 * 1024 : 216 * 1024));
+    const int max_blk = (ctas >= 3 ? 128 : (ctas == 2 ? 256 : 512)) / N;
     for (int th = 16; th >= 1; th >>= 1) {
       if (th > 1 && th / 2 >= d.Ho) continue;          // a shorter tile already covers the image height
       if (force_th && th != force_th) continue;
       for (int nb = max_blk; nb >= 1; --nb) {
         const int cols_max = nb * 128 / th;            // in_cols such that th*in_cols <= nb*128
-        int tw_max = cols_max - (d.KW - 1);
+        int tw_max = cols_max - (KWe - 1);
         if (tw_max > 250) tw_max = 250;
         if (tw_max < 1 || (tw_max < 8 && tw_max < d.Wo)) continue;
         const int ntx = ceil_div(d.Wo, tw_max);
         const int TW = ceil_div(d.Wo, ntx);
-        const int in_cols = TW + d.KW - 1;
-        const int in_rows = th + d.KH - 1;
+        const int in_cols = TW + KWe - 1;
+        const int in_rows = th + KHe - 1;
         const int n_blk = ceil_div(th * in_cols, 128);
         if (n_blk > max_blk) continue;
-        const int plane = (n_blk * 128 + (d.KH - 1) * in_cols + 8 + 7) & ~7;
+        const int plane = (n_blk * 128 + (KHe - 1) * in_cols + 8 + 7) & ~7;
         size_t work_f = (size_t)(passes == 3 ? 2 : 1) * 2 * plane * 4;
-        const size_t halo_f = (size_t)n_blk * (CC / 8) * 4 * (d.KW - 1) * (d.KW - 1) * 8;   // epilogue halo exchange
+        const size_t halo_f = (size_t)n_blk * (CC / 8) * 4 * (KWe - 1) * (KWe - 1) * 8;   // epilogue halo exchange
         if (work_f < halo_f) work_f = halo_f;
         work_f = (work_f + 31) & ~(size_t)31;
-        const size_t wslab_f = (size_t)d.KH * 2 * N * 4;
+        const size_t wslab_f = (size_t)KHe * 2 * N * 4;
         for (int r = 3; r >= 2; --r) {
           if (force_r && r != force_r) continue;
           const size_t need = (r * work_f + (passes == 3 ? 2 : 1) * r * wslab_f + 2 * (size_t)d.C1 + 8) * 4;
           if (need > smem_limit) continue;
           // ---- cycle model ------------------------------------------------------------------------
-          const double mma = (double)n_blk * d.KH * passes * (N / 2 > 32 ? N / 2 : 32);   // A read 32 clk or math N/2
+          const double mma = (double)n_blk * d.KH / d.stride * passes * (N / 2 > 32 ? N / 2 : 32);   // A read 32 clk or math N/2
           const double split = passes == 3 || d.in_stats ? 2.0 * plane / kWsThreads * (d.in_stats ? 45.0 : 24.0) : 0.0;
           const double copies = (2.0 * in_rows * in_cols * 10.0 + wslab_f / 4.0 * passes * 6.0) / kWsThreads;
           const double issue = (split + copies) * 8.0 / 4.0 + 200.0;        // 8 warps over 4 schedulers + barriers
           const double latency = r == 3 ? 600.0 : 1500.0;                    // exposed copy latency per stage
-          double stage = (mma > latency ? mma : latency) + issue;
-          if (ctas == 2) stage = stage * 0.5 > mma + 0.5 * issue ? stage * 0.5 : mma + 0.5 * issue;   // two CTAs interleave
-          const int stages = nchunks * d.KD;
-          const double epi = (double)n_blk * (CC / 8) * (60.0 + 37.0 * d.KW) + 200.0;
-          const double tile = stages * stage + (ctas == 2 ? 0.6 : 1.0) * epi + 300.0;
+          const int stages = nchunks * d.KD * d.stride * d.stride;
+          const double epi = (double)n_blk * (CC / 8) * (60.0 + 37.0 * KWe) + 200.0;
+          // one CTA alone pays the exposed latency; co-resident CTAs interleave until the tensor pipe or the
+          // instruction issue slots saturate
+          const double alone = stages * ((mma > latency ? mma : latency) + issue) + epi + 300.0;
+          const double mma_t = stages * mma, issue_t = stages * issue + epi;
+          const double busy = (mma_t > issue_t ? mma_t : issue_t) + 0.25 * (mma_t > issue_t ? issue_t : mma_t);
+          const double tile = alone / ctas > busy ? alone / ctas : busy;
           const long tiles = (long)ntx * ceil_div(d.Ho, th) * d.N * d.Do;
           const double waves = (double)ceil_div64(tiles, (int64_t)kNumSMs);   // per SM
           const double est = waves * tile;
@@ -601,6 +637,14 @@ void choose_tile(const dmvs_conv_desc& d, int N, int CC, int passes, int cin_pad
 }
 
 // Output-channel chunking shared with the host packer (packing.py::pack_ws): chunks of at most cc_max channels.
+// Extent of a K-tap kernel in phase-plane shifts for stride S: tap k reads input S*o + k - pad = S*(o + s) + phase
+// with shift s = floor((k - pad - phase) / S); smin is the smallest shift over all taps, the extent their span.
+inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+inline void ws_extent(int K, int pad, int S, int* smin, int* ext) {
+  *smin = floor_div(-pad, S);
+  *ext = floor_div(K - 1 - pad, S) - *smin + 1;
+}
+
 inline int ws_cc_max(int KW) {
   int cc = (256 / KW) & ~7;
   return cc > 64 ? 64 : cc;
@@ -609,7 +653,11 @@ inline int ws_cc_max(int KW) {
 }  // namespace
 
 bool conv_ws_supported(const dmvs_conv_desc& d) {
-  if (d.w_ws == nullptr || d.stride != 1 || d.KH > 16 || d.KW > 8) return false;
+  if (d.w_ws == nullptr || (d.stride != 1 && d.stride != 2) || d.KH > 16) return false;
+  int smin, kwe;
+  ws_extent(d.KW, d.pad_w, d.stride, &smin, &kwe);
+  if (kwe > 8) return false;
+  if (d.stride == 2 && (d.in_up2 || d.in_stats != nullptr)) return false;
   const bool vec_x = aligned16(d.x) && (d.x_ps % 4 == 0) && (d.C1 % 4 == 0);
   const bool vec_x2 = d.C2 == 0 || (aligned16(d.x2) && (d.x2_ps % 4 == 0) && (d.C2 % 4 == 0));
   if (!vec_x || !vec_x2) return false;
@@ -633,25 +681,29 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
   a.cout_pad = (d.Cout + 15) & ~15;
   a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
   a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
+  a.vec_bias = d.bias != nullptr && aligned16(d.bias);
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
 
-  const int cc_max = ws_cc_max(d.KW);
+  a.S = d.stride;
+  ws_extent(d.KH, d.pad_h, d.stride, &a.smin_h, &a.KHe);
+  ws_extent(d.KW, d.pad_w, d.stride, &a.smin_w, &a.KWe);
+  const int cc_max = ws_cc_max(a.KWe);
   if (cc_max < 8) return DMVS_ERR_UNSUPPORTED;
   int remaining = (d.Cout + 7) & ~7, co_base = 0;
   int64_t w_off = 0;
   while (remaining > 0) {
     const int CC = remaining < cc_max ? remaining : cc_max;
-    const int N = (d.KW * CC + 15) & ~15;
+    const int N = (a.KWe * CC + 15) & ~15;
     TileCfg t;
-    choose_tile(d, N, CC, passes, a.cin_pad, t);
+    choose_tile(d, a.KHe, a.KWe, N, CC, passes, a.cin_pad, t);
     if (!t.TH) return DMVS_ERR_UNSUPPORTED;
     a.co_base = co_base;
     a.CC = CC;
     a.N = N;
     a.TH = t.TH;
     a.TW = t.TW;
-    a.in_rows = t.TH + d.KH - 1;
+    a.in_rows = t.TH + a.KHe - 1;
     a.in_cols = t.in_cols;
     a.m_total = t.TH * t.in_cols;
     a.plane = t.plane;
@@ -661,8 +713,8 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
     int lanes = 32;
     while (lanes < 2 * t.in_cols && lanes < kWsThreads) lanes <<= 1;
     a.lanes_row = lanes;
-    // packed slabs of this chunk: [hi | lo][KD][cin_pad/8][KH][2][N][4]
-    const int64_t plane_w = (int64_t)d.KD * (a.cin_pad >> 3) * d.KH * 2 * N * 4;
+    // packed slabs of this chunk: [hi | lo][KD][S*S phases][cin_pad/8][KHe][2][N][4]
+    const int64_t plane_w = (int64_t)d.KD * a.S * a.S * (a.cin_pad >> 3) * a.KHe * 2 * N * 4;
     a.w_off = w_off;
     a.w_plane = plane_w;
     int cols = 32;

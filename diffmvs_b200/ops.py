@@ -223,7 +223,19 @@ class PackedConv:
     k: Tuple[int, int, int]
     w_t: Optional[Tensor] = None   # tensor-core layout [KD,KH,KW,cout_pad8,cin_pad8]
     w_tc: Optional[Tensor] = None  # tcgen05 layout [2(hi,lo),KD,KH*KW,cin_pad8/4,cout_pad16,4]
-    w_ws: Optional[Tensor] = None  # width-stacked tcgen05 slabs (packing.pack_ws)
+    w_ws: Optional[Tensor] = None  # width-stacked tcgen05 slabs for stride 1 (packing.pack_ws)
+    ws_strided: Optional[dict] = None   # (stride, pad_h, pad_w) -> slabs for strided use, built on first use
+
+    def ws_slabs(self, stride: int, pad_h: int, pad_w: int) -> Optional[Tensor]:
+        if stride == 1 or self.w_ws is None:
+            return self.w_ws
+        if self.ws_strided is None:
+            self.ws_strided = {}
+        key = (stride, pad_h, pad_w)
+        if key not in self.ws_strided:
+            from . import packing
+            self.ws_strided[key] = packing.pack_ws_from_packed(self.w, self.cout, stride, (pad_h, pad_w)).to(self.w.device)
+        return self.ws_strided[key]
 
     def to(self, device) -> "PackedConv":
         mv = lambda t: None if t is None else t.to(device)
@@ -287,7 +299,7 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         d.in_stats, d.in_g1, d.in_g0 = _ptr(in_gn.stats), _ptr(in_gn.g1), _ptr(in_gn.g0)
         d.in_inv_count = 1.0 / float(D * H * W * (C1 // 4))
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
-    d.w_t, d.w_tc, d.w_ws = _ptr(pc.w_t), _ptr(pc.w_tc), _ptr(pc.w_ws)
+    d.w_t, d.w_tc, d.w_ws = _ptr(pc.w_t), _ptr(pc.w_tc), _ptr(pc.ws_slabs(stride, ph, pw))
     d.precision = _precision if pc.w_t is not None else PREC_FP32
     if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32) and pc.w_tc is None:
         d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3) else PREC_TF32

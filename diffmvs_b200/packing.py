@@ -55,7 +55,7 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None, pad_cin: i
     hi = rna_tf32(quad)
     lo = rna_tf32(quad - hi)
     w_tc = torch.stack((hi, lo), 0).contiguous()
-    w_ws = pack_ws(full.view(kd, kh, kw, ci8, co16), cout) if kw <= 8 else None
+    w_ws = pack_ws(full.view(kd, kh, kw, ci8, co16), cout) if kw <= 8 else None   # stride-1 slabs
     return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc, w_ws)
 
 
@@ -64,29 +64,61 @@ def ws_cc_max(kw: int) -> int:
     return min(64, (256 // kw) & ~7)
 
 
-def pack_ws(full: torch.Tensor, cout: int) -> torch.Tensor:
-    """full [KD,KH,KW,cin_pad8,cout_pad16] -> flat width-stacked slabs (include/diffmvs_b200.h, `w_ws`): for every
-    output-channel chunk (CC channels, N = KW*CC rounded up to 16) the planes hi = rna_tf32(w), lo = rna_tf32(w - hi),
-    each [KD][cin_pad8/8][KH][2][N][4]; column kw*CC + c holds tap kw of output channel co_base + c."""
+def ws_extent(k: int, pad: int, stride: int) -> Tuple[int, int]:
+    """(smallest shift, extent) of a k-tap kernel in phase-plane shifts (mirrors `ws_extent` in csrc/conv_ws.cu):
+    tap t reads input stride*o + t - pad = stride*(o + s) + phase with s = floor((t - pad - phase) / stride)."""
+    smin = (-pad) // stride
+    return smin, (k - 1 - pad) // stride - smin + 1
+
+
+def pack_ws(full: torch.Tensor, cout: int, stride: int = 1, pad: Tuple[int, int] = (0, 0)) -> torch.Tensor:
+    """full [KD,KH,KW,cin_pad8,cout_pad16] -> flat width-stacked slabs (include/diffmvs_b200.h, `w_ws`).  A stride-S
+    convolution is S*S stride-1 phases over decimated input planes; with (KHe, KWe) the kernel extent in phase-plane
+    shifts, every output-channel chunk (CC channels, N = KWe*CC rounded up to 16) stores the planes
+    hi = rna_tf32(w), lo = rna_tf32(w - hi), each [KD][S*S][cin_pad8/8][KHe][2][N][4]; column kw'*CC + c of phase
+    (pa, pb) holds tap (S*(kh'+smin_h) + pa + pad_h, S*(kw'+smin_w) + pb + pad_w) of output channel co_base + c, or
+    zero where the phase has no such tap.  For stride 1 this is [KD][1][cin/8][KH][2][KW*CC][4] whatever the padding."""
     kd, kh, kw, ci8, co16 = full.shape
-    cc_max = ws_cc_max(kw)
+    S = stride
+    ph, pw = pad if S > 1 else (0, 0)
+    smin_h, khe = ws_extent(kh, ph, S)
+    smin_w, kwe = ws_extent(kw, pw, S)
+    cc_max = ws_cc_max(kwe)
     remaining, co_base, parts = (cout + 7) & ~7, 0, []
     while remaining > 0:
         cc = min(remaining, cc_max)
-        n = (kw * cc + 15) & ~15
-        blk = torch.zeros(kd, kh, kw, ci8, cc, dtype=torch.float32)
+        n = (kwe * cc + 15) & ~15
         avail = min(cc, co16 - co_base)
-        blk[..., :avail] = full[..., co_base:co_base + avail]
-        # [kd][kh][kw][chunk][quad][4][cc] -> [kd][chunk][kh][quad][kw][cc][4]
-        blk = blk.view(kd, kh, kw, ci8 // 8, 2, 4, cc).permute(0, 3, 1, 4, 2, 6, 5).reshape(kd, ci8 // 8, kh, 2, kw * cc, 4)
-        slab = torch.zeros(kd, ci8 // 8, kh, 2, n, 4, dtype=torch.float32)
-        slab[..., :kw * cc, :] = blk
+        slab = torch.zeros(kd, S * S, ci8 // 8, khe, 2, n, 4, dtype=torch.float32)
+        for pa in range(S):
+            for pb in range(S):
+                for khs in range(khe):
+                    th = S * (khs + smin_h) + pa + ph
+                    if not 0 <= th < kh:
+                        continue
+                    for kws in range(kwe):
+                        tw = S * (kws + smin_w) + pb + pw
+                        if not 0 <= tw < kw:
+                            continue
+                        # [kd][ci8][avail] -> [kd][chunk][quad][4][avail] -> [kd][chunk][quad][avail][4]
+                        tap = full[:, th, tw, :, co_base:co_base + avail].reshape(kd, ci8 // 8, 2, 4, avail)
+                        slab[:, pa * S + pb, :, khs, :, kws * cc:kws * cc + avail, :] = tap.permute(0, 1, 2, 4, 3)
         hi = rna_tf32(slab)
         lo = rna_tf32(slab - hi)
         parts += [hi.reshape(-1), lo.reshape(-1)]
         co_base += cc
         remaining -= cc
     return torch.cat(parts).contiguous()
+
+
+def pack_ws_from_packed(w: torch.Tensor, cout: int, stride: int, pad: Tuple[int, int]) -> torch.Tensor:
+    """Width-stacked slabs for a given stride / padding from the FFMA layout `PackedConv.w`
+    ([KD,KH,KW,cin_pad4,cout_pad4]); built on first use of a strided layer (ops.conv) and cached."""
+    w = w.detach().float().cpu()
+    kd, kh, kw, ci4, co4 = w.shape
+    full = torch.zeros(kd, kh, kw, (ci4 + 7) & ~7, (cout + 15) & ~15, dtype=torch.float32)
+    full[..., :ci4, :min(co4, full.shape[-1])] = w[..., :min(co4, full.shape[-1])]
+    return pack_ws(full, cout, stride, pad)
 
 
 def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:

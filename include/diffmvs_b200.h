@@ -93,9 +93,12 @@ typedef struct dmvs_conv_desc {
                                NULL when precision == DMVS_PREC_FP32 */
   const float* w_tc;        /* tcgen05 layout: two planes (hi = rna_tf32(w), lo = rna_tf32(w - hi)), each
                                [KD][KH*KW][cin_pad8/4][cout_pad16][4]; may be NULL unless precision is DMVS_PREC_TC_* */
-  const float* w_ws;        /* width-stacked tcgen05 layout (conv_ws.cu): per output-channel chunk (CC <= cc_max =
-                               min(64, (256/KW) & ~7) channels, N = KW*CC rounded up to 16) two planes (hi, lo), each
-                               [KD][cin_pad8/8][KH][2 channel quads][N][4] with column kw*CC + c; may be NULL */
+  const float* w_ws;        /* width-stacked tcgen05 layout (conv_ws.cu), packed for THIS stride and padding: a stride-S
+                               convolution runs as S*S stride-1 phases; with KHe, KWe the kernel extent in phase-plane
+                               shifts (KH, KW for S = 1), per output-channel chunk (CC <= min(64, (256/KWe) & ~7)
+                               channels, N = KWe*CC rounded up to 16) two planes (hi, lo), each
+                               [KD][S*S][cin_pad8/8][KHe][2 channel quads][N][4] with column kw'*CC + c, zero where a
+                               phase has no tap (packing.pack_ws); may be NULL */
   int32_t precision;        /* DMVS_PREC_* */
   const float* bias;        /* [Cout] or NULL */
   int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;

@@ -14,48 +14,53 @@ import torch.nn.functional as F
 
 from diffmvs_b200 import packing
 
-def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0):
-    """x [H,W,Cin] (numpy), pc PackedConv (2-D) -> y [H,W,Cout] via the kernel's data movement."""
+def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1):
+    """x [H,W,Cin] (numpy), pc PackedConv (2-D) -> y [Ho,Wo,Cout] via the kernel's data movement (stride S)."""
     H, W, Cin = x.shape
-    KD, KH, KW = pc.k
+    KD, KH_real, KW_real = pc.k
     assert KD == 1
     Cout = pc.cout
-    pad_h, pad_w = KH // 2, KW // 2
+    pad_h, pad_w = KH_real // 2, KW_real // 2
+    Ho, Wo = (H + 2 * pad_h - KH_real) // S + 1, (W + 2 * pad_w - KW_real) // S + 1
+    smin_h, KH = packing.ws_extent(KH_real, pad_h, S)      # below, KH / KW are the extents in phase-plane shifts
+    smin_w, KW = packing.ws_extent(KW_real, pad_w, S)
     cin_pad = (Cin + 7) & ~7
     cout_pad = (Cout + 15) & ~15
     qtot = cin_pad // 4
     taps = KH * KW
     N = (KW * CC + 15) & ~15
     # this launch's packed slabs: the chunks before co_base come first in w_ws (packing.pack_ws)
-    w_ws = pc.w_ws.numpy()
+    w_ws = (pc.w_ws if S == 1 else packing.pack_ws_from_packed(pc.w, Cout, S, (pad_h, pad_w))).numpy()
     nchunks = cin_pad // 8
+    nphase = S * S
     cc_max = packing.ws_cc_max(KW)
     w_off, rem, base = 0, (Cout + 7) & ~7, 0
     while base < co_base:
         cc = min(rem, cc_max)
-        w_off += 2 * KD * nchunks * KH * 2 * ((KW * cc + 15) & ~15) * 4
+        w_off += 2 * KD * nphase * nchunks * KH * 2 * ((KW * cc + 15) & ~15) * 4
         base += cc
         rem -= cc
     assert base == co_base and CC == min(rem, cc_max), "test case must follow the kernel's channel chunking"
     wslab_f = KH * 2 * N * 4
-    w_plane = KD * nchunks * wslab_f
+    w_plane = KD * nphase * nchunks * wslab_f
     in_rows, in_cols = TH + KH - 1, TW + KW - 1
     m_total = TH * in_cols
     n_blk = -(-m_total // 128)
     plane = (n_blk * 128 + (KH - 1) * in_cols + 8 + 7) & ~7
-    y = np.full((H, W, Cout), np.nan, dtype=np.float64)
+    y = np.full((Ho, Wo, Cout), np.nan, dtype=np.float64)
     rng = np.random.default_rng(0)
-    for ty0 in range(0, H, TH):
-        for tx0 in range(0, W, TW):
+    for ty0 in range(0, Ho, TH):
+        for tx0 in range(0, Wo, TW):
             E = np.zeros((n_blk * 128, N))
-            for chunk in range(cin_pad // 8):
+            for phase, chunk in [(ph, ck) for ph in range(nphase) for ck in range(cin_pad // 8)]:
+                pa, pb = (phase >> 1, phase & 1) if S == 2 else (0, 0)
                 c0 = chunk * 8
                 # ---- issue_loads: raw tile, planar by channel quad; slack keeps garbage -------------------
                 A = rng.standard_normal((2, plane, 4)) * 1e3     # garbage where the kernel does not write
                 for row in range(in_rows):
-                    iy = ty0 - pad_h + row
+                    iy = S * (ty0 + smin_h) + pa + S * row
                     for col in range(in_cols):
-                        ix = tx0 - pad_w + col
+                        ix = S * (tx0 + smin_w) + pb + S * col
                         for q in range(2):
                             ch = c0 + q * 4
                             ok = 0 <= iy < H and 0 <= ix < W and ch < Cin
@@ -65,12 +70,15 @@ def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0):
                                 v[:len(seg)] = seg
                             A[q, row * in_cols + col] = v
                 # ---- weight slab [kh][quad][N][4] from the packed global layout ---------------------------
-                src = w_off + (0 * nchunks + chunk) * wslab_f
+                src = w_off + ((0 * nphase + phase) * nchunks + chunk) * wslab_f
                 slab = (w_ws[src:src + wslab_f] + w_ws[src + w_plane:src + w_plane + wslab_f]).astype(np.float64)  # hi + lo
                 slab = slab.reshape(KH, 2, N, 4)
                 # ---- MMAs: per block and kernel row one instruction, N columns ---------------------------
                 for blk in range(n_blk):
                     for kh in range(KH):
+                        tap_row = S * (kh + smin_h) + pa + pad_h
+                        if not 0 <= tap_row < KH_real:          # this phase has no kernel row behind shift kh
+                            continue
                         a_off = blk * 128 + kh * in_cols
                         a_op = np.concatenate([A[0, a_off:a_off + 128], A[1, a_off:a_off + 128]], axis=1)   # [128][8]
                         b_op = np.concatenate([slab[kh, 0], slab[kh, 1]], axis=1)                          # [N][8]
@@ -106,7 +114,7 @@ def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0):
                         py = int((np.float32(p) + np.float32(0.5)) * np.float32(1.0 / in_cols))
                         px = p - py * in_cols
                         oy, ox = ty0 + py, tx0 + px
-                        if not (px < TW and py < TH and oy < H and ox < W and c0 < Cout):
+                        if not (px < TW and py < TH and oy < Ho and ox < Wo and c0 < Cout):
                             continue
                         for k in range(8):
                             if c0 + k < Cout:
@@ -154,4 +162,27 @@ def test_ws_output_channel_chunks():
     hi = emulate_ws_conv(xin, pc, 4, 20, 16, co_base=64)
     assert np.isnan(lo[..., 64:]).all() and np.isnan(hi[..., :64]).all()
     got = np.where(np.isnan(lo), hi, lo)
+    assert np.abs(got - ref).max() < 1e-6
+
+
+STRIDED = [
+    # cin, cout, k, H, W, TH, TW, CC
+    (8, 16, (5, 5), 20, 36, 4, 18, 16),
+    (16, 32, (5, 5), 16, 24, 2, 12, 32),
+    (8, 16, (3, 3), 18, 30, 4, 15, 16),
+    (8, 16, (2, 2), 16, 24, 4, 12, 16),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,H,W,TH,TW,CC", STRIDED)
+def test_ws_stride2_phases_match_conv2d(cin, cout, k, H, W, TH, TW, CC):
+    """Stride 2 = four stride-1 phases over decimated input planes accumulating into the same columns."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, cin, H, W, generator=g) - 0.5
+    w = (torch.rand(cout, cin, *k, generator=g) - 0.5) / math.sqrt(cin * k[0] * k[1])
+    pc = packing.pack_weight(w, None)
+    ref = F.conv2d(x.double(), w.double(), stride=2, padding=(k[0] // 2, k[1] // 2))[0].permute(1, 2, 0).numpy()
+    got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, TH, TW, CC, S=2)
+    assert got.shape == ref.shape
+    assert not np.isnan(got).any(), "some output was never written"
     assert np.abs(got - ref).max() < 1e-6
