@@ -330,6 +330,11 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
   return 0;
 }
 
+extern "C" int dmvs_conv_ws_plan(const dmvs_conv_desc* dp, int32_t* out, int32_t cap) {
+  if (dp == nullptr || out == nullptr || cap <= 0) return DMVS_ERR_ARG;
+  return plan_conv_ws(*dp, out, cap);
+}
+
 extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   if (dp == nullptr) return DMVS_ERR_ARG;
   const dmvs_conv_desc& d = *dp;

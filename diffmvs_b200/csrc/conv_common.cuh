@@ -229,5 +229,6 @@ int dispatch_conv_tc(const dmvs_conv_desc& d, cudaStream_t stream);
 // width-stacked tcgen05 back end (conv_ws.cu): the KW taps of a kernel row share one MMA (N = KW * Cout)
 bool conv_ws_supported(const dmvs_conv_desc& d);
 int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t stream);
+int plan_conv_ws(const dmvs_conv_desc& d, int32_t* out, int cap);   // tile plan only: {CC,N,TH,TW,n_blk,R,ctas,smem} per launch
 
 }  // namespace dmvs

@@ -28,7 +28,8 @@
 namespace dmvs {
 namespace {
 
-constexpr int kWsThreads = 256;
+constexpr int kWorkers = 256;     // warps 0-7: copies, split pass, epilogue
+constexpr int kWsThreads = 288;   // + warp 8: issues the MMAs while the workers refill the ring
 
 struct WsArgs {
   dmvs_conv_desc d;
@@ -80,6 +81,13 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
       : "memory");
 }
 
+// One lane of a converged warp (the compiler keeps the guarded code on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (!done) {
@@ -129,7 +137,7 @@ __device__ __forceinline__ void cp_async_wait_ring() {
 
 // PASSES = 1 (TF32) or 3 (3xTF32), R = ring depth (2, 3), GN = GroupNorm+SiLU prologue in the split pass
 template <int PASSES, int R, bool GN>
-__global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_constant__ WsArgs a) {
+__global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_constant__ WsArgs a) {
   const dmvs_conv_desc& d = a.d;
   extern __shared__ __align__(128) float smem[];
   const int N = a.N;
@@ -143,7 +151,9 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
   __shared__ __align__(8) uint64_t mbar[2];   // stages alternate barriers: a parity wait may lag by one phase only
   __shared__ float stat_s[8];
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
+  const bool worker = warp < 8;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
@@ -202,9 +212,9 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
   // instruction stream: profiles/r1b_ncu_conv_ffma_vs_ws_v1.txt).
   const int ld_u0 = tid & (a.lanes_row - 1);
   const int ld_r0 = tid / a.lanes_row;
-  const int ld_rstep = kWsThreads / a.lanes_row;
+  const int ld_rstep = kWorkers / a.lanes_row;
   auto issue_loads = [&](const Stage& s, int slot) {
-    if (s.tile < a.total_tiles) {
+    if (worker && s.tile < a.total_tiles) {
       const int c0 = s.chunk * 8;
       const int id = s.od * a.S + s.kd - d.pad_d;
       // phase (pa, pb): tile row r / column c hold input pixel (S*(ty0 + r + smin_h) + pa, S*(tx0 + c + smin_w) + pb)
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
       const float* src = d.w_ws + a.w_off + (int64_t)((s.kd * nphase + s.phase) * nchunks + s.chunk) * wslab_f;
       const int wunits = wslab_f >> 2;
 #pragma unroll 2
-      for (int idx = tid; idx < wunits; idx += kWsThreads) {
+      for (int idx = tid; idx < wunits; idx += kWorkers) {
         cp_async16_full(wh + idx * 4, src + idx * 4);
         if (PASSES == 3) cp_async16_full(wl + idx * 4, src + a.w_plane + idx * 4);
       }
@@ -274,19 +284,19 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
       const int n = cur.n, od = cur.od, ty0 = cur.ty0, tx0 = cur.tx0;
       cp_async_wait_ring<R>();                           // everything but the newest R-2 groups has landed
       if (GN && n != gn_n) {                             // GroupNorm affine of the producer is per sample
-        for (int c = tid; c < d.C1; c += kWsThreads) groupnorm_affine(d, n, c, gn_s);
+        for (int c = tid; c < d.C1; c += kWsThreads) groupnorm_affine(d, n, c, gn_s);   // (all 288 threads)
         gn_n = n;
       }
       __syncthreads();                                   // raw data of `slot` (and gn_s) visible to every thread
       float* a_hi = pair0 + slot * a.stage_f;
       float* a_lo = a_hi + plane_f;
       // ---- one pass over the staged tile: optional GroupNorm+SiLU, then the (hi, lo) split in place ----------
-      if (PASSES == 3 || GN) {
+      if ((PASSES == 3 || GN) && worker) {
         const int total = 2 * a.plane;
         const int iy0 = ty0 - d.pad_h, ix0 = tx0 - d.pad_w;
         const int c0 = cur.chunk * 8;
 #pragma unroll 2
-        for (int u = tid; u < total; u += kWsThreads) {
+        for (int u = tid; u < total; u += kWorkers) {
           float4 v = *reinterpret_cast<const float4*>(a_hi + u * 4);
           if (GN) {
             const int q = u >= a.plane ? 1 : 0;
@@ -322,8 +332,9 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       __syncthreads();                                   // operands of this stage complete
-      // ---- one thread issues the MMAs: per M block and kernel row, all KW taps in one instruction -----------
-      if (tid == 0) {
+      // ---- warp 8 issues the MMAs (one elected lane): per M block and kernel row, all KW taps in one instruction.
+      // The workers go straight on to refill the ring, so the issue latency is off their critical path.
+      if (warp == 8) {
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
         const uint64_t dah0 = umma_desc(smem_u32(a_hi), lbo_a, 128), dal0 = umma_desc(smem_u32(a_lo), lbo_a, 128);
@@ -331,26 +342,36 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
         const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + slot * wslab_f), lbo_b, 128);
         const uint32_t b_step = 2u * (uint32_t)N;              // one kernel row of weights, in 16-byte units
         const int pa = a.S == 2 ? (cur.phase >> 1) : 0;
+        // kernel rows present in this phase: shift khe <-> kernel row S*(khe + smin_h) + pa + pad_h
+        uint32_t rows = 0;
+        for (int khe = 0; khe < a.KHe; ++khe) {
+          const int kh = a.S * (khe + a.smin_h) + pa + d.pad_h;
+          if (kh >= 0 && kh < d.KH) rows |= 1u << khe;
+        }
+        const bool leader = elect_one();
         for (int blk = 0; blk < a.n_blk; ++blk) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(blk * N);
           uint32_t acc = tile_start ? 0u : 1u;
           uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
           for (int khe = 0; khe < a.KHe; ++khe, a_off += (uint32_t)a.in_cols, b_off += b_step) {
-            const int kh = a.S * (khe + a.smin_h) + pa + d.pad_h;   // kernel row behind shift khe in this phase
-            if (kh < 0 || kh >= d.KH) continue;
-            if (PASSES == 3) {
-              umma_tf32(d_tmem, dal0 + a_off, dbh0 + b_off, idesc, acc);
-              umma_tf32(d_tmem, dah0 + a_off, dbl0 + b_off, idesc, 1u);
-              umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, 1u);
-            } else {
-              umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, acc);
+            if (!((rows >> khe) & 1u)) continue;
+            if (leader) {
+              if (PASSES == 3) {
+                umma_tf32(d_tmem, dal0 + a_off, dbh0 + b_off, idesc, acc);
+                umma_tf32(d_tmem, dah0 + a_off, dbl0 + b_off, idesc, 1u);
+                umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, 1u);
+              } else {
+                umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, acc);
+              }
             }
             acc = 1u;
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                         smem_u32(&mbar[issued & 1]))
-                     : "memory");
+        if (leader)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
+                           smem_u32(&mbar[issued & 1]))
+                       : "memory");
+        __syncwarp();
       }
       ++issued;
       // ---- keep the ring full: stage s+R-1 reuses the pair of stage s-1, whose MMAs must have retired ----------
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
         const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
         const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
         if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
-        if (KWm1 > 0) {
+        if (KWm1 > 0 && worker) {
           int blk = 0, cg = half;                                // items half, half + 2, ... as (block, octet)
           while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(kWsThreads, 4) conv_ws_kernel(const __grid_con
         int blk = 0, cg = half;
         while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
-        for (int it = half; it < n_items; it += 2) {            // pass 2: shift-add, fused epilogue, store
+        for (int it = worker ? half : n_items; it < n_items; it += 2) {   // pass 2: shift-add, fused epilogue, store
           const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
           const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
           const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
@@ -611,8 +632,8 @@ void choose_tile(const dmvs_conv_desc& d, int KHe, int KWe, int N, int CC, int p
           if (need > smem_limit) continue;
           // ---- cycle model ------------------------------------------------------------------------
           const double mma = (double)n_blk * d.KH / d.stride * passes * (N / 2 > 32 ? N / 2 : 32);   // A read 32 clk or math N/2
-          const double split = passes == 3 || d.in_stats ? 2.0 * plane / kWsThreads * (d.in_stats ? 45.0 : 24.0) : 0.0;
-          const double copies = (2.0 * in_rows * in_cols * 10.0 + wslab_f / 4.0 * passes * 6.0) / kWsThreads;
+          const double split = passes == 3 || d.in_stats ? 2.0 * plane / kWorkers * (d.in_stats ? 45.0 : 24.0) : 0.0;
+          const double copies = (2.0 * in_rows * in_cols * 10.0 + wslab_f / 4.0 * passes * 6.0) / kWorkers;
           const double issue = (split + copies) * 8.0 / 4.0 + 200.0;        // 8 warps over 4 schedulers + barriers
           const double latency = r == 3 ? 600.0 : 1500.0;                    // exposed copy latency per stage
           const int stages = nchunks * d.KD * d.stride * d.stride;
@@ -671,7 +692,14 @@ bool conv_ws_supported(const dmvs_conv_desc& d) {
   return true;
 }
 
-int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
+// plan_out (optional, host pointer): per launch {CC, N, TH, TW, n_blk, R, ctas, smem bytes}; nothing is launched.
+int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out = nullptr, int plan_cap = 0);
+
+int plan_conv_ws(const dmvs_conv_desc& d, int32_t* out, int cap) { return dispatch_conv_ws(d, nullptr, out, cap); }
+
+int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) { return dispatch_conv_ws(d, st, nullptr, 0); }
+
+int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out, int plan_cap) {
   if (!conv_ws_supported(d)) return DMVS_ERR_UNSUPPORTED;
   if (!aligned16(d.w_ws)) return DMVS_ERR_ALIGN;
   const int passes = d.precision == DMVS_PREC_WS_TF32 ? 1 : 3;
@@ -692,6 +720,7 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
   if (cc_max < 8) return DMVS_ERR_UNSUPPORTED;
   int remaining = (d.Cout + 7) & ~7, co_base = 0;
   int64_t w_off = 0;
+  int n_launch = 0;
   while (remaining > 0) {
     const int CC = remaining < cc_max ? remaining : cc_max;
     const int N = (a.KWe * CC + 15) & ~15;
@@ -711,7 +740,7 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
     a.stage_f = t.stage_f;
     a.inv_in_cols = 1.0f / (float)t.in_cols;
     int lanes = 32;
-    while (lanes < 2 * t.in_cols && lanes < kWsThreads) lanes <<= 1;
+    while (lanes < 2 * t.in_cols && lanes < kWorkers) lanes <<= 1;
     a.lanes_row = lanes;
     // packed slabs of this chunk: [hi | lo][KD][S*S phases][cin_pad/8][KHe][2][N][4]
     const int64_t plane_w = (int64_t)d.KD * a.S * a.S * (a.cin_pad >> 3) * a.KHe * 2 * N * 4;
@@ -727,15 +756,23 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st) {
     a.total_tiles = (int)tiles;
     const long max_grid = (long)kNumSMs * t.ctas;
     const int grid = (int)(tiles < max_grid ? tiles : max_grid);
-    KernelFn fn = passes == 3 ? pick_r<3>(t.R, d.in_stats != nullptr) : pick_r<1>(t.R, d.in_stats != nullptr);
-    fn<<<grid, kWsThreads, t.smem, st>>>(a);
-    const int rc = launch_status();
-    if (rc) return rc;
+    if (plan_out != nullptr) {
+      if (n_launch < plan_cap) {
+        int32_t* o = plan_out + 8 * n_launch;
+        o[0] = CC; o[1] = N; o[2] = t.TH; o[3] = t.TW; o[4] = t.n_blk; o[5] = t.R; o[6] = t.ctas; o[7] = (int32_t)t.smem;
+      }
+    } else {
+      KernelFn fn = passes == 3 ? pick_r<3>(t.R, d.in_stats != nullptr) : pick_r<1>(t.R, d.in_stats != nullptr);
+      fn<<<grid, kWsThreads, t.smem, st>>>(a);
+      const int rc = launch_status();
+      if (rc) return rc;
+    }
+    ++n_launch;
     co_base += CC;
     remaining -= CC;
     w_off += 2 * plane_w;
   }
-  return 0;
+  return plan_out != nullptr ? n_launch : 0;
 }
 
 }  // namespace dmvs

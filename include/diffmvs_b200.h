@@ -125,6 +125,11 @@ int dmvs_conv_f32(const dmvs_conv_desc* desc, void* stream);
  * reference's `cudnn.benchmark = True`, test.py:18).  Launches nothing. */
 int dmvs_conv_backends(const dmvs_conv_desc* desc);
 
+/* Tile plan the width-stacked tcgen05 back end would use for `desc` (host only, launches nothing): per kernel launch
+ * eight ints {CC, N, TH, TW, M blocks, ring depth, CTAs per SM, shared-memory bytes} are written to out (capacity
+ * `cap` launches).  Returns the number of launches or DMVS_ERR_*.  Pointers in `desc` are only checked for alignment. */
+int dmvs_conv_ws_plan(const dmvs_conv_desc* desc, int32_t* out, int32_t cap);
+
 /* ConvTranspose3d(k=3, s=2, p=1, output_padding=1) + folded BN + ReLU + skip add
  * (module.Deconv3d as used by CostRegNet_small, module.py:110-144,436-437,445-446).
  * x [N][D][H][W][Cin] -> y [N][2D][2H][2W][Cout]; w packed [27][Cin][Cout]; skip has y's shape. */

@@ -5,8 +5,8 @@ O=gpurun_out
 timeout 500 python -m pytest tests/test_gpu_kernels.py -k "ws_tf32 or auto or unshuffle or bn_folding" -q --tb=short -p no:cacheprovider > $O/pytest_ws.log 2>&1
 echo "pytest_ws rc=$?" >> $O/pytest_ws.log
 tail -4 $O/pytest_ws.log
-for c in 2 3 4; do
-  DMVS_WS_MAXCTAS=$c timeout 300 python tools/bench_conv.py all ws_tf32x3 > $O/bench_conv_ctas$c.log 2>&1
+for c in 2 3; do
+  DMVS_WS_CTAS=$c timeout 300 python tools/bench_conv.py all ws_tf32x3 > $O/bench_conv_ctas$c.log 2>&1
 done
 timeout 300 python tools/bench_conv.py all fp32,tc_tf32x3,ws_tf32x3,ws_tf32 > $O/bench_conv.log 2>&1
 echo "bench_conv rc=$?" >> $O/bench_conv.log
