@@ -47,7 +47,8 @@ struct WsArgs {
   int n_blk;        // M=128 blocks per tile
   int tmem_cols;    // allocated TMEM columns (power of two >= 32)
   int tiles_x, tiles_y, total_tiles;
-  int stage_f;      // floats per ring slot: operand pair [hi | lo]; doubles as the epilogue's halo exchange buffer
+  int stage_f;      // floats per ring slot: operand pair [hi | lo]
+  int halo_f;       // floats of the epilogue's halo exchange buffer
   int vec_y, vec_res, vec_bias;
   int Hs, Ws;
   float inv_in_cols;
@@ -146,14 +147,14 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
   float* pair0 = smem;                                        // [R][stage_f]: pair = [hi | lo], raw data lands in hi
   float* w_hi0 = pair0 + R * a.stage_f;                       // [R][wslab_f]
   float* w_lo0 = w_hi0 + R * wslab_f;
-  float* gn_s = w_lo0 + (PASSES == 3 ? R * wslab_f : 0);      // [2][C1] when GN
+  float* halo_s = w_lo0 + (PASSES == 3 ? R * wslab_f : 0);    // [halo_f]: epilogue exchange of rows across lane quadrants
+  float* gn_s = halo_s + a.halo_f;                            // [2][C1] when GN
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) uint64_t mbar[2];   // stages alternate barriers: a parity wait may lag by one phase only
+  __shared__ __align__(8) uint64_t full_bar[R], empty_bar[R];
   __shared__ float stat_s[8];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
-  const bool worker = warp < 8;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
@@ -161,8 +162,10 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar[0])), "r"(1));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar[1])), "r"(1));
+    for (int i = 0; i < R; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full_bar[i])), "r"(kWorkers));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&empty_bar[i])), "r"(1));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -206,15 +209,23 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
     return first_stage_of(c.tile + (int)gridDim.x);
   };
 
-  // loads of one stage into ring slot `slot`: raw halo tile (planar by channel quad) and its weight slab.
-  // A thread owns a fixed (column, channel quad) unit of the tile and walks down the rows, so the per-copy work is
-  // a row predicate, one 64-bit multiply-add and the cp.async itself (the loader used to dominate the
-  // instruction stream: profiles/r1b_ncu_conv_ffma_vs_ws_v1.txt).
+  // ------------------------------------------------------------------------------------------------------------
+  // Warp-specialised pipeline.  Workers (warps 0-7) copy, split and - at the end of a tile - run the epilogue; warp 8
+  // issues the MMAs.  They meet only through mbarriers: full[slot] (256 worker arrivals: "my part of this stage is
+  // staged, split and fenced") and empty[slot] (one tcgen05.commit arrival: "every MMA issued so far has retired",
+  // which frees the slot and, after the last stage of a tile, publishes the accumulators).  A worker splits exactly
+  // the elements it copied itself, so workers never wait for each other inside the main loop.
+  // ------------------------------------------------------------------------------------------------------------
   const int ld_u0 = tid & (a.lanes_row - 1);
   const int ld_r0 = tid / a.lanes_row;
   const int ld_rstep = kWorkers / a.lanes_row;
-  auto issue_loads = [&](const Stage& s, int slot) {
-    if (worker && s.tile < a.total_tiles) {
+  const int up = d.in_up2 ? 1 : 0;
+
+  // copies of one stage into ring slot `slot`: raw halo tile (planar by channel quad) and its weight slab.  A thread
+  // owns fixed (column, channel quad) units and walks down the rows: per copy one predicate, one multiply-add, one
+  // cp.async.  Zero padding is written with plain stores.
+  auto copy_stage = [&](const Stage& s, int slot) {
+    if (s.tile < a.total_tiles) {
       const int c0 = s.chunk * 8;
       const int id = s.od * a.S + s.kd - d.pad_d;
       // phase (pa, pb): tile row r / column c hold input pixel (S*(ty0 + r + smin_h) + pa, S*(tx0 + c + smin_w) + pb)
@@ -229,8 +240,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
         const int ix = ix0 + a.S * col;
         const int ch = c0 + q * 4;
         const bool col_ok = ix >= 0 && ix < d.W && ch < Ctot;
-        const int sx = d.in_up2 ? (ix >> 1) : ix;
-        // pointer to (image row 0, column sx, channel ch) of this stage's depth slice; rows add sy * row_stride
+        const int sx = ix >> up;
         const bool from_x = ch < d.C1;
         const int ps = from_x ? d.x_ps : d.x2_ps;
         const float* base = from_x ? d.x + ch : d.x2 + (ch - d.C1);
@@ -239,7 +249,6 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
         const int row_stride = a.Ws * ps;            // one image plane stays below 2^31 floats (checked on the host)
         float* dst = a_raw + (q * a.plane + ld_r0 * a.in_cols + col) * 4;
         const int dst_step = ld_rstep * a.in_cols * 4;
-        const int up = d.in_up2 ? 1 : 0;
 #pragma unroll 2
         for (int row = ld_r0; row < a.in_rows; row += ld_rstep, dst += dst_step) {
           const int iy = iy0 + a.S * row;
@@ -250,7 +259,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
           }
         }
       }
-      // weights of this (kd, channel chunk): the host packed every slab [kh][quad][N][4] contiguously (w_ws)
+      // weights of this (kd, phase, channel chunk): the host packed every slab [kh'][quad][N][4] contiguously (w_ws)
       float* wh = w_hi0 + slot * wslab_f;
       float* wl = w_lo0 + slot * wslab_f;
       const float* src = d.w_ws + a.w_off + (int64_t)((s.kd * nphase + s.phase) * nchunks + s.chunk) * wslab_f;
@@ -261,94 +270,85 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
         if (PASSES == 3) cp_async16_full(wl + idx * 4, src + a.w_plane + idx * 4);
       }
     }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");   // always one group per stage slot (possibly empty)
+    asm volatile("cp.async.commit_group;\n" ::: "memory");   // always one group per stage (possibly empty)
+  };
+
+  // in-place (hi, lo) split (and GroupNorm+SiLU prologue) of exactly the elements this thread copied
+  auto split_stage = [&](const Stage& s, int slot) {
+    if (!(PASSES == 3 || GN)) return;
+    const int c0 = s.chunk * 8;
+    const int iy0 = s.ty0 + a.smin_h, ix0 = s.tx0 + a.smin_w;   // GN layers are stride 1
+    float* a_hi = pair0 + slot * a.stage_f;
+    const int lo_off = plane_f;
+#pragma unroll 1
+    for (int u = ld_u0; u < units_per_row; u += a.lanes_row) {
+      const int q = u & 1;
+      const int col = u >> 1;
+      const int ch = c0 + q * 4;
+      float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), g0 = g1;
+      bool col_ok = false;
+      if (GN) {
+        const int ix = ix0 + col;
+        col_ok = ix >= 0 && ix < d.W && ch < d.C1;
+        if (col_ok) {
+          g1 = *reinterpret_cast<const float4*>(gn_s + ch);
+          g0 = *reinterpret_cast<const float4*>(gn_s + d.C1 + ch);
+        }
+      }
+      float* ptr = a_hi + (q * a.plane + ld_r0 * a.in_cols + col) * 4;
+      const int step = ld_rstep * a.in_cols * 4;
+#pragma unroll 2
+      for (int row = ld_r0; row < a.in_rows; row += ld_rstep, ptr += step) {
+        float4 v = *reinterpret_cast<const float4*>(ptr);
+        if (GN) {
+          const int iy = iy0 + row;
+          if (col_ok && iy >= 0 && iy < d.H) {                 // padding stays zero
+            v.x = siluf_(fmaf(v.x, g1.x, g0.x));
+            v.y = siluf_(fmaf(v.y, g1.y, g0.y));
+            v.z = siluf_(fmaf(v.z, g1.z, g0.z));
+            v.w = siluf_(fmaf(v.w, g1.w, g0.w));
+          } else {
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (PASSES == 3) {
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(ptr) = h;
+          *reinterpret_cast<float4*>(ptr + lo_off) = l;
+        } else {
+          *reinterpret_cast<float4*>(ptr) = v;
+        }
+      }
+    }
   };
 
   Stage cur = first_stage_of((int)blockIdx.x);
   if (cur.tile < a.total_tiles) {
-    Stage pre = cur;
-#pragma unroll 1
-    for (int i = 0; i < R - 1; ++i) {   // prologue: R-1 stages in flight
-      issue_loads(pre, i);
-      if (pre.tile < a.total_tiles) pre = advance(pre);
-    }
-    int issued = 0, waited = 0;  // stages whose MMAs were committed / whose completion was consumed (in order)
-    bool tile_start = true;
-    int slot = 0;
-    int gn_n = -1;
-    auto wait_one = [&]() {      // stage t commits to mbar[t & 1]; its phase there has parity (t >> 1) & 1
-      mbar_wait(&mbar[waited & 1], (uint32_t)((waited >> 1) & 1));
-      ++waited;
-    };
-    for (;;) {
-      const int n = cur.n, od = cur.od, ty0 = cur.ty0, tx0 = cur.tx0;
-      cp_async_wait_ring<R>();                           // everything but the newest R-2 groups has landed
-      if (GN && n != gn_n) {                             // GroupNorm affine of the producer is per sample
-        for (int c = tid; c < d.C1; c += kWsThreads) groupnorm_affine(d, n, c, gn_s);   // (all 288 threads)
-        gn_n = n;
-      }
-      __syncthreads();                                   // raw data of `slot` (and gn_s) visible to every thread
-      float* a_hi = pair0 + slot * a.stage_f;
-      float* a_lo = a_hi + plane_f;
-      // ---- one pass over the staged tile: optional GroupNorm+SiLU, then the (hi, lo) split in place ----------
-      if ((PASSES == 3 || GN) && worker) {
-        const int total = 2 * a.plane;
-        const int iy0 = ty0 - d.pad_h, ix0 = tx0 - d.pad_w;
-        const int c0 = cur.chunk * 8;
-#pragma unroll 2
-        for (int u = tid; u < total; u += kWorkers) {
-          float4 v = *reinterpret_cast<const float4*>(a_hi + u * 4);
-          if (GN) {
-            const int q = u >= a.plane ? 1 : 0;
-            const int p = u - q * a.plane;
-            const int row = (int)(((float)p + 0.5f) * a.inv_in_cols);
-            const int col = p - row * a.in_cols;
-            const int iy = iy0 + row, ix = ix0 + col;
-            const int ch = c0 + q * 4;
-            if (row < a.in_rows && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W && ch < d.C1) {   // padding stays zero
-              const float4 g1 = *reinterpret_cast<const float4*>(gn_s + ch);
-              const float4 g0 = *reinterpret_cast<const float4*>(gn_s + d.C1 + ch);
-              v.x = siluf_(fmaf(v.x, g1.x, g0.x));
-              v.y = siluf_(fmaf(v.y, g1.y, g0.y));
-              v.z = siluf_(fmaf(v.z, g1.z, g0.z));
-              v.w = siluf_(fmaf(v.w, g1.w, g0.w));
-            } else {
-              v = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (PASSES == 3) {
-            float4 h, l;
-            split_tf32(v.x, h.x, l.x);
-            split_tf32(v.y, h.y, l.y);
-            split_tf32(v.z, h.z, l.z);
-            split_tf32(v.w, h.w, l.w);
-            *reinterpret_cast<float4*>(a_hi + u * 4) = h;
-            *reinterpret_cast<float4*>(a_lo + u * 4) = l;
-          } else {
-            *reinterpret_cast<float4*>(a_hi + u * 4) = v;
-          }
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-      __syncthreads();                                   // operands of this stage complete
-      // ---- warp 8 issues the MMAs (one elected lane): per M block and kernel row, all KW taps in one instruction.
-      // The workers go straight on to refill the ring, so the issue latency is off their critical path.
-      if (warp == 8) {
+    if (warp == 8) {
+      // =============================== MMA warp ===============================================================
+      const bool leader = elect_one();
+      const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
+      const uint32_t b_step = 2u * (uint32_t)N;                // one kernel row of weights, in 16-byte units
+      int slot = 0, use = 0;                                   // ring slot of `cur` and how often it was used before
+      bool tile_start = true;
+      for (;;) {
+        mbar_wait(&full_bar[slot], (uint32_t)(use & 1));       // operands of this stage staged, split and fenced
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
+        float* a_hi = pair0 + slot * a.stage_f;
+        float* a_lo = a_hi + plane_f;
         const uint64_t dah0 = umma_desc(smem_u32(a_hi), lbo_a, 128), dal0 = umma_desc(smem_u32(a_lo), lbo_a, 128);
         const uint64_t dbh0 = umma_desc(smem_u32(w_hi0 + slot * wslab_f), lbo_b, 128);
         const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + slot * wslab_f), lbo_b, 128);
-        const uint32_t b_step = 2u * (uint32_t)N;              // one kernel row of weights, in 16-byte units
         const int pa = a.S == 2 ? (cur.phase >> 1) : 0;
-        // kernel rows present in this phase: shift khe <-> kernel row S*(khe + smin_h) + pa + pad_h
-        uint32_t rows = 0;
+        uint32_t rows = 0;   // kernel rows present in this phase: shift khe <-> kernel row S*(khe + smin_h) + pa + pad_h
         for (int khe = 0; khe < a.KHe; ++khe) {
           const int kh = a.S * (khe + a.smin_h) + pa + d.pad_h;
           if (kh >= 0 && kh < d.KH) rows |= 1u << khe;
         }
-        const bool leader = elect_one();
         for (int blk = 0; blk < a.n_blk; ++blk) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(blk * N);
           uint32_t acc = tile_start ? 0u : 1u;
@@ -367,196 +367,223 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
             acc = 1u;
           }
         }
-        if (leader)
+        if (leader)   // arrives on empty[slot] once every MMA issued so far has retired
           asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
-                           smem_u32(&mbar[issued & 1]))
+                           smem_u32(&empty_bar[slot]))
                        : "memory");
         __syncwarp();
+        const Stage nxt = advance(cur);
+        tile_start = nxt.tile != cur.tile;
+        if (nxt.tile >= a.total_tiles) break;
+        cur = nxt;
+        if (++slot == R) { slot = 0; ++use; }
       }
-      ++issued;
-      // ---- keep the ring full: stage s+R-1 reuses the pair of stage s-1, whose MMAs must have retired ----------
-      if (issued - waited > 1) {
-        wait_one();
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    } else {
+      // =============================== workers ================================================================
+      Stage pre = cur;
+#pragma unroll 1
+      for (int i = 0; i < R - 1; ++i) {   // prologue: R-1 stages of copies in flight
+        copy_stage(pre, i);
+        if (pre.tile < a.total_tiles) pre = advance(pre);
       }
-      issue_loads(pre, (slot + R - 1) % R);
-      if (pre.tile < a.total_tiles) pre = advance(pre);
+      int slot = 0, use = 0;              // ring slot of `cur` / number of earlier uses of that slot
+      int pslot = R - 1, puse = 0;        // same for `pre`, the stage whose copies are issued next
+      int gn_n = -1;
+      const int quadrant = warp & 3, half = warp >> 2;
+      for (;;) {
+        // ---- refill: stage cur+R-1 reuses the slot of stage cur-1, whose MMAs must have retired ------------------
+        if (puse > 0 && pre.tile < a.total_tiles) {
+          mbar_wait(&empty_bar[pslot], (uint32_t)((puse - 1) & 1));
+        }
+        copy_stage(pre, pslot);
+        if (pre.tile < a.total_tiles) pre = advance(pre);
+        if (++pslot == R) { pslot = 0; ++puse; }
+        // ---- this thread's copies of stage `cur` have landed -> split them in place, publish ------------------------
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(R - 1) : "memory");
+        if (GN && cur.n != gn_n) {                        // GroupNorm affine of the producer is per sample
+          // every worker needs the whole table: recompute behind a worker barrier (once per sample)
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          for (int c = tid; c < d.C1; c += kWorkers) groupnorm_affine(d, cur.n, c, gn_s);
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          gn_n = cur.n;
+        }
+        split_stage(cur, slot);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[slot])) : "memory");
 
-      const Stage nxt = advance(cur);
-      const bool tile_done = nxt.tile != cur.tile;
-      tile_start = tile_done;
-      if (tile_done) {
-        // ---- all MMAs of the tile retired -> shift-add epilogue ------------------------------------------------
-        while (waited < issued) wait_one();
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        // A lane owns one accumulator row (position p) and 8 output channels: tap kw of its output lives in row
-        // p + kw, i.e. in lane + kw of the same warp (a shuffle) or, for the last KW-1 lanes, in the first rows of
-        // the next lane quadrant / next M block (a small shared "halo" written in a first pass).  Work items are
-        // (M block, channel octet) pairs, split between the two warp halves (warp % 4 = TMEM lane quadrant).
-        float* halo = pair0 + slot * a.stage_f;   // this stage's pair is dead now: [item][quadrant][kw-1][lane][8]
-        const int ncg = a.CC >> 3;
-        const int n_items = a.n_blk * ncg;
-        const int quadrant = warp & 3, half = warp >> 2;
-        const int KWm1 = a.KWe - 1;
-        const int halo_q = KWm1 * KWm1 * 8;       // floats per (item, quadrant)
-        const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
-        const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
-        const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
-        if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
-        if (KWm1 > 0 && worker) {
-          int blk = 0, cg = half;                                // items half, half + 2, ... as (block, octet)
+        const Stage nxt = advance(cur);
+        if (nxt.tile != cur.tile) {
+          // ---- last stage of the tile: wait for its MMAs, then the shift-add epilogue ----------------------------
+          const int n = cur.n, od = cur.od, ty0 = cur.ty0, tx0 = cur.tx0;
+          mbar_wait(&empty_bar[slot], (uint32_t)(use & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          // A lane owns one accumulator row (position p) and 8 output channels: tap kw of its output lives in row
+          // p + kw, i.e. in lane + kw of the same warp (a shuffle) or, for the last KW-1 lanes, in the first rows of
+          // the next lane quadrant / next M block (a small shared "halo" written in a first pass).  Work items are
+          // (M block, channel octet) pairs, split between the two warp halves (warp % 4 = TMEM lane quadrant).
+          float* halo = halo_s;                     // dedicated exchange buffer: [item][quadrant][kw-1][lane][8]
+          const int ncg = a.CC >> 3;
+          const int n_items = a.n_blk * ncg;
+          const int KWm1 = a.KWe - 1;
+          const int halo_q = KWm1 * KWm1 * 8;       // floats per (item, quadrant)
+          const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
+          const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
+          const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
+          if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
+          if (KWm1 > 0) {
+            int blk = 0, cg = half;                                // items half, half + 2, ... as (block, octet)
+            while (cg >= ncg) { cg -= ncg; ++blk; }
+  #pragma unroll 1
+            for (int it = half; it < n_items; it += 2) {          // pass 1: rows other quadrants will need
+              const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
+              float* hq = halo + (it * 4 + quadrant) * halo_q;
+  #pragma unroll 1
+              for (int kw = 1; kw < a.KWe; ++kw) {
+                float v[8];
+                tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
+                if (lane < kw) {
+                  float* dst = hq + ((kw - 1) * KWm1 + lane) * 8;
+                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+              }
+              cg += 2;
+              while (cg >= ncg) { cg -= ncg; ++blk; }
+            }
+          }
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");   // workers only: halo (and the zeroed statistics) visible
+          int blk = 0, cg = half;
           while (cg >= ncg) { cg -= ncg; ++blk; }
-#pragma unroll 1
-          for (int it = half; it < n_items; it += 2) {          // pass 1: rows other quadrants will need
+  #pragma unroll 1
+          for (int it = half; it < n_items; it += 2) {            // pass 2: shift-add, fused epilogue, store
             const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
-            float* hq = halo + (it * 4 + quadrant) * halo_q;
-#pragma unroll 1
+            const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
+            const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
+            float acc[8];
+            tmem_ld8(trow, acc);
+  #pragma unroll 1
             for (int kw = 1; kw < a.KWe; ++kw) {
               float v[8];
               tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
-              if (lane < kw) {
-                float* dst = hq + ((kw - 1) * KWm1 + lane) * 8;
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
+              if (lane + kw >= 32) {                              // the row lives in the next quadrant / block
+                if (have_next) {
+                  const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * 8;
+                  const float4 h0 = *reinterpret_cast<const float4*>(src), h1 = *reinterpret_cast<const float4*>(src + 4);
+                  v[0] = h0.x; v[1] = h0.y; v[2] = h0.z; v[3] = h0.w;
+                  v[4] = h1.x; v[5] = h1.y; v[6] = h1.z; v[7] = h1.w;
+                } else {
+  #pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j] = 0.0f;        // past the last block: never a valid output
+                }
+              }
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += v[j];
+            }
+            const int c0 = a.co_base + cg * 8;                    // first absolute output channel of this lane
+            const int p = blk * 128 + quadrant * 32 + lane;
+            const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
+            const int px = p - py * a.in_cols;
+            const int oy = ty0 + py, ox = tx0 + px;
+            const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
+            float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};   // per channel pair: sum, sum of squares
+            if (valid) {
+              const bool full8 = c0 + 8 <= d.Cout;
+              if (d.bias != nullptr) {
+                if (a.vec_bias && full8) {
+                  const float4 b0 = ldg4(d.bias + c0), b1 = ldg4(d.bias + c0 + 4);
+                  acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
+                  acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
+                } else {
+  #pragma unroll
+                  for (int k = 0; k < 8; ++k)
+                    if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
+                }
+              }
+              const int64_t opix = (img_base + oy) * d.Wo + ox;
+              int64_t rpix = opix;
+              if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+              if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+                float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (d.res_mode != DMVS_RES_NONE) {
+                  const float* rp = d.res + rpix * d.res_ps + c0;
+                  if (a.vec_res && full8) {
+                    const float4 r0 = ldg4(rp), r1 = ldg4(rp + 4);
+                    r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
+                    r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+                  } else {
+  #pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                      if (c0 + k < d.Cout) r[k] = __ldg(rp + k);
+                  }
+                }
+                const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+                if (relu_from <= c0) {          // the common case: ReLU on every channel of the octet
+  #pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    const float x = fmaxf(pre_act ? acc[k] + r[k] : acc[k], 0.0f);
+                    acc[k] = pre_act ? x : x + r[k];
+                  }
+                } else {
+  #pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    float x = pre_act ? acc[k] + r[k] : acc[k];
+                    if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
+                    acc[k] = pre_act ? x : x + r[k];
+                  }
+                }
+              } else {
+  #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if (c0 + k < d.Cout) acc[k] = epilogue_value(d, acc[k], c0 + k, opix, rpix);
+              }
+              float* yp = d.y + opix * d.y_ps + c0;
+              if (a.vec_y && full8) {
+                *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+              } else {
+  #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                  if (c0 + k < d.Cout) yp[k] = acc[k];
+              }
+              if (d.out_stats != nullptr) {
+  #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  const float x = c0 + k < d.Cout ? acc[k] : 0.0f;
+                  ps[k >> 1] += x;
+                  pq[k >> 1] += x * x;
+                }
+              }
+            }
+            if (d.out_stats != nullptr) {
+              // GroupNorm statistics: Cout/4 channels per group is 2, 4 or a multiple of 8 (checked on the host), so a
+              // channel pair never straddles two groups
+              const int cpg = d.Cout >> 2;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
+                const int c = c0 + 2 * j;
+                if (lane == 0 && c < d.Cout) {
+                  const int g = c / cpg;
+                  atomicAdd(&stat_s[g * 2 + 0], s);
+                  atomicAdd(&stat_s[g * 2 + 1], q);
+                }
               }
             }
             cg += 2;
             while (cg >= ncg) { cg -= ncg; ++blk; }
           }
-        }
-        __syncthreads();
-        int blk = 0, cg = half;
-        while (cg >= ncg) { cg -= ncg; ++blk; }
-#pragma unroll 1
-        for (int it = worker ? half : n_items; it < n_items; it += 2) {   // pass 2: shift-add, fused epilogue, store
-          const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
-          const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
-          const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
-          float acc[8];
-          tmem_ld8(trow, acc);
-#pragma unroll 1
-          for (int kw = 1; kw < a.KWe; ++kw) {
-            float v[8];
-            tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
-            if (lane + kw >= 32) {                              // the row lives in the next quadrant / block
-              if (have_next) {
-                const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * 8;
-                const float4 h0 = *reinterpret_cast<const float4*>(src), h1 = *reinterpret_cast<const float4*>(src + 4);
-                v[0] = h0.x; v[1] = h0.y; v[2] = h0.z; v[3] = h0.w;
-                v[4] = h1.x; v[5] = h1.y; v[6] = h1.z; v[7] = h1.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = 0.0f;        // past the last block: never a valid output
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += v[j];
-          }
-          const int c0 = a.co_base + cg * 8;                    // first absolute output channel of this lane
-          const int p = blk * 128 + quadrant * 32 + lane;
-          const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
-          const int px = p - py * a.in_cols;
-          const int oy = ty0 + py, ox = tx0 + px;
-          const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
-          float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};   // per channel pair: sum, sum of squares
-          if (valid) {
-            const bool full8 = c0 + 8 <= d.Cout;
-            if (d.bias != nullptr) {
-              if (a.vec_bias && full8) {
-                const float4 b0 = ldg4(d.bias + c0), b1 = ldg4(d.bias + c0 + 4);
-                acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
-                acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
-              } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
-              }
-            }
-            const int64_t opix = (img_base + oy) * d.Wo + ox;
-            int64_t rpix = opix;
-            if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
-            if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
-              float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-              if (d.res_mode != DMVS_RES_NONE) {
-                const float* rp = d.res + rpix * d.res_ps + c0;
-                if (a.vec_res && full8) {
-                  const float4 r0 = ldg4(rp), r1 = ldg4(rp + 4);
-                  r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
-                  r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-                } else {
-#pragma unroll
-                  for (int k = 0; k < 8; ++k)
-                    if (c0 + k < d.Cout) r[k] = __ldg(rp + k);
-                }
-              }
-              const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
-              if (relu_from <= c0) {          // the common case: ReLU on every channel of the octet
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float x = fmaxf(pre_act ? acc[k] + r[k] : acc[k], 0.0f);
-                  acc[k] = pre_act ? x : x + r[k];
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  float x = pre_act ? acc[k] + r[k] : acc[k];
-                  if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
-                  acc[k] = pre_act ? x : x + r[k];
-                }
-              }
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (c0 + k < d.Cout) acc[k] = epilogue_value(d, acc[k], c0 + k, opix, rpix);
-            }
-            float* yp = d.y + opix * d.y_ps + c0;
-            if (a.vec_y && full8) {
-              *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-              *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            } else {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (c0 + k < d.Cout) yp[k] = acc[k];
-            }
-            if (d.out_stats != nullptr) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const float x = c0 + k < d.Cout ? acc[k] : 0.0f;
-                ps[k >> 1] += x;
-                pq[k >> 1] += x * x;
-              }
-            }
-          }
           if (d.out_stats != nullptr) {
-            // GroupNorm statistics: Cout/4 channels per group is 2, 4 or a multiple of 8 (checked on the host), so a
-            // channel pair never straddles two groups
-            const int cpg = d.Cout >> 2;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
-              const int c = c0 + 2 * j;
-              if (lane == 0 && c < d.Cout) {
-                const int g = c / cpg;
-                atomicAdd(&stat_s[g * 2 + 0], s);
-                atomicAdd(&stat_s[g * 2 + 1], q);
-              }
-            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");   // every worker's shared atomics are in
+            if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
           }
-          cg += 2;
-          while (cg >= ncg) { cg -= ncg; ++blk; }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next full[] arrival
         }
-        __syncthreads();   // halo reads done before the next stage's loads land here; statistics complete
-        if (d.out_stats != nullptr) {
-          if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
-          __syncthreads();
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads done before the next tile's MMAs
+        if (nxt.tile >= a.total_tiles) break;
+        cur = nxt;
+        if (++slot == R) { slot = 0; ++use; }
       }
-      if (nxt.tile >= a.total_tiles) break;
-      cur = nxt;
-      slot = (slot + 1) % R;
     }
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -586,7 +613,7 @@ KernelFn pick_r(int r, bool gn) {
 }
 
 struct TileCfg {
-  int TH = 0, TW = 0, in_cols = 0, n_blk = 0, plane = 0, R = 0, stage_f = 0, ctas = 0;
+  int TH = 0, TW = 0, in_cols = 0, n_blk = 0, plane = 0, R = 0, stage_f = 0, halo_f = 0, ctas = 0;
   size_t smem = 0;
   double est = 1e30;   // modelled cycles for the whole launch
 };
@@ -600,7 +627,7 @@ void choose_tile(const dmvs_conv_desc& d, int KHe, int KWe, int N, int CC, int p
   static const int force_r = getenv("DMVS_WS_R") ? atoi(getenv("DMVS_WS_R")) : 0;
   static const int force_ctas = getenv("DMVS_WS_CTAS") ? atoi(getenv("DMVS_WS_CTAS")) : 0;
   const int nchunks = cin_pad >> 3;
-  static const int max_ctas = getenv("DMVS_WS_MAXCTAS") ? atoi(getenv("DMVS_WS_MAXCTAS")) : 3;
+  static const int max_ctas = getenv("DMVS_WS_MAXCTAS") ? atoi(getenv("DMVS_WS_MAXCTAS")) : 2;   // 3-4 measured slower
   for (int ctas = max_ctas; ctas >= 1; --ctas) {
     if (force_ctas && ctas != force_ctas) continue;
     // co-resident CTAs share 227 KB of shared memory and 512 TMEM columns (allocations are powers of two)
@@ -622,13 +649,12 @@ void choose_tile(const dmvs_conv_desc& d, int KHe, int KWe, int N, int CC, int p
         if (n_blk > max_blk) continue;
         const int plane = (n_blk * 128 + (KHe - 1) * in_cols + 8 + 7) & ~7;
         size_t work_f = (size_t)(passes == 3 ? 2 : 1) * 2 * plane * 4;
-        const size_t halo_f = (size_t)n_blk * (CC / 8) * 4 * (KWe - 1) * (KWe - 1) * 8;   // epilogue halo exchange
-        if (work_f < halo_f) work_f = halo_f;
+        const size_t halo_f = ((size_t)n_blk * (CC / 8) * 4 * (KWe - 1) * (KWe - 1) * 8 + 31) & ~(size_t)31;   // epilogue halo exchange
         work_f = (work_f + 31) & ~(size_t)31;
         const size_t wslab_f = (size_t)KHe * 2 * N * 4;
         for (int r = 3; r >= 2; --r) {
           if (force_r && r != force_r) continue;
-          const size_t need = (r * work_f + (passes == 3 ? 2 : 1) * r * wslab_f + 2 * (size_t)d.C1 + 8) * 4;
+          const size_t need = (r * work_f + (passes == 3 ? 2 : 1) * r * wslab_f + halo_f + 2 * (size_t)d.C1 + 8) * 4;
           if (need > smem_limit) continue;
           // ---- cycle model ------------------------------------------------------------------------
           const double mma = (double)n_blk * d.KH / d.stride * passes * (N / 2 > 32 ? N / 2 : 32);   // A read 32 clk or math N/2
@@ -649,7 +675,7 @@ void choose_tile(const dmvs_conv_desc& d, int KHe, int KWe, int N, int CC, int p
           const double est = waves * tile;
           if (est < best.est) {
             best.TH = th; best.TW = TW; best.in_cols = in_cols; best.n_blk = n_blk; best.plane = plane; best.R = r;
-            best.stage_f = (int)work_f; best.smem = need; best.est = est; best.ctas = ctas;
+            best.stage_f = (int)work_f; best.halo_f = (int)halo_f; best.smem = need; best.est = est; best.ctas = ctas;
           }
         }
       }
@@ -738,6 +764,7 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out
     a.plane = t.plane;
     a.n_blk = t.n_blk;
     a.stage_f = t.stage_f;
+    a.halo_f = t.halo_f;
     a.inv_in_cols = 1.0f / (float)t.in_cols;
     int lanes = 32;
     while (lanes < 2 * t.in_cols && lanes < kWorkers) lanes <<= 1;
