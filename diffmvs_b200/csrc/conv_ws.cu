@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
   }
   if (tid == 0) {
     for (int i = 0; i < R; ++i) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full_bar[i])), "r"(kWorkers));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&full_bar[i])), "r"(kWorkers / 32));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&empty_bar[i])), "r"(1));
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n");
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
 
   // ------------------------------------------------------------------------------------------------------------
   // Warp-specialised pipeline.  Workers (warps 0-7) copy, split and - at the end of a tile - run the epilogue; warp 8
-  // issues the MMAs.  They meet only through mbarriers: full[slot] (256 worker arrivals: "my part of this stage is
+  // issues the MMAs.  They meet only through mbarriers: full[slot] (one arrival per worker warp: "our part of this stage is
   // staged, split and fenced") and empty[slot] (one tcgen05.commit arrival: "every MMA issued so far has retired",
   // which frees the slot and, after the last stage of a tile, publishes the accumulators).  A worker splits exactly
   // the elements it copied itself, so workers never wait for each other inside the main loop.
@@ -391,15 +391,8 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
       int gn_n = -1;
       const int quadrant = warp & 3, half = warp >> 2;
       for (;;) {
-        // ---- refill: stage cur+R-1 reuses the slot of stage cur-1, whose MMAs must have retired ------------------
-        if (puse > 0 && pre.tile < a.total_tiles) {
-          mbar_wait(&empty_bar[pslot], (uint32_t)((puse - 1) & 1));
-        }
-        copy_stage(pre, pslot);
-        if (pre.tile < a.total_tiles) pre = advance(pre);
-        if (++pslot == R) { pslot = 0; ++puse; }
         // ---- this thread's copies of stage `cur` have landed -> split them in place, publish ------------------------
-        asm volatile("cp.async.wait_group %0;\n" ::"n"(R - 1) : "memory");
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(R - 2) : "memory");
         if (GN && cur.n != gn_n) {                        // GroupNorm affine of the producer is per sample
           // every worker needs the whole table: recompute behind a worker barrier (once per sample)
           asm volatile("bar.sync 1, 256;\n" ::: "memory");
@@ -409,7 +402,17 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
         }
         split_stage(cur, slot);
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[slot])) : "memory");
+        __syncwarp();                                      // one arrival per warp: the lanes' writes are ordered before it
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&full_bar[slot])) : "memory");
+        // ---- refill: stage cur+R-1 reuses the slot of stage cur-1, whose MMAs must have retired (the MMAs of `cur`
+        // run meanwhile; the split above did not have to wait for them) -----------------------------------------------
+        if (puse > 0 && pre.tile < a.total_tiles) {
+          mbar_wait(&empty_bar[pslot], (uint32_t)((puse - 1) & 1));
+        }
+        copy_stage(pre, pslot);
+        if (pre.tile < a.total_tiles) pre = advance(pre);
+        if (++pslot == R) { pslot = 0; ++puse; }
 
         const Stage nxt = advance(cur);
         if (nxt.tile != cur.tile) {
