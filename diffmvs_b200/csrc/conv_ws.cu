@@ -96,10 +96,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(done)
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");
-    if (!done) {
-      __nanosleep(20);                             // keep the issue slots for the warps that have work
-      if (++spins > (1u << 22)) __trap();          // watchdog: a lost arrival must not hang the GPU
-    }
+    if (!done && ++spins > (1u << 24)) __trap();   // watchdog: a lost commit must not hang the GPU
   }
 }
 
@@ -252,7 +249,7 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
         const int row_stride = a.Ws * ps;            // one image plane stays below 2^31 floats (checked on the host)
         float* dst = a_raw + (q * a.plane + ld_r0 * a.in_cols + col) * 4;
         const int dst_step = ld_rstep * a.in_cols * 4;
-#pragma unroll 4
+#pragma unroll 2
         for (int row = ld_r0; row < a.in_rows; row += ld_rstep, dst += dst_step) {
           const int iy = iy0 + a.S * row;
           if (col_ok && iy >= 0 && iy < d.H) {
@@ -300,39 +297,30 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
       }
       float* ptr = a_hi + (q * a.plane + ld_r0 * a.in_cols + col) * 4;
       const int step = ld_rstep * a.in_cols * 4;
-      // four rows per trip: the shared loads are issued together, so their latency overlaps
-#pragma unroll 1
-      for (int row = ld_r0; row < a.in_rows; row += 4 * ld_rstep, ptr += 4 * step) {
-        float4 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (row + j * ld_rstep < a.in_rows) v[j] = *reinterpret_cast<const float4*>(ptr + j * step);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (row + j * ld_rstep >= a.in_rows) break;
-          float4 x = v[j];
-          if (GN) {
-            const int iy = iy0 + row + j * ld_rstep;
-            if (col_ok && iy >= 0 && iy < d.H) {                 // padding stays zero
-              x.x = siluf_(fmaf(x.x, g1.x, g0.x));
-              x.y = siluf_(fmaf(x.y, g1.y, g0.y));
-              x.z = siluf_(fmaf(x.z, g1.z, g0.z));
-              x.w = siluf_(fmaf(x.w, g1.w, g0.w));
-            } else {
-              x = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-          if (PASSES == 3) {
-            float4 h, l;
-            split_tf32(x.x, h.x, l.x);
-            split_tf32(x.y, h.y, l.y);
-            split_tf32(x.z, h.z, l.z);
-            split_tf32(x.w, h.w, l.w);
-            *reinterpret_cast<float4*>(ptr + j * step) = h;
-            *reinterpret_cast<float4*>(ptr + j * step + lo_off) = l;
+#pragma unroll 2
+      for (int row = ld_r0; row < a.in_rows; row += ld_rstep, ptr += step) {
+        float4 v = *reinterpret_cast<const float4*>(ptr);
+        if (GN) {
+          const int iy = iy0 + row;
+          if (col_ok && iy >= 0 && iy < d.H) {                 // padding stays zero
+            v.x = siluf_(fmaf(v.x, g1.x, g0.x));
+            v.y = siluf_(fmaf(v.y, g1.y, g0.y));
+            v.z = siluf_(fmaf(v.z, g1.z, g0.z));
+            v.w = siluf_(fmaf(v.w, g1.w, g0.w));
           } else {
-            *reinterpret_cast<float4*>(ptr + j * step) = x;
+            v = make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        }
+        if (PASSES == 3) {
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(ptr) = h;
+          *reinterpret_cast<float4*>(ptr + lo_off) = l;
+        } else {
+          *reinterpret_cast<float4*>(ptr) = v;
         }
       }
     }
