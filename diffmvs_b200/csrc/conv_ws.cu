@@ -22,6 +22,7 @@
 //     accumulators the other one's MMAs keep the tensor pipe busy - overlap without warp specialisation.
 //   * Stages = (tile, depth tap, 8 input channels) stream through an R-deep cp.async ring exactly as in conv_tc.cu.
 #include <cstdlib>
+#include <type_traits>
 
 #include "conv_common.cuh"
 
@@ -115,14 +116,31 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
 }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
+// TMEM -> registers: NCH consecutive fp32 columns of this thread's lane (32x32b shape); no wait inside
+template <int NCH>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NCH]);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+        "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+      : "r"(taddr));
+}
+// every register written by earlier tcgen05.ld of this thread is valid after this
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// The compiler does not know that tcgen05.ld results only exist after the wait: route the registers through an empty
+// volatile asm placed after it, so that no use of them can be scheduled above the wait (costs no instruction).
+template <int NCH>
+__device__ __forceinline__ void tmem_pin(float (&v)[NCH]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+  for (int j = 0; j < NCH; ++j) asm volatile("" : "+f"(v[j])::"memory");
 }
 
 // 16-byte asynchronous copy without the src-size operand (the zero-fill form costs ~10 extra instructions of
@@ -138,7 +156,7 @@ __device__ __forceinline__ void cp_async_wait_ring() {
 
 // PASSES = 1 (TF32) or 3 (3xTF32), R = ring depth (2, 3), GN = GroupNorm+SiLU prologue in the split pass
 template <int PASSES, int R, bool GN>
-__global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_constant__ WsArgs a) {
+__global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_constant__ WsArgs a) {
   const dmvs_conv_desc& d = a.d;
   extern __shared__ __align__(128) float smem[];
   const int N = a.N;
@@ -326,6 +344,200 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
     }
   };
 
+  // Shift-add epilogue of one tile (workers only; see the call site).  All TMEM loads of an item are issued before
+  // the single wait when the kernel row has at most three taps (every 3x3 layer), so their latency overlaps.
+  auto epilogue = [&](auto nch_tag, int n, int od, int ty0, int tx0, int quadrant, int half) {
+    constexpr int NCH = decltype(nch_tag)::value;
+    float* halo = halo_s;                     // [item][quadrant][kw-1][lane][NCH]
+    const int ncg = a.CC / NCH;
+    const int n_items = a.n_blk * ncg;
+    const int KWe = a.KWe, KWm1 = KWe - 1;
+    const int halo_q = KWm1 * KWm1 * NCH;     // floats per (item, quadrant)
+    const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
+    const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
+    const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
+    if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
+    if (KWm1 > 0) {
+      int blk = 0, cg = half;                                // items half, half + 2, ... as (block, channel group)
+      while (cg >= ncg) { cg -= ncg; ++blk; }
+#pragma unroll 1
+      for (int it = half; it < n_items; it += 2) {          // pass 1: rows other quadrants will need
+        const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * NCH);
+        float* hq = halo + (it * 4 + quadrant) * halo_q;
+#pragma unroll 1
+        for (int kw = 1; kw < KWe; ++kw) {
+          float v[NCH];
+          tmem_ld<NCH>(trow + (uint32_t)(kw * a.CC), v);
+          tmem_wait_ld();
+          tmem_pin(v);
+          if (lane < kw) {
+            float* dst = hq + ((kw - 1) * KWm1 + lane) * NCH;
+#pragma unroll
+            for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+        cg += 2;
+        while (cg >= ncg) { cg -= ncg; ++blk; }
+      }
+    }
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");   // workers only: halo (and the zeroed statistics) visible
+    int blk = 0, cg = half;
+    while (cg >= ncg) { cg -= ncg; ++blk; }
+#pragma unroll 1
+    for (int it = half; it < n_items; it += 2) {            // pass 2: shift-add, fused epilogue, store
+      const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * NCH);
+      const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
+      const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
+      // value of tap kw for this lane's output: row of lane + kw (shuffle) or the halo of the next quadrant / block
+      auto shift_in = [&](float (&v)[NCH], int kw) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
+        if (lane + kw >= 32) {
+          if (have_next) {
+            const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * NCH;
+#pragma unroll
+            for (int j = 0; j < NCH; j += 4) {
+              const float4 h4 = *reinterpret_cast<const float4*>(src + j);
+              v[j] = h4.x; v[j + 1] = h4.y; v[j + 2] = h4.z; v[j + 3] = h4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) v[j] = 0.0f;      // past the last block: never a valid output
+          }
+        }
+      };
+      float acc[NCH];
+      if (KWe == 3) {
+        float v1[NCH], v2[NCH];
+        tmem_ld<NCH>(trow, acc);
+        tmem_ld<NCH>(trow + (uint32_t)a.CC, v1);
+        tmem_ld<NCH>(trow + (uint32_t)(2 * a.CC), v2);
+        tmem_wait_ld();
+        tmem_pin(acc);
+        tmem_pin(v1);
+        tmem_pin(v2);
+        shift_in(v1, 1);
+        shift_in(v2, 2);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) acc[j] = (acc[j] + v1[j]) + v2[j];
+      } else {
+        tmem_ld<NCH>(trow, acc);
+        tmem_wait_ld();
+        tmem_pin(acc);
+#pragma unroll 1
+        for (int kw = 1; kw < KWe; ++kw) {
+          float v[NCH];
+          tmem_ld<NCH>(trow + (uint32_t)(kw * a.CC), v);
+          tmem_wait_ld();
+          tmem_pin(v);
+          shift_in(v, kw);
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) acc[j] += v[j];
+        }
+      }
+      const int c0 = a.co_base + cg * NCH;                  // first absolute output channel of this lane
+      const int p = blk * 128 + quadrant * 32 + lane;
+      const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
+      const int px = p - py * a.in_cols;
+      const int oy = ty0 + py, ox = tx0 + px;
+      const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
+      float ps[NCH / 2], pq[NCH / 2];                       // per channel pair: sum, sum of squares
+#pragma unroll
+      for (int j = 0; j < NCH / 2; ++j) ps[j] = pq[j] = 0.0f;
+      if (valid) {
+        const bool full = c0 + NCH <= d.Cout;
+        if (d.bias != nullptr) {
+          if (a.vec_bias && full) {
+#pragma unroll
+            for (int j = 0; j < NCH; j += 4) {
+              const float4 b4 = ldg4(d.bias + c0 + j);
+              acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+              if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
+          }
+        }
+        const int64_t opix = (img_base + oy) * d.Wo + ox;
+        int64_t rpix = opix;
+        if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+        if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+          const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+          if (d.res_mode != DMVS_RES_NONE) {
+            float r[NCH];
+            const float* rp = d.res + rpix * d.res_ps + c0;
+            if (a.vec_res && full) {
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4) {
+                const float4 r4 = ldg4(rp + j);
+                r[j] = r4.x; r[j + 1] = r4.y; r[j + 2] = r4.z; r[j + 3] = r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) r[k] = c0 + k < d.Cout ? __ldg(rp + k) : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              float x = pre_act ? acc[k] + r[k] : acc[k];
+              if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
+              acc[k] = pre_act ? x : x + r[k];
+            }
+          } else if (relu_from <= c0) {                     // the common case: ReLU on every channel
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) acc[k] = fmaxf(acc[k], 0.0f);
+          } else if (relu_from < c0 + NCH) {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+              if (c0 + k >= relu_from) acc[k] = fmaxf(acc[k], 0.0f);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < NCH; ++k)
+            if (c0 + k < d.Cout) acc[k] = epilogue_value(d, acc[k], c0 + k, opix, rpix);
+        }
+        float* yp = d.y + opix * d.y_ps + c0;
+        if (a.vec_y && full) {
+#pragma unroll
+          for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < NCH; ++k)
+            if (c0 + k < d.Cout) yp[k] = acc[k];
+        }
+        if (d.out_stats != nullptr) {
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const float x = c0 + k < d.Cout ? acc[k] : 0.0f;
+            ps[k >> 1] += x;
+            pq[k >> 1] += x * x;
+          }
+        }
+      }
+      if (d.out_stats != nullptr) {
+        // GroupNorm statistics: Cout/4 channels per group is 2, 4 or a multiple of 8 (checked on the host), so a
+        // channel pair never straddles two groups
+        const int cpg = d.Cout >> 2;
+#pragma unroll
+        for (int j = 0; j < NCH / 2; ++j) {
+          const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
+          const int c = c0 + 2 * j;
+          if (lane == 0 && c < d.Cout) {
+            const int g = c / cpg;
+            atomicAdd(&stat_s[g * 2 + 0], s);
+            atomicAdd(&stat_s[g * 2 + 1], q);
+          }
+        }
+      }
+      cg += 2;
+      while (cg >= ncg) { cg -= ncg; ++blk; }
+    }
+    if (d.out_stats != nullptr) {
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // every worker's shared atomics are in
+      if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+    }
+  };
+
   Stage cur = first_stage_of((int)blockIdx.x);
   if (cur.tile < a.total_tiles) {
     if (warp == 8) {
@@ -420,167 +632,14 @@ __global__ void __launch_bounds__(kWsThreads, 3) conv_ws_kernel(const __grid_con
           const int n = cur.n, od = cur.od, ty0 = cur.ty0, tx0 = cur.tx0;
           mbar_wait(&empty_bar[slot], (uint32_t)(use & 1));
           asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-          // A lane owns one accumulator row (position p) and 8 output channels: tap kw of its output lives in row
-          // p + kw, i.e. in lane + kw of the same warp (a shuffle) or, for the last KW-1 lanes, in the first rows of
-          // the next lane quadrant / next M block (a small shared "halo" written in a first pass).  Work items are
-          // (M block, channel octet) pairs, split between the two warp halves (warp % 4 = TMEM lane quadrant).
-          float* halo = halo_s;                     // dedicated exchange buffer: [item][quadrant][kw-1][lane][8]
-          const int ncg = a.CC >> 3;
-          const int n_items = a.n_blk * ncg;
-          const int KWm1 = a.KWe - 1;
-          const int halo_q = KWm1 * KWm1 * 8;       // floats per (item, quadrant)
-          const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
-          const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
-          const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
-          if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
-          if (KWm1 > 0) {
-            int blk = 0, cg = half;                                // items half, half + 2, ... as (block, octet)
-            while (cg >= ncg) { cg -= ncg; ++blk; }
-  #pragma unroll 1
-            for (int it = half; it < n_items; it += 2) {          // pass 1: rows other quadrants will need
-              const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
-              float* hq = halo + (it * 4 + quadrant) * halo_q;
-  #pragma unroll 1
-              for (int kw = 1; kw < a.KWe; ++kw) {
-                float v[8];
-                tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
-                if (lane < kw) {
-                  float* dst = hq + ((kw - 1) * KWm1 + lane) * 8;
-                  *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                  *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                }
-              }
-              cg += 2;
-              while (cg >= ncg) { cg -= ncg; ++blk; }
-            }
-          }
-          asm volatile("bar.sync 1, 256;\n" ::: "memory");   // workers only: halo (and the zeroed statistics) visible
-          int blk = 0, cg = half;
-          while (cg >= ncg) { cg -= ncg; ++blk; }
-  #pragma unroll 1
-          for (int it = half; it < n_items; it += 2) {            // pass 2: shift-add, fused epilogue, store
-            const uint32_t trow = tmem_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * 8);
-            const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
-            const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
-            float acc[8];
-            tmem_ld8(trow, acc);
-  #pragma unroll 1
-            for (int kw = 1; kw < a.KWe; ++kw) {
-              float v[8];
-              tmem_ld8(trow + (uint32_t)(kw * a.CC), v);
-  #pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
-              if (lane + kw >= 32) {                              // the row lives in the next quadrant / block
-                if (have_next) {
-                  const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * 8;
-                  const float4 h0 = *reinterpret_cast<const float4*>(src), h1 = *reinterpret_cast<const float4*>(src + 4);
-                  v[0] = h0.x; v[1] = h0.y; v[2] = h0.z; v[3] = h0.w;
-                  v[4] = h1.x; v[5] = h1.y; v[6] = h1.z; v[7] = h1.w;
-                } else {
-  #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = 0.0f;        // past the last block: never a valid output
-                }
-              }
-  #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] += v[j];
-            }
-            const int c0 = a.co_base + cg * 8;                    // first absolute output channel of this lane
-            const int p = blk * 128 + quadrant * 32 + lane;
-            const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
-            const int px = p - py * a.in_cols;
-            const int oy = ty0 + py, ox = tx0 + px;
-            const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
-            float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};   // per channel pair: sum, sum of squares
-            if (valid) {
-              const bool full8 = c0 + 8 <= d.Cout;
-              if (d.bias != nullptr) {
-                if (a.vec_bias && full8) {
-                  const float4 b0 = ldg4(d.bias + c0), b1 = ldg4(d.bias + c0 + 4);
-                  acc[0] += b0.x; acc[1] += b0.y; acc[2] += b0.z; acc[3] += b0.w;
-                  acc[4] += b1.x; acc[5] += b1.y; acc[6] += b1.z; acc[7] += b1.w;
-                } else {
-  #pragma unroll
-                  for (int k = 0; k < 8; ++k)
-                    if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
-                }
-              }
-              const int64_t opix = (img_base + oy) * d.Wo + ox;
-              int64_t rpix = opix;
-              if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
-              if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
-                float r[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (d.res_mode != DMVS_RES_NONE) {
-                  const float* rp = d.res + rpix * d.res_ps + c0;
-                  if (a.vec_res && full8) {
-                    const float4 r0 = ldg4(rp), r1 = ldg4(rp + 4);
-                    r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w;
-                    r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-                  } else {
-  #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                      if (c0 + k < d.Cout) r[k] = __ldg(rp + k);
-                  }
-                }
-                const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
-                if (relu_from <= c0) {          // the common case: ReLU on every channel of the octet
-  #pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    const float x = fmaxf(pre_act ? acc[k] + r[k] : acc[k], 0.0f);
-                    acc[k] = pre_act ? x : x + r[k];
-                  }
-                } else {
-  #pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    float x = pre_act ? acc[k] + r[k] : acc[k];
-                    if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
-                    acc[k] = pre_act ? x : x + r[k];
-                  }
-                }
-              } else {
-  #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  if (c0 + k < d.Cout) acc[k] = epilogue_value(d, acc[k], c0 + k, opix, rpix);
-              }
-              float* yp = d.y + opix * d.y_ps + c0;
-              if (a.vec_y && full8) {
-                *reinterpret_cast<float4*>(yp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                *reinterpret_cast<float4*>(yp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-              } else {
-  #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                  if (c0 + k < d.Cout) yp[k] = acc[k];
-              }
-              if (d.out_stats != nullptr) {
-  #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                  const float x = c0 + k < d.Cout ? acc[k] : 0.0f;
-                  ps[k >> 1] += x;
-                  pq[k >> 1] += x * x;
-                }
-              }
-            }
-            if (d.out_stats != nullptr) {
-              // GroupNorm statistics: Cout/4 channels per group is 2, 4 or a multiple of 8 (checked on the host), so a
-              // channel pair never straddles two groups
-              const int cpg = d.Cout >> 2;
-  #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
-                const int c = c0 + 2 * j;
-                if (lane == 0 && c < d.Cout) {
-                  const int g = c / cpg;
-                  atomicAdd(&stat_s[g * 2 + 0], s);
-                  atomicAdd(&stat_s[g * 2 + 1], q);
-                }
-              }
-            }
-            cg += 2;
-            while (cg >= ncg) { cg -= ncg; ++blk; }
-          }
-          if (d.out_stats != nullptr) {
-            asm volatile("bar.sync 1, 256;\n" ::: "memory");   // every worker's shared atomics are in
-            if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
-          }
+          // A lane owns one accumulator row (position p) and NCH = 8 or 16 output channels: tap kw of its output lives in
+          // row p + kw, i.e. in lane + kw of the same warp (a shuffle) or, for the last KW-1 lanes, in the first rows
+          // of the next lane quadrant / next M block (a small shared "halo" written in a first pass).  Work items are
+          // (M block, channel group) pairs, split between the two warp halves (warp % 4 = TMEM lane quadrant).
+          if ((a.CC & 15) == 0)
+            epilogue(std::integral_constant<int, 16>{}, n, od, ty0, tx0, quadrant, half);
+          else
+            epilogue(std::integral_constant<int, 8>{}, n, od, ty0, tx0, quadrant, half);
           asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads ordered before the next full[] arrival
         }
         if (nxt.tile >= a.total_tiles) break;
