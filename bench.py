@@ -162,6 +162,8 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.lib()
+    if a.load_tuned:
+        ops.load_tuned(a.load_tuned)
 
     variant, H, W, V, D0 = synth.WORKLOADS[a.workload]
     args = synth.workload_args(a.workload)
@@ -342,11 +344,7 @@ def run_ours(a):
     }
     print(json.dumps(line), flush=True)
     if a.dump_tuned:
-        names = {v: k for k, v in ops.PRECISIONS.items()}
-        rows = [{"sig": list(map(int, k)), "choice": names[c], "ms": {names[m]: t for m, t in ts.items()}}
-                for k, (c, ts) in ops.tuned_table().items()]
-        with open(a.dump_tuned, "w") as f:
-            json.dump(rows, f, indent=0)
+        ops.save_tuned(a.dump_tuned)
     if world > 1:
         dist.destroy_process_group()
 
@@ -362,6 +360,8 @@ def main():
     ap.add_argument("--no-alt-modes", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")
     ap.add_argument("--dump-tuned", default=None, help="write the per-layer autotuning table (JSON) to this path")
+    ap.add_argument("--load-tuned", default=None, help="preload an autotuning table (use under a profiler, whose "
+                    "timings would mislead the tuner)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -58,6 +58,29 @@ def set_autotune(enabled: bool, use_ws: Optional[bool] = None) -> None:
     _TUNED.clear()
 
 
+def save_tuned(path: str) -> None:
+    """Write the autotuning table as JSON (signature -> chosen back end and the measured times)."""
+    import json
+    names = {v: k for k, v in PRECISIONS.items()}
+    rows = [{"sig": [int(x) for x in k], "choice": names[c], "ms": {names[m]: t for m, t in ts.items()}}
+            for k, (c, ts) in _TUNED.items()]
+    with open(path, "w") as f:
+        json.dump(rows, f, indent=0)
+
+
+def load_tuned(path: str) -> int:
+    """Preload the autotuning table written by `save_tuned` (e.g. so that a run under a profiler, whose timings are
+    distorted, uses the back ends a normal run chose).  Returns the number of entries."""
+    import json
+    with open(path) as f:
+        rows = json.load(f)
+    for r in rows:
+        sig = r["sig"]
+        key = tuple(sig[:15]) + (bool(sig[15]),) + tuple(sig[16:])
+        _TUNED[key] = (PRECISIONS[r["choice"]], {PRECISIONS[m]: t for m, t in r.get("ms", {}).items()})
+    return len(rows)
+
+
 def tuned_table() -> dict:
     """signature -> (chosen precision code, {code: ms}) of every convolution tuned so far."""
     return dict(_TUNED)
