@@ -309,9 +309,20 @@ def run_ours(a):
     top_name = max(fam, key=lambda k: fam[k]["ms"]) if fam else "n/a"
     top = fam.get(top_name, {"ms": 1.0, "bytes": 0, "calls": 1})
     achieved = top["bytes"] / (top["ms"] / 1e3) / 1e9 if top["ms"] > 0 else 0.0
+    # DRAM traffic of the same kernel family over one step, from the committed ncu capture (profiles/); per step, like
+    # the algorithmic bytes behind `achieved`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "conv_dram_traffic.json")
+    if top_name == "conv" and a.workload == "cfg3" and os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic, traffic_src = float(tj["conv_dram_bytes_per_step"]), tj.get("source")
+        except Exception:
+            pass
     roofline = {
         "bound": "hbm", "kernel": f"dmvs_{top_name} (all launches of one step)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_bytes": top["bytes"], "peak_source": peak_src,
         "share_of_step": top["ms"] / tot_ms, "launches_per_step": top["calls"],
         "whole_step": {"algorithmic_bytes": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7),
                        "achieved": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7) / (ms_step / 1e3) / 1e9,
