@@ -12,15 +12,16 @@
 // p = flattened position of the staged (TH+KH-1) x (TW+KW-1) halo tile (pitch in_cols), exactly the planar-by-
 // channel-quad operand layout of conv_tc.cu: a kh tap is still a descriptor offset of kh*in_cols positions, the
 // kw taps become columns.  One A read now feeds KW*CC >= 24..224 columns, MMA count drops KW-fold, and the
-// shift-add costs KW*CC FADDs per pixel (1-10 % of the FMAs it replaces) through a small shared staging ring.
+// shift-add costs KW*CC FADDs per pixel (1-10 % of the FMAs it replaces): warp shuffles plus a small shared halo.
 //
-//   * 3xTF32 (fp32-class): hi = rna_tf32(x), lo = rna_tf32(x - hi), D += Alo*Bhi + Ahi*Blo + Ahi*Bhi; activations
-//     are split once per stage in shared memory (in place), weights are pre-split on the host (w_tc layout).
+//   * 3xTF32 (fp32-class): hi = x rounded to TF32, lo = (x - hi) truncated to TF32, D += Alo*Bhi + Ahi*Blo + Ahi*Bhi;
+//     activations are split once per stage in shared memory (in place), weights are pre-split on the host (w_ws slabs).
 //   * GroupNorm(4)+affine+SiLU of the producer (update.py:117-133) is applied inside the split pass, so those
 //     layers keep the asynchronous cp.async landing path.
-//   * Persistent CTAs, two per SM (<= 112 KB shared, <= 256 TMEM columns each): while one CTA drains its
-//     accumulators the other one's MMAs keep the tensor pipe busy - overlap without warp specialisation.
-//   * Stages = (tile, depth tap, 8 input channels) stream through an R-deep cp.async ring exactly as in conv_tc.cu.
+//   * Persistent CTAs, two per SM (<= 112 KB shared, <= 256 TMEM columns each), warp specialised: warps 0-7 copy and
+//     split (each thread its own elements) and run the epilogue, warp 8 issues the MMAs; full/empty mbarriers only.
+//   * Stages = (tile, depth tap, stride phase, 8 input channels) stream through an R-deep cp.async ring.
+//   * Stride 2 runs as four stride-1 phases over decimated input planes accumulating into the same TMEM columns.
 #include <cstdlib>
 #include <type_traits>
 
@@ -51,6 +52,7 @@ struct WsArgs {
   int stage_f;      // floats per ring slot: operand pair [hi | lo]
   int halo_f;       // floats of the epilogue's halo exchange buffer
   int vec_y, vec_res, vec_bias;
+  int raw_hi;       // 1: keep raw fp32 in the hi plane (hardware truncation), compute only the lo plane
   int Hs, Ws;
   float inv_in_cols;
   int lanes_row;    // threads that share one tile row in the loader (32..256, power of two >= 2*in_cols when possible)
@@ -101,16 +103,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
 // x = hi + lo + r with hi, lo exactly representable in TF32 and |r| < 2^-21 |x|.  hi is x rounded to nearest
 // (integer add of half an ulp, then mask - the same result as cvt.rna.tf32.f32 for finite values, which ptxas expands
 // to four instructions on sm_100a); lo = x - hi is exact in fp32 and is truncated to TF32 explicitly, so the
 // result does not depend on what the tensor core does with the 13 low mantissa bits.  4 instructions per value.
+__device__ __forceinline__ void lo_trunc(float x, float& lo) {
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
   lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
@@ -149,11 +149,6 @@ __device__ __forceinline__ void cp_async16_full(float* smem_dst, const float* gs
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 
-template <int R>
-__device__ __forceinline__ void cp_async_wait_ring() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(R - 2) : "memory");
-}
-
 // PASSES = 1 (TF32) or 3 (3xTF32), R = ring depth (2, 3), GN = GroupNorm+SiLU prologue in the split pass
 template <int PASSES, int R, bool GN>
 __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_constant__ WsArgs a) {
@@ -173,6 +168,9 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue (TMEM allocation, barrier
+  // initialisation) while this grid drains; our own prologue likewise overlaps the tail of the previous kernel.
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
@@ -189,6 +187,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  asm volatile("griddepcontrol.wait;\n" ::: "memory");   // everything the previous kernels wrote is visible from here on
   const uint32_t tmem_base = tmem_base_s;
   // instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
@@ -331,11 +330,18 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
         }
         if (PASSES == 3) {
           float4 h, l;
-          split_tf32(v.x, h.x, l.x);
-          split_tf32(v.y, h.y, l.y);
-          split_tf32(v.z, h.z, l.z);
-          split_tf32(v.w, h.w, l.w);
-          *reinterpret_cast<float4*>(ptr) = h;
+          if (a.raw_hi) {
+            // the tensor core reads only the 10 upper mantissa bits of a TF32 operand: the raw value can stay in the hi
+            // plane (hi = x truncated), only lo = x - trunc(x) is computed (|lo| < 2^-10 |x|, truncated to TF32)
+            lo_trunc(v.x, l.x); lo_trunc(v.y, l.y); lo_trunc(v.z, l.z); lo_trunc(v.w, l.w);
+            if (GN) *reinterpret_cast<float4*>(ptr) = v;
+          } else {
+            split_tf32(v.x, h.x, l.x);
+            split_tf32(v.y, h.y, l.y);
+            split_tf32(v.z, h.z, l.z);
+            split_tf32(v.w, h.w, l.w);
+            *reinterpret_cast<float4*>(ptr) = h;
+          }
           *reinterpret_cast<float4*>(ptr + lo_off) = l;
         } else {
           *reinterpret_cast<float4*>(ptr) = v;
@@ -704,7 +710,14 @@ void choose_tile(const dmvs_conv_desc& d, int KHe, int KWe, int N, int CC, int p
         if (tw_max > 250) tw_max = 250;
         if (tw_max < 1 || (tw_max < 8 && tw_max < d.Wo)) continue;
         const int ntx = ceil_div(d.Wo, tw_max);
-        const int TW = ceil_div(d.Wo, ntx);
+        int TW = ceil_div(d.Wo, ntx);
+        // operand rows of 16 bytes: a kernel-row offset of in_cols positions keeps the 8-row core matrices on 128-byte
+        // lines only if in_cols is a multiple of 8
+        static const int align8 = getenv("DMVS_WS_ALIGN8") ? atoi(getenv("DMVS_WS_ALIGN8")) : 0;
+        if (align8) {
+          const int padded = ((TW + KWe - 1 + 7) & ~7) - (KWe - 1);
+          if (padded <= tw_max) TW = padded;
+        }
         const int in_cols = TW + KWe - 1;
         const int in_rows = th + KHe - 1;
         const int n_blk = ceil_div(th * in_cols, 128);
@@ -798,6 +811,8 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out
   a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
   a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
   a.vec_bias = d.bias != nullptr && aligned16(d.bias);
+  static const int raw_hi = getenv("DMVS_WS_RAWHI") ? atoi(getenv("DMVS_WS_RAWHI")) : 0;
+  a.raw_hi = raw_hi;
   a.Hs = d.in_up2 ? d.H / 2 : d.H;
   a.Ws = d.in_up2 ? d.W / 2 : d.W;
 
@@ -852,7 +867,22 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out
       }
     } else {
       KernelFn fn = passes == 3 ? pick_r<3>(t.R, d.in_stats != nullptr) : pick_r<1>(t.R, d.in_stats != nullptr);
-      fn<<<grid, kWsThreads, t.smem, st>>>(a);
+      static const int use_pdl = getenv("DMVS_PDL") ? atoi(getenv("DMVS_PDL")) : 0;
+      if (use_pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kWsThreads);
+        cfg.dynamicSmemBytes = t.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, fn, a);
+      } else {
+        fn<<<grid, kWsThreads, t.smem, st>>>(a);
+      }
       const int rc = launch_status();
       if (rc) return rc;
     }

@@ -1,0 +1,86 @@
+"""Host-side logic of the width-stacked tcgen05 convolution that runs without a GPU: the tile planner
+(`dmvs_conv_ws_plan`), the back-end query and the save / load round trip of the autotuning table."""
+import ctypes as C
+import json
+
+import pytest
+
+from diffmvs_b200 import _cabi, ops
+
+
+def _desc(N, cin, cout, k, stride, dims, gn=False):
+    d = _cabi.ConvDesc()
+    D, H, W = dims
+    kd, kh, kw = k
+    pd, ph, pw = kd // 2, kh // 2, kw // 2
+    d.x = d.w = d.w_ws = d.y = d.bias = 0x1000           # only alignment is inspected
+    d.N, d.D, d.H, d.W, d.C1, d.C2 = N, D, H, W, cin, 0
+    d.x_ps, d.y_ps = cin, cout
+    d.KD, d.KH, d.KW, d.stride, d.pad_d, d.pad_h, d.pad_w = kd, kh, kw, stride, pd, ph, pw
+    d.Do = (D + 2 * pd - kd) // stride + 1
+    d.Ho = (H + 2 * ph - kh) // stride + 1
+    d.Wo = (W + 2 * pw - kw) // stride + 1
+    d.Cout = cout
+    d.precision = _cabi.PREC_WS_TF32X3
+    if gn:
+        d.in_stats = d.in_g1 = d.in_g0 = 0x1000
+    return d
+
+
+LAYERS = [
+    (7, 8, 8, (1, 3, 3), 1, (1, 1152, 1600)),
+    (7, 8, 16, (1, 5, 5), 2, (1, 1152, 1600)),
+    (7, 64, 16, (1, 3, 3), 1, (1, 576, 800)),
+    (7, 64, 64, (1, 3, 3), 1, (1, 144, 200)),
+    (1, 64, 16, (1, 7, 7), 1, (1, 288, 400)),
+    (1, 64, 64, (1, 1, 5), 1, (1, 144, 200)),
+    (1, 52, 40, (1, 5, 1), 1, (1, 144, 200)),
+    (6, 4, 8, (3, 3, 3), 1, (48, 144, 200)),
+    (1, 8, 16, (3, 3, 3), 2, (48, 144, 200)),
+    (1, 32, 32, (1, 3, 3), 1, (1, 16, 20)),
+    (1, 64, 144, (1, 3, 3), 1, (1, 36, 50)),
+]
+
+
+@pytest.mark.parametrize("N,cin,cout,k,stride,dims", LAYERS)
+def test_tile_plan_respects_the_hardware_budgets(N, cin, cout, k, stride, dims):
+    lib = _cabi.lib()
+    d = _desc(N, cin, cout, k, stride, dims)
+    assert lib.dmvs_conv_backends(C.byref(d)) & 8, "the width-stacked back end should accept this layer"
+    out = (C.c_int32 * 64)()
+    n = lib.dmvs_conv_ws_plan(C.byref(d), out, 8)
+    assert n >= 1
+    covered = 0
+    for i in range(n):
+        CC, Nn, TH, TW, n_blk, R, ctas, smem = out[8 * i:8 * i + 8]
+        assert CC % 8 == 0 and 8 <= CC <= 64 and Nn % 16 == 0 and Nn <= 256
+        assert n_blk * Nn <= (256 if ctas >= 2 else 512), "accumulators must fit the TMEM columns of a CTA"
+        assert smem <= (112 if ctas >= 2 else 216) * 1024, "shared memory budget of co-resident CTAs"
+        assert R in (2, 3) and TH >= 1 and TW >= 1 and ctas in (1, 2)
+        covered += CC
+    assert covered >= cout
+
+
+def test_unsupported_layers_are_refused():
+    lib = _cabi.lib()
+    d = _desc(1, 3, 8, (1, 3, 3), 1, (1, 64, 64))          # 3 input channels: no 16-byte channel groups
+    assert not lib.dmvs_conv_backends(C.byref(d)) & 8
+    out = (C.c_int32 * 8)()
+    assert lib.dmvs_conv_ws_plan(C.byref(d), out, 1) == -3
+    d = _desc(1, 16, 20, (1, 3, 3), 1, (1, 64, 64))
+    d.out_stats = 0x1000                                    # GroupNorm groups of 5 channels: pairs would straddle
+    assert not lib.dmvs_conv_backends(C.byref(d)) & 8
+
+
+def test_autotune_table_round_trip(tmp_path):
+    ops._TUNED.clear()
+    key = (7, 1, 576, 800, 64, 0, 16, 1, 3, 3, 1, 0, 1, 1, 0, False, 0, 0, 0, 64, 0, 16)
+    ops._TUNED[key] = (ops.PREC_WS_TF32X3, {ops.PREC_FP32: 1.39, ops.PREC_WS_TF32X3: 0.61})
+    path = tmp_path / "tuned.json"
+    ops.save_tuned(str(path))
+    rows = json.load(open(path))
+    assert rows[0]["choice"] == "ws_tf32x3"
+    ops._TUNED.clear()
+    assert ops.load_tuned(str(path)) == 1
+    assert ops._TUNED[key][0] == ops.PREC_WS_TF32X3
+    ops._TUNED.clear()
