@@ -146,6 +146,25 @@ __device__ __forceinline__ Taps make_taps(float u, float v, int Hs, int Ws) {
   return t;
 }
 
+// The LPP lanes of a pixel share every hypothesis: one lane computes the projection and the taps (four IEEE
+// divisions and the grid_sample round trip are the expensive part of these kernels), the others receive them.
+__device__ __forceinline__ Taps bcast_taps(const Taps& mine, int src_lane) {
+  Taps t;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    t.off[i] = __shfl_sync(0xffffffffu, mine.off[i], src_lane);
+    t.wgt[i] = __shfl_sync(0xffffffffu, mine.wgt[i], src_lane);
+  }
+  return t;
+}
+
+__device__ __forceinline__ Taps masked_taps() {
+  Taps t;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t.off[i] = -1; t.wgt[i] = 0.0f; }
+  return t;
+}
+
 // bilinear sample of VEC float4s starting at channel `c0` of a channels-last map with pixel stride ps
 template <int VEC>
 __device__ __forceinline__ void gather(const float* __restrict__ src, int ps, int c0, const Taps& t, float4 out[VEC]) {
@@ -255,16 +274,27 @@ __global__ void __launch_bounds__(256) plane_sweep_kernel(const float* __restric
   ray_of_pixel(Hm, (float)x, (float)y, ray);
 
   float* out = cor + ((int64_t)(b * (V - 1) + v1) * D) * HW * G;
-  for (int d = 0; d < D; ++d) {
-    float u, vv;
-    project(Hm, ray, __ldg(plane_depth + b * D + d), u, vv);
-    const Taps t = make_taps(u, vv, H, W);
-    float4 wf[VEC];
-    gather<VEC>(src, C, c0, t, wf);
-    float s = dot_vec<VEC>(rf, wf);
+  const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);   // first lane of this pixel's group
+  for (int d0 = 0; d0 < D; d0 += LPP) {
+    // lane `sub` of the group prepares plane d0 + sub, then the group walks the LPP planes together
+    Taps mine = masked_taps();
+    if (d0 + sub < D) {
+      float u, vv;
+      project(Hm, ray, __ldg(plane_depth + b * D + d0 + sub), u, vv);
+      mine = make_taps(u, vv, H, W);
+    }
 #pragma unroll
-    for (int o = 1; o < LPG; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (active && (sub % LPG) == 0) out[((int64_t)d * HW + p) * G + sub / LPG] = __fdiv_rn(s, cpg);
+    for (int j = 0; j < LPP; ++j) {
+      const int d = d0 + j;
+      if (d >= D) break;                                   // uniform across the warp
+      const Taps t = bcast_taps(mine, lane_base + j);
+      float4 wf[VEC];
+      gather<VEC>(src, C, c0, t, wf);
+      float s = dot_vec<VEC>(rf, wf);
+#pragma unroll
+      for (int o = 1; o < LPG; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (active && (sub % LPG) == 0) out[((int64_t)d * HW + p) * G + sub / LPG] = __fdiv_rn(s, cpg);
+    }
   }
 }
 
@@ -385,19 +415,20 @@ __global__ void __launch_bounds__(256) get_cost_kernel(const float* __restrict__
     lo = __fsub_rn(cur, r);
     hi = __fadd_rn(cur, r);
   }
-  float samp[D], dep[D];
-  if (D > 1) {
-    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1));
+  // lane `sub` of the pixel's group owns hypotheses sub, sub + LPP, ...: it computes their sample, metric depth and,
+  // per source view, their projection and taps; the other lanes of the group receive the taps by shuffle
+  constexpr int NCHUNK = (D + LPP - 1) / LPP;
+  float my_samp[NCHUNK], my_dep[NCHUNK];
+  const float step = D > 1 ? __fdiv_rn(__fsub_rn(hi, lo), (float)(D - 1)) : 0.0f;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const float s = __fadd_rn(__fmul_rn((float)d, step), lo);
-      samp[d] = fminf(fmaxf(s, 0.0f), 1.0f);
-      dep[d] = rng.to_depth(samp[d]);
-    }
-  } else {
-    samp[0] = cur;
-    dep[0] = rng.to_depth(cur);
+  for (int j = 0; j < NCHUNK; ++j) {
+    const int d = j * LPP + sub;
+    float sv = cur;
+    if (D > 1) sv = fminf(fmaxf(__fadd_rn(__fmul_rn((float)d, step), lo), 0.0f), 1.0f);
+    my_samp[j] = sv;
+    my_dep[j] = rng.to_depth(sv);
   }
+  const int lane_base = (threadIdx.x & 31) & ~(LPP - 1);   // first lane of this pixel's group
 
   const float* ref = feats + ((int64_t)b * HW + p) * C + c0;
   float4 rf[VEC];
@@ -418,16 +449,26 @@ __global__ void __launch_bounds__(256) get_cost_kernel(const float* __restrict__
     float ray[3];
     ray_of_pixel(Hm, (float)x, (float)y, ray);
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      float u, vv;
-      project(Hm, ray, dep[d], u, vv);
-      const Taps t = make_taps(u, vv, H, W);
-      float4 wf[VEC];
-      gather<VEC>(src, C, c0, t, wf);
-      float s = dot_vec<VEC>(rf, wf);
+    for (int jc = 0; jc < NCHUNK; ++jc) {
+      Taps mine = masked_taps();
+      if (jc * LPP + sub < D) {
+        float u, vv;
+        project(Hm, ray, my_dep[jc], u, vv);
+        mine = make_taps(u, vv, H, W);
+      }
 #pragma unroll
-      for (int o = 1; o < LPG; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      acc[d] = __fadd_rn(acc[d], __fmul_rn(wv, __fdiv_rn(s, cpg)));
+      for (int j = 0; j < LPP; ++j) {
+        const int d = jc * LPP + j;
+        if (d < D) {
+          const Taps t = bcast_taps(mine, lane_base + j);
+          float4 wf[VEC];
+          gather<VEC>(src, C, c0, t, wf);
+          float s = dot_vec<VEC>(rf, wf);
+#pragma unroll
+          for (int o = 1; o < LPG; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          acc[d] = __fadd_rn(acc[d], __fmul_rn(wv, __fdiv_rn(s, cpg)));
+        }
+      }
     }
   }
   if (!active) return;
@@ -437,11 +478,10 @@ __global__ void __launch_bounds__(256) get_cost_kernel(const float* __restrict__
 #pragma unroll
     for (int d = 0; d < D; ++d) cp[d] = __fdiv_rn(acc[d], wsum);
   }
-  if (sub == 0) {
-    float* sp = samples + ((int64_t)b * HW + p) * samp_ps;
+  float* sp = samples + ((int64_t)b * HW + p) * samp_ps;
 #pragma unroll
-    for (int d = 0; d < D; ++d) sp[d] = samp[d];
-  }
+  for (int j = 0; j < NCHUNK; ++j)
+    if (j * LPP + sub < D) sp[j * LPP + sub] = my_samp[j];   // every lane stores the samples it owns
 }
 
 }  // namespace
