@@ -74,14 +74,20 @@ class CasDiffMVS(_PlannedModule):
         self._use_graph = bool(enabled)
         return self
 
-    def forward(self, imgs, proj_matrices, depth_values, depth_gt_ms=None):
+    def forward(self, imgs, proj_matrices, depth_values, depth_gt_ms=None, features=None, return_features=False):
         """`imgs`: list of V `[B,3,H,W]`; `proj_matrices`: dict stage1..4 -> `[B,V,2,4,4]`; `depth_values [B,N]`
-        -> {"depth": [...], "conf": [], "photometric_confidence": [...]} (diffusion.py:139-295, test mode)."""
+        -> {"depth": [...], "conf": [], "photometric_confidence": [...]} (diffusion.py:139-295, test mode).
+
+        Extension (not in the reference): `return_features=True` adds `"features"`, the per-view FeatureNet pyramids;
+        passing them back as `features=[pyramid or None per view]` on a later call skips FeatureNet for those views
+        (a scan re-uses every image as a source view of its neighbours).  Results are unchanged."""
         if not self.test or depth_gt_ms is not None:
             raise NotImplementedError("training-mode outputs (per-iteration lists, ground-truth injection) are out of "
                                       "scope: build with test=True (SURVEY.md section 2)")
         with torch.no_grad():
             plan = self.plan(imgs[0].device)
+            if features is not None or return_features:
+                return plan.forward(imgs, proj_matrices, depth_values, features=features, return_features=return_features)
             if getattr(self, "_use_graph", False):
                 return plan.forward_graphed(imgs, proj_matrices, depth_values)
             return plan.forward(imgs, proj_matrices, depth_values)

@@ -418,7 +418,13 @@ class CasDiffMVSPlan:
                 timesteps=args.timesteps[s], sampling_timesteps=args.sampling_timesteps[s], eta=args.ddim_eta[s])
 
     def forward(self, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
-                taps: Optional[dict] = None) -> Dict[str, List[Tensor]]:
+                taps: Optional[dict] = None, features: Optional[Sequence[Optional[Dict[str, Tensor]]]] = None,
+                return_features: bool = False) -> Dict[str, List[Tensor]]:
+        """`features` (optional, SURVEY.md 8(f) row 1 - cross-ref-view feature cache): per view either None or the
+        feature pyramid `{"stage1": [B,h,w,C], ...}` (channels-last) a previous call returned for the same image
+        under `return_features=True`; FeatureNet then runs only on the views that are missing.  Neighbouring
+        reference views of a scan share most of their source images, so a caller that keeps the pyramids re-encodes
+        about one image per reference view instead of V."""
         args = self.args
         V = len(imgs)
         B, _, H, W = imgs[0].shape
@@ -430,12 +436,32 @@ class CasDiffMVSPlan:
         depth_min = (1.0 / depth_values[:, -1]).contiguous()
         interval0 = 1.0 / depth_values.size(1)
 
-        # all views through FeatureNet as one batch (the reference loops, diffusion.py:156-157)
-        x_all = torch.empty((V, B, H, W, 4), device=dev, dtype=torch.float32)   # RGB + one zero channel
-        for v, im in enumerate(imgs):
-            ops.image_to_nhwc4(im.float(), out=x_all[v])
-        feats = self.feature(x_all.view(V * B, H, W, 4))
-        ctx_feats = self.context.trunk(x_all[0])
+        # all (missing) views through FeatureNet as one batch (the reference loops, diffusion.py:156-157)
+        missing = [v for v in range(V) if features is None or features[v] is None]
+        staged = sorted(set(missing) | {0})                  # ContextNet always needs the reference image
+        x_st = torch.empty((len(staged), B, H, W, 4), device=dev, dtype=torch.float32)   # RGB + one zero channel
+        for i, v in enumerate(staged):
+            ops.image_to_nhwc4(imgs[v].float(), out=x_st[i])
+        if len(missing) == V:
+            feats = self.feature(x_st.view(V * B, H, W, 4))
+        else:
+            fresh = {}
+            if missing:
+                rows = torch.cat([x_st[staged.index(v)] for v in missing], 0) if len(missing) != len(staged) else \
+                    x_st.view(len(staged) * B, H, W, 4)
+                fresh = self.feature(rows)
+            keys = ["stage1", "stage2"] + (["stage3"] if self.cas else [])
+            feats = {}
+            for key in keys:
+                ref = fresh[key] if missing else features[0][key]
+                buf = torch.empty((V * B,) + tuple(ref.shape[1:]), device=dev, dtype=torch.float32)
+                for v in range(V):
+                    src = fresh[key][missing.index(v) * B:(missing.index(v) + 1) * B] if v in missing else features[v][key]
+                    if tuple(src.shape) != (B,) + tuple(ref.shape[1:]):
+                        raise ValueError(f"cached features of view {v} ({tuple(src.shape)}) do not match this input")
+                    buf[v * B:(v + 1) * B].copy_(src)
+                feats[key] = buf
+        ctx_feats = self.context.trunk(x_st[0])
 
         slots = sum(b.stats_slots() for b in self.blocks.values())
         arena = StatsArena(dev, B, max(slots, 1))
@@ -491,7 +517,10 @@ class CasDiffMVSPlan:
                 if taps is not None:
                     taps[f"{key}_mask"] = mask
                     taps[f"{key}_hidden0"] = hidden
-        return {"depth": depths, "conf": [], "photometric_confidence": confs}
+        out = {"depth": depths, "conf": [], "photometric_confidence": confs}
+        if return_features:
+            out["features"] = [{k: f.view(V, B, *f.shape[1:])[v] for k, f in feats.items()} for v in range(V)]
+        return out
 
     # --------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole forward: ~800 kernel launches per

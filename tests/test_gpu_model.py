@@ -249,6 +249,33 @@ def test_cuda_graph_replay_matches_eager():
     assert g3["depth"][-1].data_ptr() != g1["depth"][-1].data_ptr()   # results are the caller's own tensors
 
 
+def test_feature_cache_leaves_results_unchanged(monkeypatch):
+    """Cross-ref-view feature cache: pyramids returned by one call and passed back for all or
+    some views give the same depths as re-encoding every image."""
+    args = synth.workload_args("cas_tiny")
+    sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
+    imgs, proj, dv = _to_dev(*synth.workload_inputs("cas_tiny"))
+    model = _build(args, sd)
+
+    def run(**kw):
+        torch.manual_seed(21)
+        return model(imgs, proj, dv, **kw)
+
+    base = run(return_features=True)
+    feats = base["features"]
+    assert len(feats) == len(imgs) and set(feats[0]) == {"stage1", "stage2", "stage3"}
+    full = run(features=feats)
+    partial = run(features=[None] + feats[1:])              # new reference image, cached sources
+    mixed = run(features=[feats[0], None] + feats[2:])
+    for other in (full, partial, mixed):
+        for a, b in zip(base["depth"], other["depth"]):
+            assert rel_l1(a, b) < 1e-6
+    with pytest.raises(ValueError):
+        bad = [dict(f) for f in feats]
+        bad[1]["stage1"] = bad[1]["stage1"][:, :-1]
+        run(features=bad)
+
+
 def test_zz_report():
     """Prints the collected parity numbers (kept in gpurun_out/ when run on the GPU box)."""
     import os
