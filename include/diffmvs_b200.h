@@ -227,6 +227,27 @@ int dmvs_image_to_nhwc4(const float* x, float* y, int32_t N, int32_t HW, void* s
 int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t N, int32_t C, int32_t HW, void* stream);
 int dmvs_nhwc_to_nchw(const float* x, int32_t x_ps, float* y, int32_t N, int32_t C, int32_t HW, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Depth-map filtering / fusion (filter.py:8-87,189-215).  Host-side matrix algebra (float32 inverses and
+ * products, as numpy computes them in the reference) is passed in as doubles.
+ * ------------------------------------------------------------------------------------------- */
+
+/* check_geometric_consistency (filter.py:54-87) for one (reference, source) pair of depth maps [H][W] / [Hs][Ws]:
+ * mats68 = inv(K_ref)[9], E_src@inv(E_ref)[16], K_src[9], inv(K_src)[9], E_ref@inv(E_src)[16], K_ref[9] (row major).
+ * Writes mask (0/1), the reprojected depth (0 where inconsistent) and optionally the source pixel coordinates; when
+ * sum_reproj / count are given they are updated in place (+= depth_reproj, += mask), which accumulates
+ * `sum(all_srcview_depth_ests)` and `geo_mask_sum` of filter_depth over successive source views. */
+int dmvs_geo_consistency(const float* depth_ref, const float* depth_src, const double* mats68, float depth_min,
+                         float depth_max, float pix_thres, float depth_thres, uint8_t* mask, float* depth_reproj,
+                         float* x_src, float* y_src, float* sum_reproj, int32_t* count, int32_t H, int32_t W,
+                         int32_t Hs, int32_t Ws, void* stream);
+
+/* Averaged depth (float64, as numpy's float32 / int32 quotient), geometric and final masks and the world-space point
+ * of every pixel (filter.py:189-212).  mats25 = inv(K_ref)[9], inv(E_ref)[16]; photo_mask may be NULL. */
+int dmvs_fuse_points(const float* depth_ref, const float* sum_reproj, const int32_t* count, const uint8_t* photo_mask,
+                     int32_t geo_thres, const double* mats25, double* depth_avg, uint8_t* geo_mask, uint8_t* final_mask,
+                     float* xyz, int32_t H, int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

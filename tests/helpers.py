@@ -50,3 +50,35 @@ def replay_noise(golden):
 def rel_l1(a: torch.Tensor, b: torch.Tensor) -> float:
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return ((a - b).abs().mean() / b.abs().mean().clamp_min(1e-30)).item()
+
+
+def plane_scene(H=48, W=64, V=4, seed=0):
+    """Small multi-view depth-map set for the fusion tests: a tilted plane seen by V cameras (shared intrinsics,
+    x-translated, slightly rotated), analytic depth per view, plus noise / outliers in some regions so that the
+    consistency masks are neither empty nor full.  Returns float32 numpy arrays."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    K = np.array([[1.1 * W, 0, W / 2 - 0.5], [0, 1.1 * W, H / 2 - 0.5], [0, 0, 1]], dtype=np.float32)
+    n = np.array([0.08, -0.05, 1.0])
+    c0 = 600.0                                           # plane n . P = c0 (world)
+    Es, depths = [], []
+    for v in range(V):
+        ang = 0.01 * v
+        R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+        t = np.array([-25.0 * v, 3.0 * (v % 2), 0.5 * v])
+        E = np.eye(4)
+        E[:3, :3], E[:3, 3] = R, t
+        Es.append(E.astype(np.float32))
+        # camera-frame ray d = K^-1 (u, v, 1); world point P = R^T (s d - t); n . P = c0  =>  s
+        u, w = np.meshgrid(np.arange(W), np.arange(H))
+        d = np.linalg.inv(K.astype(np.float64)) @ np.vstack((u.reshape(-1), w.reshape(-1), np.ones(H * W)))
+        nr = R @ n                                       # n^T R^T = (R n)^T
+        s = (c0 + nr @ t) / (nr @ d)
+        depth = s.reshape(H, W)
+        depth = depth * (1 + 2e-4 * rng.standard_normal((H, W)))         # within the 1 % consistency band
+        depth[H // 3: H // 2, W // 4: W // 2] *= 1.0 + 0.05 * (v % 2)      # inconsistent patch in odd views
+        depths.append(depth.astype(np.float32))
+    depths[0][:3] = 2000.0                               # rows outside the depth range of the reference view
+    confs = [rng.random((H, W), dtype=np.float32) for _ in range(3)]
+    img = rng.random((H, W, 3), dtype=np.float32)
+    return {"K": K, "E": Es, "depth": depths, "conf": confs, "img": img, "depth_min": 425.0, "depth_max": 935.0}
