@@ -11,6 +11,7 @@ tail -2 $O/smoke.log
 timeout 600 python bench.py --dump-tuned $O/tuned.json > $O/bench.log 2>&1
 echo "bench rc=$?" >> $O/bench.log
 tail -2 $O/bench.log | cut -c1-300
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_ws" -c 6 \
-   -o $O/ws_final -f env BENCH_CONV_REPS=1 python tools/bench_conv.py "feat.conv1.1,feat.out3,feat.conv3.0" ws_tf32x3 > $O/ncu_ws.log 2>&1
+true
 ls -la $O | head -20
+timeout 200 python tools/bench_fusion.py > $O/fusion.log 2>&1
+tail -1 $O/fusion.log | cut -c1-600
