@@ -100,3 +100,50 @@ def fuse_view(ref_depth: Tensor, ref_intrinsics, ref_extrinsics, depth_max, dept
     if ref_img is not None:
         out["colors"] = (ref_img.to(dev)[final] * 255).to(torch.uint8)
     return out
+
+
+def fuse_view_dynamic(ref_depth: Tensor, ref_intrinsics, ref_extrinsics, depth_max, depth_min, confidences: Sequence[Tensor],
+                      photo_thres: Sequence[float], src_views: Sequence[Tuple[Tensor, object, object]],
+                      dh_pixel_dist_num: Sequence[int], ref_img: Optional[Tensor] = None):
+    """One reference view of `filter_depth_dynamic` (filter.py:230-262, 311-412; Tanks & Temples).  For every source
+    view the consistency test is evaluated for the thresholds i / dh_dist pixels and i / dh_rel_diff relative depth,
+    i = dh_view_num .. 10; a pixel is kept when at least i source views pass test i for some i.  The loosest test
+    (i = 10) also defines the reprojected depths that are averaged.  `dh_pixel_dist_num` = [dh_view_num, dh_dist,
+    dh_rel_diff] (per-scene tables: `oracle.filter_ref.DH_*`, filter.py:274-301)."""
+    ref_depth = _req(ref_depth, "ref_depth")
+    H, W = ref_depth.shape
+    dev = ref_depth.device
+    view_num, dh_dist, dh_rel = dh_pixel_dist_num
+    photo = torch.ones((H, W), device=dev, dtype=torch.bool)
+    for conf, thr in zip(confidences, photo_thres):
+        photo &= _req(conf, "confidence") > thr
+    acc_sum = torch.zeros((H, W), device=dev, dtype=torch.float32)     # sum of the reprojected depths (test i = 10)
+    acc_cnt = torch.zeros((H, W), device=dev, dtype=torch.int32)       # geo_mask_sum (test i = 10)
+    level_cnt = {i: torch.zeros((H, W), device=dev, dtype=torch.int32) for i in range(view_num, 10)}
+    inf = float("inf")
+    for d_src, K_src, E_src in src_views:
+        for i in range(view_num, 11):
+            last = i == 10
+            mask, _, _, _ = check_geometric_consistency(ref_depth, ref_intrinsics, ref_extrinsics, d_src, K_src, E_src, inf, -inf,
+                                                        i / dh_dist, i / dh_rel, _acc=(acc_sum, acc_cnt) if last else None)
+            if not last:
+                level_cnt[i] += mask.to(torch.int32)
+    geo = acc_cnt >= 10
+    for i in range(view_num, 10):
+        geo |= level_cnt[i] >= i
+    K_ref, E_ref = _f32(ref_intrinsics), _f32(ref_extrinsics)
+    mats = np.ascontiguousarray(np.concatenate([np.linalg.inv(K_ref).astype(np.float64).reshape(-1),
+                                                np.linalg.inv(E_ref).astype(np.float64).reshape(-1)]))
+    depth_avg = torch.empty((H, W), device=dev, dtype=torch.float64)
+    geo_unused = torch.empty((H, W), device=dev, dtype=torch.uint8)
+    fin_unused = torch.empty((H, W), device=dev, dtype=torch.uint8)
+    xyz = torch.empty((H, W, 3), device=dev, dtype=torch.float32)
+    check(_cabi.lib().dmvs_fuse_points(ref_depth.data_ptr(), acc_sum.data_ptr(), acc_cnt.data_ptr(), None, 0,
+                                       mats.ctypes.data_as(C.c_void_p), depth_avg.data_ptr(), geo_unused.data_ptr(),
+                                       fin_unused.data_ptr(), xyz.data_ptr(), H, W, _stream()), "dmvs_fuse_points")
+    in_range = (depth_avg >= depth_min) & (depth_avg <= depth_max)
+    final = photo & geo & in_range
+    out = {"photo_mask": photo, "geo_mask": geo, "final_mask": final, "depth_avg": depth_avg, "points": xyz[final]}
+    if ref_img is not None:
+        out["colors"] = (ref_img.to(dev)[final] * 255).to(torch.uint8)
+    return out

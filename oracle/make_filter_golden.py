@@ -28,6 +28,10 @@ def main():
         mask, drep, xs, ys = ref_filter.check_geometric_consistency(
             sc["depth"][0], sc["K"], sc["E"][0], sc["depth"][v], sc["K"], sc["E"][v], sc["depth_max"], sc["depth_min"], 1.0, 0.01)
         out[f"mask{v}"], out[f"drep{v}"], out[f"xs{v}"], out[f"ys{v}"] = mask, drep, xs, ys
+    dh = [2, 12, 1600]                                   # 'Family' (filter.py:274-301)
+    masks, last, drep, _, _ = ref_filter.check_geometric_consistency_dynamic(
+        sc["depth"][0], sc["K"], sc["E"][0], sc["depth"][1], sc["K"], sc["E"][1], dh)
+    out["dyn_masks"], out["dyn_last"], out["dyn_drep"] = np.stack(masks), last, drep
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "filter.npz"), **out)
     print({k: (v.shape, float(np.mean(v))) for k, v in out.items() if k.startswith("mask")})
 

@@ -24,6 +24,15 @@ def test_oracle_matches_the_reference_filter():
         assert np.array_equal(xs, GOLD[f"xs{v}"]) and np.array_equal(ys, GOLD[f"ys{v}"])
 
 
+def test_oracle_matches_the_reference_dynamic_filter():
+    sc = plane_scene()
+    masks, last, drep, _, _ = F.check_geometric_consistency_dynamic(sc["depth"][0], sc["K"], sc["E"][0], sc["depth"][1], sc["K"],
+                                                                    sc["E"][1], [2, 12, 1600])
+    assert np.array_equal(np.stack(masks), GOLD["dyn_masks"]) and np.array_equal(last, GOLD["dyn_last"])
+    assert np.array_equal(drep, GOLD["dyn_drep"])
+    assert 0 < GOLD["dyn_masks"][0].mean() < GOLD["dyn_masks"][-1].mean() < 1      # the thresholds actually differ
+
+
 def emulate_remap(src, mx, my):
     """numpy replay of `remap_linear` in csrc/fusion.cu."""
     Hs, Ws = src.shape

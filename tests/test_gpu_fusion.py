@@ -51,6 +51,26 @@ def test_fuse_view_matches_oracle():
     assert np.array_equal(out["colors"].cpu().numpy(), ref["colors"])
 
 
+def test_dynamic_fuse_view_matches_oracle():
+    """Tanks & Temples variant (filter.py:230-262, 311-412): thresholds i/dh_dist, i/dh_rel_diff for i = 2..10."""
+    sc = plane_scene(96, 128, 4, 3)
+    dh = [2, 12, 1600]
+    src_np = [(sc["depth"][v], sc["K"], sc["E"][v]) for v in range(1, 4)]
+    ref = F.fuse_view_dynamic(sc["depth"][0], sc["K"], sc["E"][0], sc["depth_max"], sc["depth_min"], sc["conf"], [0.3, 0.5, 0.5],
+                              src_np, dh, ref_img=sc["img"])
+    out = fusion.fuse_view_dynamic(_t(sc["depth"][0]), sc["K"], sc["E"][0], sc["depth_max"], sc["depth_min"],
+                                   [_t(c) for c in sc["conf"]], [0.3, 0.5, 0.5], [(_t(d), K, E) for d, K, E in src_np], dh,
+                                   ref_img=_t(sc["img"]))
+    for k in ("photo_mask", "geo_mask", "final_mask"):
+        diff = out[k].cpu().numpy() != ref[k]
+        assert diff.mean() <= 1e-4, (k, int(diff.sum()))     # thresholds are passed as float32: a tie could flip a pixel
+    assert np.allclose(out["depth_avg"].cpu().numpy(), ref["depth_avg"], rtol=1e-6, atol=0)
+    if np.array_equal(out["final_mask"].cpu().numpy(), ref["final_mask"]):
+        assert np.allclose(out["points"].cpu().numpy(), ref["points"], rtol=1e-5, atol=1e-3)
+        assert np.array_equal(out["colors"].cpu().numpy(), ref["colors"])
+    assert 0 < ref["final_mask"].mean() < 1
+
+
 def test_cpu_tensors_are_rejected():
     sc = plane_scene()
     with pytest.raises(ValueError):
