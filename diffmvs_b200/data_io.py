@@ -251,3 +251,42 @@ def save_outputs(outdir: str, filename: str, depth: np.ndarray, confs: Sequence[
     write_cam(path("cams", "_cam.txt"), cam, depth_max, depth_min)
     for i, c in enumerate(confs):
         save_pfm(path(f"conf{i}", ".pfm"), np.ascontiguousarray(c, dtype=np.float32))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused point cloud (filter.py:214-227 writes it through `plyfile`, which is not installed here: the layout below is
+# plyfile's default - binary little endian, one `vertex` element with float x, y, z and uchar red, green, blue - and
+# is NOT pinned against plyfile itself)
+# ------------------------------------------------------------------------------------------------
+_PLY_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+
+
+def write_ply(filename: str, points: np.ndarray, colors: np.ndarray) -> None:
+    """points [N,3] float32 (world), colors [N,3] uint8 -> binary PLY."""
+    points, colors = np.asarray(points, dtype=np.float32), np.asarray(colors, dtype=np.uint8)
+    if points.ndim != 2 or points.shape[1] != 3 or colors.shape != points.shape:
+        raise ValueError("write_ply: points and colors must both be [N,3]")
+    rec = np.empty(len(points), dtype=_PLY_DTYPE)
+    rec["x"], rec["y"], rec["z"] = points[:, 0], points[:, 1], points[:, 2]
+    rec["red"], rec["green"], rec["blue"] = colors[:, 0], colors[:, 1], colors[:, 2]
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex {}\nproperty float x\nproperty float y\nproperty float z\n"
+              "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n").format(len(points))
+    with open(filename, "wb") as f:
+        f.write(header.encode("ascii"))
+        rec.tofile(f)
+
+
+def read_ply(filename: str) -> Tuple[np.ndarray, np.ndarray]:
+    """Inverse of `write_ply` (only that layout)."""
+    with open(filename, "rb") as f:
+        n = None
+        while True:
+            line = f.readline().decode("ascii").strip()
+            if line.startswith("element vertex"):
+                n = int(line.split()[-1])
+            if line == "end_header":
+                break
+            if not line:
+                raise ValueError(f"{filename}: malformed PLY header")
+        rec = np.fromfile(f, dtype=_PLY_DTYPE, count=n)
+    return np.stack((rec["x"], rec["y"], rec["z"]), 1), np.stack((rec["red"], rec["green"], rec["blue"]), 1)

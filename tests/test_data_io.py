@@ -97,3 +97,18 @@ def test_save_outputs_layout_round_trips(tmp_path):
     assert np.array_equal(data_io.read_pfm(str(tmp_path / "scan1/conf2/00000007.pfm"))[0], confs[2])
     intr, ext, _, _ = data_io.read_camera_parameters(str(tmp_path / "scan1/cams/00000007_cam.txt"))
     assert np.array_equal(ext, cam[0]) and np.array_equal(intr, cam[1, :3, :3])
+
+
+def test_ply_round_trip(tmp_path):
+    rng = np.random.default_rng(1)
+    pts = rng.standard_normal((257, 3)).astype(np.float32) * 100
+    col = rng.integers(0, 256, size=(257, 3), dtype=np.uint8)
+    path = str(tmp_path / "fused.ply")
+    data_io.write_ply(path, pts, col)
+    head = open(path, "rb").read(200).decode("ascii", "ignore")
+    assert head.startswith("ply\nformat binary_little_endian 1.0\nelement vertex 257\nproperty float x\n")
+    assert os.path.getsize(path) == head.index("end_header\n") + len("end_header\n") + 257 * 15
+    p2, c2 = data_io.read_ply(path)
+    assert np.array_equal(p2, pts) and np.array_equal(c2, col)
+    with pytest.raises(ValueError):
+        data_io.write_ply(path, pts, col[:-1])
