@@ -43,3 +43,43 @@ def gather_maps(local: torch.Tensor, counts: Sequence[int], dst: int = 0) -> Opt
     if rank != dst:
         return None
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+
+
+def all_gather_maps(local: torch.Tensor, counts: Sequence[int]) -> torch.Tensor:
+    """Every rank gets every rank's depth maps `[sum(n_r), H, W]` in view order: geometric filtering of reference view
+    i needs the depth maps of its source views, which other ranks may own.  One fixed-size
+    all_gather of padded blocks."""
+    world = dist.get_world_size()
+    n_max = max(counts)
+    H, W = local.shape[-2:]
+    buf = local.new_zeros((n_max, H, W))
+    buf[:local.shape[0]] = local
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+
+
+def gather_points(points: torch.Tensor, colors: torch.Tensor, dst: int = 0):
+    """The single gather of the fused point cloud (north_star): ranks hold different numbers of points
+    `[n_r, 3]` float32 + colours `[n_r, 3]` uint8.  Counts are exchanged first, then one padded gather of 15-byte
+    records (xyz as raw bytes + rgb) moves everything to `dst`; returns (points, colors) there and (None, None)
+    elsewhere.  Order: rank 0's points, then rank 1's, ... (ranks own contiguous view blocks, so this is view order)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if points.dim() != 2 or points.shape[1] != 3 or tuple(colors.shape) != tuple(points.shape):
+        raise ValueError("gather_points: points and colors must both be [N,3]")
+    n = torch.tensor([points.shape[0]], dtype=torch.int64, device=points.device)
+    all_n = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(all_n, n)
+    counts = [int(c.item()) for c in all_n]
+    n_max = max(max(counts), 1)
+    rec = torch.zeros((n_max, 15), dtype=torch.uint8, device=points.device)
+    if points.shape[0]:
+        rec[:points.shape[0], :12] = points.to(torch.float32).contiguous().view(torch.uint8).view(-1, 12)
+        rec[:points.shape[0], 12:] = colors.to(torch.uint8)
+    out = [torch.empty_like(rec) for _ in range(world)] if rank == dst else None
+    dist.gather(rec, out, dst=dst)
+    if rank != dst:
+        return None, None
+    allrec = torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+    pts = allrec[:, :12].contiguous().view(torch.float32).view(-1, 3)
+    return pts, allrec[:, 12:].contiguous()

@@ -51,3 +51,45 @@ def test_gather_maps_two_ranks_gloo(num_views):
     mp.spawn(_worker, args=(2, port, num_views, ret), nprocs=2, join=True)
     assert ret["shape"] == (num_views, 4, 6)
     assert ret["vals"] == [float(v) for v in range(num_views)]
+
+
+def _fusion_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    num_views = 5
+    mine = sharding.shard_views(num_views, rank, world)
+    counts = [len(sharding.shard_views(num_views, r, world)) for r in range(world)]
+    local = torch.stack([torch.full((3, 4), float(v)) for v in mine])
+    every = sharding.all_gather_maps(local, counts)              # each rank now sees all depth maps
+    assert every[:, 0, 0].tolist() == [float(v) for v in range(num_views)]
+    # rank r fuses 2*r + 1 points (rank 1 more than rank 0: ragged), values encode (rank, index)
+    n = 2 * rank + 1
+    pts = torch.arange(n * 3, dtype=torch.float32).view(n, 3) + 100.0 * rank + 0.25
+    col = (torch.arange(n * 3).view(n, 3) % 251 + rank).to(torch.uint8)
+    p, c = sharding.gather_points(pts, col, dst=0)
+    if rank == 0:
+        ret["pts"], ret["col"] = p.tolist(), c.tolist()
+    else:
+        assert p is None and c is None
+    # an empty contribution is legal
+    p, c = sharding.gather_points(pts[:0] if rank == 0 else pts, col[:0] if rank == 0 else col, dst=0)
+    if rank == 0:
+        ret["n2"] = p.shape[0]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_point_cloud_gather_two_ranks_gloo():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ret = mp.Manager().dict()
+    mp.spawn(_fusion_worker, args=(2, port, ret), nprocs=2, join=True)
+    exp_pts, exp_col = [], []
+    for rank in range(2):
+        n = 2 * rank + 1
+        exp_pts += (torch.arange(n * 3, dtype=torch.float32).view(n, 3) + 100.0 * rank + 0.25).tolist()
+        exp_col += (torch.arange(n * 3).view(n, 3) % 251 + rank).tolist()
+    assert ret["pts"] == exp_pts and ret["col"] == exp_col
+    assert ret["n2"] == 3
