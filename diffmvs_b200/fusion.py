@@ -3,7 +3,7 @@
 `check_geometric_consistency` has the reference's signature (`filter.py:54-87`) on CUDA tensors; `fuse_view` is the
 array-level core of `filter_depth` (`:90-227`): photometric mask, geometric consistency against every source view,
 averaged depth, final mask and the fused points / colours of one reference view.  File handling (PFM, cams,
-pair.txt) is `diffmvs_b200.data_io`.  The small matrix algebra is done with numpy in float32 exactly as the
+pair.txt) is `diffmvs_b200.scene_io`.  The small matrix algebra is done with numpy in float32 exactly as the
 reference does, so both implementations feed identical matrices to the per-pixel arithmetic.
 """
 from __future__ import annotations

@@ -4,7 +4,7 @@ camera files, `pair.txt`, and the assembly of the model's inputs from a referenc
 Behaviour follows `/root/reference/datasets/data_io.py` (PFM :59-122, `write_cam` :124-141,
 `read_camera_parameters` :143-163, `read_pair_file` :172-190) and `/root/reference/datasets/mvs.py`
 (`build_metas` :41-77, `read_cam_file` :79-91, resizing :99-124, `__getitem__` :129-210) so that files written by
-either implementation are read identically by the other; `tests/test_data_io.py` checks this against fixtures
+either implementation are read identically by the other; `tests/test_scene_io.py` checks this against fixtures
 produced by the reference's own functions (`oracle/make_io_golden.py`).  Pure host code (numpy); image resizing
 uses OpenCV exactly like the reference when it is installed.
 """

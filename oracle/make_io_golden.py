@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Golden fixtures for `diffmvs_b200/data_io.py`, produced by the REFERENCE's own functions
+"""Golden fixtures for `diffmvs_b200/scene_io.py`, produced by the REFERENCE's own functions
 (`/root/reference/datasets/data_io.py`, `/root/reference/datasets/mvs.py`) in the build container.
 
     python -m oracle.make_io_golden        # rewrites tests/golden/io/

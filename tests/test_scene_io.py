@@ -1,4 +1,4 @@
-"""`diffmvs_b200/data_io.py` against fixtures produced by the reference's own I/O functions and evaluation loader
+"""`diffmvs_b200/scene_io.py` against fixtures produced by the reference's own I/O functions and evaluation loader
 (`oracle/make_io_golden.py`, run in the build container): PFM and camera files must be byte-identical when written
 and bit-identical when read; `pair.txt` selection, intrinsics rescaling, projection-matrix pyramids and the inverse
 depth range must equal what `datasets/mvs.py` hands to the model."""
@@ -9,7 +9,7 @@ import os
 import numpy as np
 import pytest
 
-from diffmvs_b200 import data_io
+from diffmvs_b200 import scene_io as data_io
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "io")
 META = json.load(open(os.path.join(G, "meta.json")))
