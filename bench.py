@@ -135,7 +135,7 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": a.workload, "views": _views(a.workload)},
+        "dtype": "f32", "data": "synthetic", "config": _config(a.workload, 1, "reference algorithm on the host cores"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -143,9 +143,13 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def _views(workload):
+def _config(workload, world, parallelism):
+    """The `config` object of the JSON line (same for both arms)."""
     from diffmvs_b200 import synth
-    return synth.WORKLOADS[workload][3]
+    variant, H, W, V, D0 = synth.WORKLOADS[workload]
+    return {"workload": workload, "variant": variant, "image": [W, H], "views": V, "numdepth_initial": D0,
+            "numdepth": 384, "batch": 1, "l2": "inputs (155 MB at cfg3) and per-step working set exceed L2",
+            "parallelism": parallelism}
 
 
 def run_ours(a):
@@ -343,9 +347,7 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "precision": ops.get_precision(), "cuda_graph": not a.no_graph, "alt_modes": alt,
-        "config": {"workload": a.workload, "variant": variant, "image": [W, H], "views": V, "numdepth_initial": D0,
-                   "numdepth": 384, "batch": 1, "l2": "inputs (155 MB at cfg3) and per-step working set exceed L2",
-                   "parallelism": f"ref-views sharded, {world} GPU(s), no data-path collective"},
+        "config": _config(a.workload, world, f"ref-views sharded, {world} GPU(s), no data-path collective"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
