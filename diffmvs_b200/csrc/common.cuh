@@ -58,6 +58,22 @@ struct DepthRange {
 // Number of kernels this library has launched in this process (bench.py reports it as gpu_launches).
 extern unsigned long long g_launch_count;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember per kernel AND per device that the
+// opt-in happened (a process may drive several GPUs, e.g. torch tensors on cuda:1 while cuda:0 is also in use).
+struct SmemOptIn {
+  bool done[64] = {};
+  template <typename Fn>
+  void ensure(Fn fn, int bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0, done[0] = false;
+    if (!done[dev]) {
+      cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      done[dev] = true;
+    }
+  }
+};
+
 inline int launch_status() {
   ++g_launch_count;
   cudaError_t e = cudaGetLastError();

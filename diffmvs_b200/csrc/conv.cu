@@ -162,12 +162,9 @@ using KernelFn = void (*)(const ConvArgs);
 
 template <int CO_T, int WC, int PX, int S>
 KernelFn get_kernel() {
-  static bool configured = false;
+  static SmemOptIn opt_in;
   KernelFn fn = conv_kernel<CO_T, WC, PX, S>;
-  if (!configured) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  opt_in.ensure(fn, 200 * 1024);
   return fn;
 }
 
@@ -425,12 +422,12 @@ extern "C" int dmvs_deconv3d_f32(const float* x, const float* w, const float* bi
   int blocks = (int)(ceil_div64(total, 128) < (int64_t)kNumSMs * 16 ? ceil_div64(total, 128) : (int64_t)kNumSMs * 16);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cout == 8) {
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(deconv3d_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+    static SmemOptIn opt_in;
+    opt_in.ensure(deconv3d_kernel<8>, 100 * 1024);
     deconv3d_kernel<8><<<blocks, 128, smem, st>>>(x, w, bias, skip, y, N, D, H, W, Cin);
   } else {
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(deconv3d_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); cfg = true; }
+    static SmemOptIn opt_in;
+    opt_in.ensure(deconv3d_kernel<16>, 100 * 1024);
     deconv3d_kernel<16><<<blocks, 128, smem, st>>>(x, w, bias, skip, y, N, D, H, W, Cin);
   }
   return launch_status();

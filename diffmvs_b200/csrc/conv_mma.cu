@@ -286,12 +286,9 @@ using KernelFn = void (*)(const ConvArgs);
 
 template <int NT, int WC, int PX, int S, int PASSES>
 KernelFn get_kernel() {
-  static bool configured = false;
+  static SmemOptIn opt_in;
   KernelFn fn = conv_mma_kernel<NT, WC, PX, S, PASSES>;
-  if (!configured) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    configured = true;
-  }
+  opt_in.ensure(fn, 200 * 1024);
   return fn;
 }
 

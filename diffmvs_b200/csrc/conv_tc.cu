@@ -462,12 +462,9 @@ using KernelFn = void (*)(const TcArgs);
 
 template <int N, int PASSES, int R>
 KernelFn get_kernel() {
-  static bool configured = false;
+  static SmemOptIn opt_in;
   KernelFn fn = conv_tc_kernel<N, PASSES, R>;
-  if (!configured) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    configured = true;
-  }
+  opt_in.ensure(fn, 220 * 1024);
   return fn;
 }
 

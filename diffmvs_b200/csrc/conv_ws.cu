@@ -665,12 +665,9 @@ using KernelFn = void (*)(const WsArgs);
 
 template <int PASSES, int R, bool GN>
 KernelFn get_kernel() {
-  static bool configured = false;
+  static SmemOptIn opt_in;
   KernelFn fn = conv_ws_kernel<PASSES, R, GN>;
-  if (!configured) {
-    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    configured = true;
-  }
+  opt_in.ensure(fn, 220 * 1024);
   return fn;
 }
 

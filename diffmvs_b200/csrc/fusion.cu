@@ -52,7 +52,7 @@ __device__ __forceinline__ float remap_linear(const float* __restrict__ src, int
 }
 
 __global__ void geo_consistency_kernel(const float* __restrict__ depth_ref, const float* __restrict__ depth_src,
-                                       const GeoMats m, float dmin, float dmax, float pix_thres, float depth_thres,
+                                       const GeoMats m, float dmin, float dmax, double pix_thres, float depth_thres,
                                        uint8_t* __restrict__ mask, float* __restrict__ depth_reproj,
                                        float* __restrict__ x_src_out, float* __restrict__ y_src_out,
                                        float* __restrict__ sum_reproj, int32_t* __restrict__ count, int H, int W, int Hs,
@@ -93,7 +93,7 @@ __global__ void geo_consistency_kernel(const float* __restrict__ depth_ref, cons
   const double dist = sqrt(ddx * ddx + ddy * ddy);
   const float depth_diff = fabsf(__fsub_rn(drep, dref_f));
   const float rel = __fdiv_rn(depth_diff, dref_f);
-  const bool ok = dist < (double)pix_thres && rel < depth_thres && dref_f > dmin && dref_f < dmax;
+  const bool ok = dist < pix_thres && rel < depth_thres && dref_f > dmin && dref_f < dmax;
   if (!ok) drep = 0.0f;
   mask[i] = ok ? 1 : 0;
   depth_reproj[i] = drep;
@@ -139,7 +139,7 @@ __global__ void fuse_kernel(const float* __restrict__ depth_ref, const float* __
 using namespace dmvs;
 
 extern "C" int dmvs_geo_consistency(const float* depth_ref, const float* depth_src, const double* mats68, float depth_min,
-                                    float depth_max, float pix_thres, float depth_thres, uint8_t* mask,
+                                    float depth_max, double pix_thres, float depth_thres, uint8_t* mask,
                                     float* depth_reproj, float* x_src, float* y_src, float* sum_reproj, int32_t* count,
                                     int32_t H, int32_t W, int32_t Hs, int32_t Ws, void* stream) {
   if (!depth_ref || !depth_src || !mats68 || !mask || !depth_reproj) return DMVS_ERR_ARG;

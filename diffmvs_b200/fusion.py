@@ -43,6 +43,22 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device_of(argpos: int = 0):
+    """Run the call with the device of its first tensor argument current (kernel launches follow the CUDA current
+    device, not the tensors)."""
+    def deco(fn):
+        def wrapper(*a, **k):
+            t = a[argpos]
+            if isinstance(t, torch.Tensor) and t.is_cuda and t.device.index != torch.cuda.current_device():
+                with torch.cuda.device(t.device):
+                    return fn(*a, **k)
+            return fn(*a, **k)
+        wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+        return wrapper
+    return deco
+
+
+@_on_device_of(0)
 def check_geometric_consistency(depth_ref: Tensor, intrinsics_ref, extrinsics_ref, depth_src: Tensor, intrinsics_src,
                                 extrinsics_src, ref_depth_max, ref_depth_min, geo_pixel_thres: float = 1.0,
                                 geo_depth_thres: float = 0.01, _acc: Optional[Tuple[Tensor, Tensor]] = None):
@@ -65,6 +81,7 @@ def check_geometric_consistency(depth_ref: Tensor, intrinsics_ref, extrinsics_re
     return mask.bool(), drep, xs, ys
 
 
+@_on_device_of(0)
 def fuse_view(ref_depth: Tensor, ref_intrinsics, ref_extrinsics, depth_max, depth_min, confidences: Sequence[Tensor],
               photo_thres: Sequence[float], src_views: Sequence[Tuple[Tensor, object, object]], ref_img: Optional[Tensor] = None,
               geo_mask_thres: int = 3, geo_pixel_thres: float = 1.0, geo_depth_thres: float = 0.01):
@@ -102,6 +119,7 @@ def fuse_view(ref_depth: Tensor, ref_intrinsics, ref_extrinsics, depth_max, dept
     return out
 
 
+@_on_device_of(0)
 def fuse_view_dynamic(ref_depth: Tensor, ref_intrinsics, ref_extrinsics, depth_max, depth_min, confidences: Sequence[Tensor],
                       photo_thres: Sequence[float], src_views: Sequence[Tuple[Tensor, object, object]],
                       dh_pixel_dist_num: Sequence[int], ref_img: Optional[Tensor] = None):

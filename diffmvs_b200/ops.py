@@ -178,9 +178,23 @@ def _tensor_bytes(obj) -> int:
     return 0
 
 
+def _first_cuda_device(a, k) -> Optional[int]:
+    for t in list(a) + list(k.values()):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device.index
+    return None
+
+
 def _profiled(name: str):
+    """Decorator of every kernel entry point: runs the call with the tensors' device current (launches, streams and
+    the per-device shared-memory opt-in all follow the CUDA current device, so a model on cuda:1 must not launch
+    on cuda:0's stream), and records CUDA-event timings when a `Profiler` is installed."""
     def deco(fn):
         def wrapper(*a, **k):
+            dev = _first_cuda_device(a, k)
+            if dev is not None and dev != torch.cuda.current_device():
+                with torch.cuda.device(dev):
+                    return wrapper(*a, **k)
             prof = _PROFILER
             if prof is None:
                 return fn(*a, **k)

@@ -58,9 +58,18 @@ def make_args(variant: str, numdepth_initial: int = 48, numdepth: int = 384, **o
     return argparse.Namespace(**base)
 
 
+# per-workload overrides of the DTU defaults: Tanks & Temples runs with a smaller noise scale
+# (`/root/reference/scripts/test/test_tank_casdiffmvs.sh:11-17`: numdepth_initial 96, scale 0 .125 .025, ddim_eta 0 1 1)
+_WORKLOAD_OVERRIDES: Dict[str, dict] = {
+    "cfg4": dict(scale=[0.0, 0.125, 0.025]),
+}
+
+
 def workload_args(name: str, **over) -> argparse.Namespace:
     variant, _, _, _, d_init = WORKLOADS[name]
-    return make_args(variant, numdepth_initial=d_init, **over)
+    kw = dict(_WORKLOAD_OVERRIDES.get(name, {}))
+    kw.update(over)
+    return make_args(variant, numdepth_initial=d_init, **kw)
 
 
 # ----------------------------------------------------------------------------------------

@@ -238,7 +238,7 @@ int dmvs_nhwc_to_nchw(const float* x, int32_t x_ps, float* y, int32_t N, int32_t
  * sum_reproj / count are given they are updated in place (+= depth_reproj, += mask), which accumulates
  * `sum(all_srcview_depth_ests)` and `geo_mask_sum` of filter_depth over successive source views. */
 int dmvs_geo_consistency(const float* depth_ref, const float* depth_src, const double* mats68, float depth_min,
-                         float depth_max, float pix_thres, float depth_thres, uint8_t* mask, float* depth_reproj,
+                         float depth_max, double pix_thres, float depth_thres, uint8_t* mask, float* depth_reproj,
                          float* x_src, float* y_src, float* sum_reproj, int32_t* count, int32_t H, int32_t W,
                          int32_t Hs, int32_t Ws, void* stream);
 

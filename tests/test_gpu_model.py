@@ -180,6 +180,48 @@ def test_full_size_against_oracle_on_device(workload, monkeypatch):
         assert e < 1e-3, (i, e)
     assert tuple(out["depth"][-1].shape) == (1, imgs[0].shape[2], imgs[0].shape[3])
 
+@pytest.mark.parametrize("workload", ["cfg3", "cfg4"])
+def test_full_size_against_cpu_fp32_oracle(workload, monkeypatch):
+    """BASELINE.json configs[2] (cfg3: DTU 1600x1152, 7 views, D_init 48) and configs[3] (cfg4: Tanks & Temples shaped
+    1920x1024, 11 views, D_init 96, `scale 0 .125 .025`, `/root/reference/scripts/test/test_tank_casdiffmvs.sh:11-17`)
+    end to end against the CPU fp32 oracle (the restatement pinned bit-exact to the reference), same inputs, weights
+    and noise.  Records depth rel-L1 per output and the stage-1 floor-index mismatch rate (north_star: <= 1e-3 rel-L1,
+    hypothesis indices exact)."""
+    args = synth.workload_args(workload)
+    if workload == "cfg4":
+        assert args.numdepth_initial == 96 and args.scale == [0.0, 0.125, 0.025] and args.ddim_eta == [0, 1, 1]
+    sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
+    imgs, proj, dv = synth.workload_inputs(workload)
+
+    def mk():
+        gen = torch.Generator().manual_seed(3)
+        return lambda like: torch.randn(like.shape, generator=gen, dtype=torch.float32)
+
+    taps_ref = {}
+    with torch.no_grad():
+        ref = O.casdiffmvs_forward(sd, args, imgs, proj, dv, randn=mk(), taps=taps_ref)
+    keep = {k: taps_ref[k] for k in ("stage1_floor", "view_weights")}
+    taps_ref.clear()
+    model = _build(args, sd)
+    _patch_noise(monkeypatch, mk())
+    taps = {}
+    with torch.no_grad():
+        out = model.plan(DEV).forward(*_to_dev(imgs, proj, dv), taps=taps)
+    mism = (taps["stage1_floor"].cpu().long() != keep["stage1_floor"][:, 0]).float().mean().item()
+    REPORT.append((workload, "stage1 floor-index mismatch rate vs CPU fp32 oracle", mism))
+    assert mism < 2e-3, mism
+    assert rel_l1(taps["view_weights"], keep["view_weights"]) < 1e-4
+    assert len(out["depth"]) == len(ref["depth"]) == 6
+    for i, (d, r) in enumerate(zip(out["depth"], ref["depth"])):
+        assert tuple(d.shape) == tuple(r.shape)
+        assert torch.isfinite(d).all()
+        e = rel_l1(d, r)
+        REPORT.append((workload, f"depth[{i}] vs CPU fp32 oracle", e))
+        assert e < DEPTH_TOL, (workload, i, e)
+    for i, (c, r) in enumerate(zip(out["photometric_confidence"], ref["photometric_confidence"])):
+        assert (c.cpu() - r).abs().mean().item() < 1e-4, (workload, "conf", i)
+
+
 @pytest.mark.parametrize("mode,tol", [("tf32x3", DEPTH_TOL), ("ws_tf32x3", DEPTH_TOL), ("tf32", 1e-2)])
 @pytest.mark.parametrize("workload", ["cas_small", "cfg2"])
 def test_tensor_core_modes_meet_the_parity_bar(workload, mode, tol, monkeypatch):
