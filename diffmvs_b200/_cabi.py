@@ -16,7 +16,9 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4
 RES_NONE, RES_PRE_ACT, RES_POST_ACT = 0, 1, 2
 EPI_STD, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_TC_TF32X3, PREC_TC_TF32, PREC_AUTO = 0, 1, 2, 3, 4, 5
-PREC_WS_TF32X3, PREC_WS_TF32 = 6, 7
+PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3 = 6, 7, 8
+
+ABI_VERSION = 3   # DMVS_ABI_VERSION of include/diffmvs_b200.h
 
 f32p = C.c_void_p
 i32 = C.c_int32
@@ -46,6 +48,7 @@ SIGNATURES = {
     "dmvs_conv_f32": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "dmvs_conv_backends": (C.c_int, [C.POINTER(ConvDesc)]),
     "dmvs_conv_ws_plan": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i32]),
+    "dmvs_conv_ws2_plan": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i32]),
     "dmvs_deconv3d_f32": (C.c_int, [f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_compose_homographies": (C.c_int, [f32p, f32p, i32, i32, C.c_void_p]),
     "dmvs_warp_volume": (C.c_int, [f32p, i32, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]),
@@ -68,6 +71,9 @@ SIGNATURES = {
                                        f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_fuse_points": (C.c_int, [f32p, f32p, C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, f32p, i32, i32, C.c_void_p]),
+    "dmvs_fuse_view": (C.c_int, [f32p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, C.c_void_p, C.c_void_p, i32,
+                                 C.c_void_p, C.c_float, C.c_float, C.c_double, C.c_float, i32, i32, C.c_double, C.c_double,
+                                 C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, f32p, C.c_void_p]),
     "dmvs_nchw_to_nhwc": (C.c_int, [f32p, f32p, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_nhwc_to_nchw": (C.c_int, [f32p, i32, f32p, i32, i32, i32, C.c_void_p]),
 }
@@ -91,7 +97,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.dmvs_abi_version() != 2:
+        if handle.dmvs_abi_version() != ABI_VERSION:
             raise KernelLibraryError("ABI version mismatch between _cabi.py and the built library")
         _LIB = handle
     return _LIB

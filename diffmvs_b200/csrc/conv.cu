@@ -232,6 +232,15 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
       alt.precision = DMVS_PREC_TC_TF32X3;
       return dispatch_conv_tc(alt, static_cast<cudaStream_t>(stream));
     }
+  } else if (d.precision == DMVS_PREC_WS2_TF32X3) {
+    // TMA-fed width-stacked kernel where it applies, the first-generation one for nearest-upsampled inputs, FFMA elsewhere
+    if (conv_ws2_supported(d)) return dispatch_conv_ws2(d, static_cast<cudaStream_t>(stream));
+    if (conv_ws_supported(d)) {
+      dmvs_conv_desc alt = d;
+      alt.precision = DMVS_PREC_WS_TF32X3;
+      return dispatch_conv_ws(alt, static_cast<cudaStream_t>(stream));
+    }
+    // fall through to the FFMA kernel
   } else if (d.precision == DMVS_PREC_WS_TF32X3 || d.precision == DMVS_PREC_WS_TF32) {
     // width-stacked tcgen05 kernel wherever its layout preconditions hold (stride 1, 16-byte channel groups);
     // DMVS_WS_MIN_K / DMVS_WS_MIN_MACS bound the layers it takes (tuning aids, see dispatch rule below)
@@ -332,6 +341,11 @@ extern "C" int dmvs_conv_ws_plan(const dmvs_conv_desc* dp, int32_t* out, int32_t
   return plan_conv_ws(*dp, out, cap);
 }
 
+extern "C" int dmvs_conv_ws2_plan(const dmvs_conv_desc* dp, int32_t* out, int32_t cap) {
+  if (dp == nullptr || out == nullptr || cap <= 0) return DMVS_ERR_ARG;
+  return plan_conv_ws2(*dp, out, cap);
+}
+
 extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   if (dp == nullptr) return DMVS_ERR_ARG;
   const dmvs_conv_desc& d = *dp;
@@ -339,6 +353,7 @@ extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   if (d.w_t) mask |= 2;                                // bit 1: legacy mma.sync kernel
   if (d.w_tc && conv_tc_supported(d)) mask |= 4;       // bit 2: tcgen05 kernel, taps as descriptor offsets
   if (conv_ws_supported(d)) mask |= 8;       // bit 3: tcgen05 kernel, kernel-row taps stacked along N
+  if (conv_ws2_supported(d)) mask |= 16;     // bit 4: the same arithmetic behind the TMA-fed pipeline (conv_ws2.cu)
   return mask;
 }
 

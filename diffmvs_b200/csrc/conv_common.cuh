@@ -231,4 +231,10 @@ bool conv_ws_supported(const dmvs_conv_desc& d);
 int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t stream);
 int plan_conv_ws(const dmvs_conv_desc& d, int32_t* out, int cap);   // tile plan only: {CC,N,TH,TW,n_blk,R,ctas,smem} per launch
 
+// second-generation width-stacked back end (conv_ws2.cu): TMA-fed ring, dedicated split / MMA / epilogue warps, two
+// TMEM accumulator sets
+bool conv_ws2_supported(const dmvs_conv_desc& d);
+int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t stream);
+int plan_conv_ws2(const dmvs_conv_desc& d, int32_t* out, int cap);
+
 }  // namespace dmvs

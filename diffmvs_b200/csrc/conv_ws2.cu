@@ -1,0 +1,691 @@
+// Width-stacked tcgen05 / TMEM implicit-GEMM convolution, second generation ("ws2"): the arithmetic and operand
+// layouts of conv_ws.cu (kernel-row taps stacked along N, 3xTF32, shift-add epilogue - see the header of that file)
+// behind a fully asynchronous, role-specialised pipeline:
+//
+//   warp 0      TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
+//                              hardware zero fill = the convolution's padding) + cp.async.bulk of the stage's weight
+//                              slabs, all completing on tma_full[slot] (mbarrier transaction count)
+//   warps 2-9   split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
+//                              fence.proxy.async and one arrival per warp on op_full[slot]
+//   warp 1      MMA issuer     one elected lane issues the row MMAs x3 passes into one of TWO TMEM accumulator sets;
+//                              tcgen05.commit frees the ring slot (empty[slot]) and, after a tile's last stage,
+//                              publishes the accumulators (acc_full[set])
+//   warps 10-13 epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
+//                              t+1 fill the other set; acc_empty[set] hands the set back
+//
+// One persistent CTA per SM; the ring is R = 2..4 stages deep, a stage = (tile, depth tap, stride phase, 8 input
+// channels).  Compared with conv_ws.cu nothing in a CTA waits for global-memory latency any more: the producer runs up
+// to R-1 stages ahead, the split of stage s+1 overlaps the MMAs of stage s, and the epilogue overlaps the next tile.
+#include <cstdlib>
+#include <type_traits>
+
+#include "conv_common.cuh"
+#include "tcgen05_common.cuh"
+
+namespace dmvs {
+namespace {
+
+using namespace tc;
+
+constexpr int kSplitWarps = 8;
+constexpr int kEpiWarps = 4;                                       // warp % 4 = TMEM lane quadrant
+constexpr int kFirstSplitWarp = 2;
+constexpr int kFirstEpiWarp = kFirstSplitWarp + kSplitWarps;      // 10: 10 % 4 = 2, 11 -> 3, 12 -> 0, 13 -> 1
+constexpr int kWs2Threads = 32 * (kFirstEpiWarp + kEpiWarps);     // 448
+constexpr int kSplitThreads = 32 * kSplitWarps;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kMaxRing = 4;
+
+struct alignas(64) Ws2Args {
+  CUtensorMap map_x;     // (C, W, H, D, N) view of x, box {4, S*in_cols, S*in_rows, 1, 1}, traversal step S in W and H
+  CUtensorMap map_x2;    // same for x2 (only read when C2 > 0)
+  dmvs_conv_desc d;
+  int cin_pad;           // (C1+C2) rounded up to 8
+  int co_base;           // first output channel of this launch
+  int CC;                // output channels of this launch (multiple of 8)
+  int N;                 // MMA N = KWe*CC rounded up to 16
+  int S;                 // stride (1 or 2): a stride-2 convolution runs as S*S stride-1 phases over decimated planes
+  int KHe, KWe;          // kernel extent in phase-plane shifts
+  int smin_h, smin_w;
+  int TH, TW, in_rows, in_cols;
+  int plane;             // positions per channel-quad plane (multiple of 8; incl. slack read by the last M block)
+  int box_units;         // in_rows * in_cols: 16-byte units per quad plane written by one TMA box
+  int n_blk;             // M=128 blocks per tile
+  int acc_cols;          // TMEM columns of one accumulator set (n_blk * N)
+  int tmem_cols;         // allocated TMEM columns (power of two >= 2 * acc_cols)
+  int tiles_x, tiles_y, total_tiles;
+  int R;                 // ring depth
+  int stage_f;           // floats per operand plane set of one stage (2 * plane * 4)
+  int wslab_f;           // floats per weight slab (KHe * 2 * N * 4)
+  int halo_f;            // floats of ONE halo exchange buffer (two are allocated, alternating per tile)
+  int vec_y, vec_res, vec_bias;
+  float inv_in_cols;
+  int64_t w_off;         // offset (floats) of this launch's hi slabs inside w_ws
+  int64_t w_plane;       // distance (floats) from a hi slab to its lo twin
+};
+
+struct Stage {
+  int tile, kd, phase, chunk;
+  int n, od, ty0, tx0;
+};
+
+template <bool GN>
+__global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_constant__ Ws2Args a) {
+  const dmvs_conv_desc& d = a.d;
+  extern __shared__ __align__(1024) float smem[];
+  const int N = a.N;
+  float* hi0 = smem;                                   // [R][stage_f]   raw tile lands here, split in place -> hi
+  float* lo0 = hi0 + a.R * a.stage_f;                  // [R][stage_f]
+  float* w_hi0 = lo0 + a.R * a.stage_f;                // [R][wslab_f]
+  float* w_lo0 = w_hi0 + a.R * a.wslab_f;              // [R][wslab_f]
+  float* halo0 = w_lo0 + a.R * a.wslab_f;              // [2][halo_f]
+  float* gn_s = halo0 + 2 * a.halo_f;                  // [2][C1] when GN
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) uint64_t tma_full[kMaxRing], op_full[kMaxRing], empty_bar[kMaxRing], acc_full[2], acc_empty[2];
+  __shared__ float stat_s[2][8];
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < kMaxRing; ++i) {
+      mbar_init(&tma_full[i], 1);
+      mbar_init(&op_full[i], kSplitWarps);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    mbar_init_fence();
+    prefetch_tensormap(&a.map_x);
+    if (d.C2 > 0) prefetch_tensormap(&a.map_x2);
+  }
+  if (tid < 16) stat_s[tid >> 3][tid & 7] = 0.0f;
+  fence_tc_before();
+  __syncthreads();
+  fence_tc_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nchunks = a.cin_pad >> 3;
+  const int nphase = a.S * a.S;
+
+  auto kd_first = [&](int od) { const int v = d.pad_d - od * a.S; return v > 0 ? v : 0; };
+  auto kd_last = [&](int od) { const int v = d.D - 1 + d.pad_d - od * a.S; return v < d.KD - 1 ? v : d.KD - 1; };
+  auto first_stage_of = [&](int tile) {
+    Stage s{tile, 0, 0, 0, 0, 0, 0, 0};
+    if (tile < a.total_tiles) {
+      const int tx = tile % a.tiles_x;
+      const int r = tile / a.tiles_x;
+      const int ty = r % a.tiles_y;
+      const int z = r / a.tiles_y;
+      s.n = z / d.Do;
+      s.od = z - s.n * d.Do;
+      s.ty0 = ty * a.TH;
+      s.tx0 = tx * a.TW;
+      s.kd = kd_first(s.od);
+    }
+    return s;
+  };
+  auto advance = [&](const Stage& c) {
+    Stage s = c;
+    if (++s.chunk < nchunks) return s;
+    s.chunk = 0;
+    if (++s.phase < nphase) return s;
+    s.phase = 0;
+    if (++s.kd <= kd_last(c.od)) return s;
+    return first_stage_of(c.tile + (int)gridDim.x);
+  };
+
+  Stage cur = first_stage_of((int)blockIdx.x);
+
+  if (warp == 0) {
+    // =============================== TMA producer ==================================================================
+    if (elect_one()) {
+      int slot = 0, use = 0;
+      const uint32_t box_bytes = (uint32_t)a.box_units * 16u, w_bytes = (uint32_t)a.wslab_f * 4u;
+      while (cur.tile < a.total_tiles) {
+        if (use > 0) mbar_wait(&empty_bar[slot], (uint32_t)((use - 1) & 1));   // the MMAs that read this slot have retired
+        mbar_arrive_expect_tx(&tma_full[slot], 2u * box_bytes + 2u * w_bytes);
+        const int pa = a.S == 2 ? (cur.phase >> 1) : 0, pb = a.S == 2 ? (cur.phase & 1) : 0;
+        const int iy0 = a.S * (cur.ty0 + a.smin_h) + pa, ix0 = a.S * (cur.tx0 + a.smin_w) + pb;
+        const int id = cur.od * a.S + cur.kd - d.pad_d;
+        float* dst = hi0 + slot * a.stage_f;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int ch = cur.chunk * 8 + q * 4;
+          // channels past C1+C2 (cin_pad rounding) are out of bounds of the tensor map: zero filled
+          if (ch < d.C1 || d.C2 == 0)
+            tma_load_5d(dst + q * a.plane * 4, &a.map_x, &tma_full[slot], ch, ix0, iy0, id, cur.n);
+          else
+            tma_load_5d(dst + q * a.plane * 4, &a.map_x2, &tma_full[slot], ch - d.C1, ix0, iy0, id, cur.n);
+        }
+        const float* wsrc = d.w_ws + a.w_off + (int64_t)((cur.kd * nphase + cur.phase) * nchunks + cur.chunk) * a.wslab_f;
+        bulk_load(w_hi0 + slot * a.wslab_f, wsrc, w_bytes, &tma_full[slot]);
+        bulk_load(w_lo0 + slot * a.wslab_f, wsrc + a.w_plane, w_bytes, &tma_full[slot]);
+        cur = advance(cur);
+        if (++slot == a.R) { slot = 0; ++use; }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ====================================================================
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_tf32_m128(N);
+    const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
+    const uint32_t b_step = 2u * (uint32_t)N;                // one kernel row of weights, in 16-byte units
+    int slot = 0, use = 0;
+    int acc = 0, acc_use = 0;                                // accumulator set of the current tile / earlier uses of that set
+    bool tile_start = true;
+    while (cur.tile < a.total_tiles) {
+      if (tile_start && acc_use > 0) {                       // the epilogue of the tile two back has drained this set
+        mbar_wait(&acc_empty[acc], (uint32_t)((acc_use - 1) & 1));
+        fence_tc_after();
+      }
+      mbar_wait(&op_full[slot], (uint32_t)(use & 1));        // operands of this stage are split and fenced
+      fence_tc_after();
+      float* a_hi = hi0 + slot * a.stage_f;
+      float* a_lo = lo0 + slot * a.stage_f;
+      const uint64_t dah0 = umma_desc(smem_u32(a_hi), lbo_a, 128), dal0 = umma_desc(smem_u32(a_lo), lbo_a, 128);
+      const uint64_t dbh0 = umma_desc(smem_u32(w_hi0 + slot * a.wslab_f), lbo_b, 128);
+      const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + slot * a.wslab_f), lbo_b, 128);
+      const int pa = a.S == 2 ? (cur.phase >> 1) : 0;
+      uint32_t rows = 0;   // kernel rows present in this phase: shift khe <-> kernel row S*(khe + smin_h) + pa + pad_h
+      for (int khe = 0; khe < a.KHe; ++khe) {
+        const int kh = a.S * (khe + a.smin_h) + pa + d.pad_h;
+        if (kh >= 0 && kh < d.KH) rows |= 1u << khe;
+      }
+      const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
+      for (int blk = 0; blk < a.n_blk; ++blk) {
+        const uint32_t d_tmem = acc_base + (uint32_t)(blk * N);
+        uint32_t accum = tile_start ? 0u : 1u;
+        uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
+        for (int khe = 0; khe < a.KHe; ++khe, a_off += (uint32_t)a.in_cols, b_off += b_step) {
+          if (!((rows >> khe) & 1u)) continue;
+          if (leader) {
+            umma_tf32(d_tmem, dal0 + a_off, dbh0 + b_off, idesc, accum);
+            umma_tf32(d_tmem, dah0 + a_off, dbl0 + b_off, idesc, 1u);
+            umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, 1u);
+          }
+          accum = 1u;
+        }
+      }
+      const Stage nxt = advance(cur);
+      const bool tile_end = nxt.tile != cur.tile;
+      if (leader) {
+        umma_commit(&empty_bar[slot]);                        // slot reusable once every MMA issued so far has retired
+        if (tile_end) umma_commit(&acc_full[acc]);            // ... and the tile's accumulators are complete
+      }
+      __syncwarp();
+      tile_start = tile_end;
+      if (tile_end && ++acc == 2) { acc = 0; ++acc_use; }
+      cur = nxt;
+      if (++slot == a.R) { slot = 0; ++use; }
+    }
+  } else if (warp < kFirstEpiWarp) {
+    // =============================== split workers ================================================================
+    const int wtid = tid - 32 * kFirstSplitWarp;
+    int slot = 0, use = 0, gn_n = -1;
+    while (cur.tile < a.total_tiles) {
+      if (GN && cur.n != gn_n) {                             // GroupNorm affine of the producer is per sample
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kSplitThreads) : "memory");
+        for (int c = wtid; c < d.C1; c += kSplitThreads) groupnorm_affine(d, cur.n, c, gn_s);
+        asm volatile("bar.sync 1, %0;\n" ::"n"(kSplitThreads) : "memory");
+        gn_n = cur.n;
+      }
+      mbar_wait(&tma_full[slot], (uint32_t)(use & 1));       // raw tile (and weights) of this stage have landed
+      float* hi = hi0 + slot * a.stage_f;
+      float* lo = lo0 + slot * a.stage_f;
+      const int iy0 = cur.ty0 + a.smin_h, ix0 = cur.tx0 + a.smin_w;   // GN layers are stride 1
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), g0 = g1;
+        bool ch_ok = false;
+        if (GN) {
+          const int ch = cur.chunk * 8 + q * 4;
+          ch_ok = ch < d.C1;
+          if (ch_ok) {
+            g1 = *reinterpret_cast<const float4*>(gn_s + ch);
+            g0 = *reinterpret_cast<const float4*>(gn_s + d.C1 + ch);
+          }
+        }
+        float4* ph = reinterpret_cast<float4*>(hi + q * a.plane * 4);
+        float4* pl = reinterpret_cast<float4*>(lo + q * a.plane * 4);
+#pragma unroll 4
+        for (int u = wtid; u < a.box_units; u += kSplitThreads) {
+          float4 v = ph[u];
+          if (GN) {
+            const int row = (int)(((float)u + 0.5f) * a.inv_in_cols);
+            const int col = u - row * a.in_cols;
+            const int iy = iy0 + row, ix = ix0 + col;
+            if (ch_ok && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {   // padding stays zero
+              v.x = siluf_(fmaf(v.x, g1.x, g0.x));
+              v.y = siluf_(fmaf(v.y, g1.y, g0.y));
+              v.z = siluf_(fmaf(v.z, g1.z, g0.z));
+              v.w = siluf_(fmaf(v.w, g1.w, g0.w));
+            } else {
+              v = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x);
+          split_tf32(v.y, h.y, l.y);
+          split_tf32(v.z, h.z, l.z);
+          split_tf32(v.w, h.w, l.w);
+          ph[u] = h;
+          pl[u] = l;
+        }
+      }
+      fence_async_smem();
+      __syncwarp();                                          // one arrival per warp: the lanes' writes are ordered before it
+      if (lane == 0) mbar_arrive(&op_full[slot]);
+      cur = advance(cur);
+      if (++slot == a.R) { slot = 0; ++use; }
+    }
+  } else {
+    // =============================== epilogue warps ==============================================================
+    // A lane owns one accumulator row (position p) and NCH = 8 or 16 output channels: tap kw of its output lives in row
+    // p + kw, i.e. in lane + kw of the same warp (a shuffle) or, for the last KW-1 lanes, in the first rows of the next
+    // lane quadrant / next M block (a small shared "halo", written in a first pass).  Warp w handles TMEM lane quadrant
+    // w % 4 of every M block.
+    const int quadrant = warp & 3;
+    const int etid = tid - 32 * kFirstEpiWarp;
+    auto epilogue = [&](auto nch_tag, int n, int od, int ty0, int tx0, uint32_t acc_base, float* halo, float* stat) {
+      constexpr int NCH = decltype(nch_tag)::value;
+      const int ncg = a.CC / NCH;
+      const int n_items = a.n_blk * ncg;                    // (block, channel group) pairs, block-major
+      const int KWe = a.KWe, KWm1 = KWe - 1;
+      const int halo_q = KWm1 * KWm1 * NCH;                 // floats per (item, quadrant)
+      const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
+      const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
+      const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
+      if (KWm1 > 0) {
+        int blk = 0, cg = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_items; ++it) {              // pass 1: rows other quadrants will need
+          const uint32_t trow = acc_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * NCH);
+          float* hq = halo + (it * 4 + quadrant) * halo_q;
+#pragma unroll 1
+          for (int kw = 1; kw < KWe; ++kw) {
+            float v[NCH];
+            tmem_ld<NCH>(trow + (uint32_t)(kw * a.CC), v);
+            tmem_wait_ld();
+            tmem_pin(v);
+            if (lane < kw) {
+              float* dst = hq + ((kw - 1) * KWm1 + lane) * NCH;
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          }
+          if (++cg == ncg) { cg = 0; ++blk; }
+        }
+        asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // epilogue warps only: halo visible
+      }
+      int blk = 0, cg = 0;
+#pragma unroll 1
+      for (int it = 0; it < n_items; ++it) {                // pass 2: shift-add, fused epilogue, store
+        const uint32_t trow = acc_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * NCH);
+        const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
+        const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
+        // value of tap kw for this lane's output: row of lane + kw (shuffle) or the halo of the next quadrant / block
+        auto shift_in = [&](float (&v)[NCH], int kw) {
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
+          if (lane + kw >= 32) {
+            if (have_next) {
+              const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * NCH;
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4) {
+                const float4 h4 = *reinterpret_cast<const float4*>(src + j);
+                v[j] = h4.x; v[j + 1] = h4.y; v[j + 2] = h4.z; v[j + 3] = h4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NCH; ++j) v[j] = 0.0f;      // past the last block: never a valid output
+            }
+          }
+        };
+        float acc[NCH];
+        if (KWe == 3) {
+          float v1[NCH], v2[NCH];
+          tmem_ld<NCH>(trow, acc);
+          tmem_ld<NCH>(trow + (uint32_t)a.CC, v1);
+          tmem_ld<NCH>(trow + (uint32_t)(2 * a.CC), v2);
+          tmem_wait_ld();
+          tmem_pin(acc);
+          tmem_pin(v1);
+          tmem_pin(v2);
+          shift_in(v1, 1);
+          shift_in(v2, 2);
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) acc[j] = (acc[j] + v1[j]) + v2[j];
+        } else {
+          tmem_ld<NCH>(trow, acc);
+          tmem_wait_ld();
+          tmem_pin(acc);
+#pragma unroll 1
+          for (int kw = 1; kw < KWe; ++kw) {
+            float v[NCH];
+            tmem_ld<NCH>(trow + (uint32_t)(kw * a.CC), v);
+            tmem_wait_ld();
+            tmem_pin(v);
+            shift_in(v, kw);
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) acc[j] += v[j];
+          }
+        }
+        const int c0 = a.co_base + cg * NCH;                  // first absolute output channel of this lane
+        const int p = blk * 128 + quadrant * 32 + lane;
+        const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
+        const int px = p - py * a.in_cols;
+        const int oy = ty0 + py, ox = tx0 + px;
+        const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
+        float ps[NCH / 2], pq[NCH / 2];                       // per channel pair: sum, sum of squares
+#pragma unroll
+        for (int j = 0; j < NCH / 2; ++j) ps[j] = pq[j] = 0.0f;
+        if (valid) {
+          const bool full = c0 + NCH <= d.Cout;
+          if (d.bias != nullptr) {
+            if (a.vec_bias && full) {
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4) {
+                const float4 b4 = ldg4(d.bias + c0 + j);
+                acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k)
+                if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
+            }
+          }
+          const int64_t opix = (img_base + oy) * d.Wo + ox;
+          int64_t rpix = opix;
+          if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+          if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
+            const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+            if (d.res_mode != DMVS_RES_NONE) {
+              float r[NCH];
+              const float* rp = d.res + rpix * d.res_ps + c0;
+              if (a.vec_res && full) {
+#pragma unroll
+                for (int j = 0; j < NCH; j += 4) {
+                  const float4 r4 = ldg4(rp + j);
+                  r[j] = r4.x; r[j + 1] = r4.y; r[j + 2] = r4.z; r[j + 3] = r4.w;
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) r[k] = c0 + k < d.Cout ? __ldg(rp + k) : 0.0f;
+              }
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                float x = pre_act ? acc[k] + r[k] : acc[k];
+                if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
+                acc[k] = pre_act ? x : x + r[k];
+              }
+            } else if (relu_from <= c0) {                     // the common case: ReLU on every channel
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) acc[k] = fmaxf(acc[k], 0.0f);
+            } else if (relu_from < c0 + NCH) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k)
+                if (c0 + k >= relu_from) acc[k] = fmaxf(acc[k], 0.0f);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+              if (c0 + k < d.Cout) acc[k] = epilogue_value(d, acc[k], c0 + k, opix, rpix);
+          }
+          float* yp = d.y + opix * d.y_ps + c0;
+          if (a.vec_y && full) {
+#pragma unroll
+            for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+              if (c0 + k < d.Cout) yp[k] = acc[k];
+          }
+          if (d.out_stats != nullptr) {
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const float x = c0 + k < d.Cout ? acc[k] : 0.0f;
+              ps[k >> 1] += x;
+              pq[k >> 1] += x * x;
+            }
+          }
+        }
+        if (d.out_stats != nullptr) {
+          // GroupNorm statistics: Cout/4 channels per group is 2, 4 or a multiple of 8 (checked on the host), so a
+          // channel pair never straddles two groups
+          const int cpg = d.Cout >> 2;
+#pragma unroll
+          for (int j = 0; j < NCH / 2; ++j) {
+            const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
+            const int c = c0 + 2 * j;
+            if (lane == 0 && c < d.Cout) {
+              const int g = c / cpg;
+              atomicAdd(&stat[g * 2 + 0], s);
+              atomicAdd(&stat[g * 2 + 1], q);
+            }
+          }
+        }
+        if (++cg == ncg) { cg = 0; ++blk; }
+      }
+      if (d.out_stats != nullptr) {
+        asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // every epilogue warp's shared atomics are in
+        if (etid < 8) {
+          atomicAdd(d.out_stats + n * 8 + etid, (double)stat[etid]);
+          stat[etid] = 0.0f;                                   // ready for the tile after next (same buffer)
+        }
+      }
+    };
+
+    int t_local = 0;
+    for (int tile = (int)blockIdx.x; tile < a.total_tiles; tile += (int)gridDim.x, ++t_local) {
+      const Stage s = first_stage_of(tile);
+      const int acc = t_local & 1;
+      mbar_wait(&acc_full[acc], (uint32_t)((t_local >> 1) & 1));
+      fence_tc_after();
+      const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
+      float* halo = halo0 + acc * a.halo_f;
+      if ((a.CC & 15) == 0)
+        epilogue(std::integral_constant<int, 16>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo, stat_s[acc]);
+      else
+        epilogue(std::integral_constant<int, 8>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo, stat_s[acc]);
+      fence_tc_before();                                     // TMEM reads ordered before the hand-back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  fence_tc_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(a.tmem_cols));
+}
+
+using KernelFn = void (*)(const Ws2Args);
+
+template <bool GN>
+KernelFn get_kernel() {
+  static SmemOptIn opt_in;
+  KernelFn fn = conv_ws2_kernel<GN>;
+  opt_in.ensure(fn, 227 * 1024);
+  return fn;
+}
+
+struct TileCfg2 {
+  int TH = 0, TW = 0, in_cols = 0, n_blk = 0, plane = 0, R = 0, halo_f = 0;
+  size_t smem = 0;
+  double est = 1e30;   // modelled cycles for the whole launch
+};
+
+inline int floor_div(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+inline void ws_extent(int K, int pad, int S, int* smin, int* ext) {
+  *smin = floor_div(-pad, S);
+  *ext = floor_div(K - 1 - pad, S) - *smin + 1;
+}
+inline int ws_cc_max(int KW) {
+  int cc = (256 / KW) & ~7;
+  return cc > 64 ? 64 : cc;
+}
+
+// Tile search: every (tile height, M blocks, ring depth) that fits 227 KB of shared memory and half of TMEM (two
+// accumulator sets) is scored with a small throughput model - per tile the slower of the tensor pipe and the
+// shared-memory port (MMA operand reads + split pass + TMA writes), plus a fixed per-tile cost - times the number of
+// tile waves over the SMs.  Deeper rings win ties.
+void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int CC, int cin_pad, TileCfg2& best) {
+  static const int force_th = getenv("DMVS_WS2_TH") ? atoi(getenv("DMVS_WS2_TH")) : 0;   // tuning aids
+  static const int force_r = getenv("DMVS_WS2_R") ? atoi(getenv("DMVS_WS2_R")) : 0;
+  static const int force_nb = getenv("DMVS_WS2_NB") ? atoi(getenv("DMVS_WS2_NB")) : 0;
+  const int nchunks = cin_pad >> 3;
+  const size_t smem_limit = 224 * 1024;
+  const int max_blk = 256 / N;
+  const size_t wslab_f = (size_t)KHe * 2 * N * 4;
+  for (int th = 32; th >= 1; th >>= 1) {
+    if (th > 1 && th / 2 >= d.Ho) continue;          // a shorter tile already covers the image height
+    if (force_th && th != force_th) continue;
+    for (int nb = max_blk; nb >= 1; --nb) {
+      if (force_nb && nb != force_nb) continue;
+      const int cols_max = nb * 128 / th;            // in_cols such that th*in_cols <= nb*128
+      int tw_max = cols_max - (KWe - 1);
+      if (tw_max > 250) tw_max = 250;
+      if (tw_max * S + (KWe - 1) * S > 256) tw_max = 256 / S - (KWe - 1);   // TMA box limit
+      if (tw_max < 1 || (tw_max < 8 && tw_max < d.Wo)) continue;
+      const int ntx = ceil_div(d.Wo, tw_max);
+      const int TW = ceil_div(d.Wo, ntx);
+      const int in_cols = TW + KWe - 1;
+      const int in_rows = th + KHe - 1;
+      if (in_rows * S > 256) continue;
+      const int n_blk = ceil_div(th * in_cols, 128);
+      if (n_blk > max_blk) continue;
+      const int plane = (n_blk * 128 + (KHe - 1) * in_cols + 8 + 7) & ~7;
+      const size_t stage_f = (size_t)2 * plane * 4;
+      const size_t halo_f = ((size_t)n_blk * (CC / 8) * 4 * (KWe - 1) * (KWe - 1) * 8 + 31) & ~(size_t)31;
+      for (int r = kMaxRing; r >= 2; --r) {
+        if (force_r && r != force_r) continue;
+        const size_t need = (r * (2 * stage_f + 2 * wslab_f) + 2 * halo_f + 2 * (size_t)d.C1 + 64) * 4;
+        if (need > smem_limit) continue;
+        const int stages = nchunks * d.KD * S * S;
+        const double rows_per_stage = (double)d.KH / S;                      // kernel rows per phase (average)
+        const double mma_n = (double)n_blk * rows_per_stage * 3.0;          // MMAs per stage
+        const double mma_clk = mma_n * (N / 2 > 32 ? N / 2 : 32);
+        const double port_clk = mma_n * (4096.0 + 32.0 * N) / 128.0          // A and B operand reads
+                                + 2.0 * in_rows * in_cols * (64.0 + 16.0) / 128.0   // split (16 read + 32 written) + TMA write
+                                + 2.0 * wslab_f * 4.0 / 128.0;
+        const double split_issue = 2.0 * in_rows * in_cols * (d.in_stats ? 60.0 : 26.0) / 32.0 / 4.0;   // 8 warps on 4 schedulers
+        double stage_clk = mma_clk > port_clk ? mma_clk : port_clk;
+        if (split_issue > stage_clk) stage_clk = split_issue;
+        const double fill = r >= 4 ? 0.0 : (r == 3 ? 150.0 : 700.0);        // exposed load latency per stage when the ring is shallow
+        const double epi = (double)n_blk * (CC / 8) * (60.0 + 37.0 * KWe) * 2.0 + 300.0;   // 4 epilogue warps, overlapped
+        double tile = stages * (stage_clk + fill + 60.0);
+        if (epi > tile) tile = epi;
+        tile += 250.0;
+        const long tiles = (long)ntx * ceil_div(d.Ho, th) * d.N * d.Do;
+        const double waves = (double)ceil_div64(tiles, (int64_t)kNumSMs);
+        const double est = waves * tile;
+        if (est < best.est) {
+          best.TH = th; best.TW = TW; best.in_cols = in_cols; best.n_blk = n_blk; best.plane = plane; best.R = r;
+          best.halo_f = (int)halo_f; best.smem = need; best.est = est;
+        }
+        break;   // shallower rings of the same shape are never better
+      }
+    }
+  }
+}
+
+}  // namespace
+
+bool conv_ws2_supported(const dmvs_conv_desc& d) {
+  if (!conv_ws_supported(d)) return false;
+  if (d.in_up2) return false;                                  // a TMA box cannot replicate pixels
+  if (d.precision == DMVS_PREC_WS_TF32) return false;          // the single-pass mode stays on conv_ws.cu
+  if ((d.x_ps % 4) != 0 || (d.C2 > 0 && (d.x2_ps % 4) != 0)) return false;
+  return true;
+}
+
+int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out, int plan_cap) {
+  if (!conv_ws2_supported(d)) return DMVS_ERR_UNSUPPORTED;
+  if (!aligned16(d.w_ws)) return DMVS_ERR_ALIGN;
+  Ws2Args a;
+  a.d = d;
+  a.cin_pad = (d.C1 + d.C2 + 7) & ~7;
+  a.vec_y = aligned16(d.y) && (d.y_ps % 4 == 0);
+  a.vec_res = d.res != nullptr && aligned16(d.res) && (d.res_ps % 4 == 0);
+  a.vec_bias = d.bias != nullptr && aligned16(d.bias);
+  a.S = d.stride;
+  ws_extent(d.KH, d.pad_h, d.stride, &a.smin_h, &a.KHe);
+  ws_extent(d.KW, d.pad_w, d.stride, &a.smin_w, &a.KWe);
+  const int cc_max = ws_cc_max(a.KWe);
+  if (cc_max < 8) return DMVS_ERR_UNSUPPORTED;
+  int remaining = (d.Cout + 7) & ~7, co_base = 0;
+  int64_t w_off = 0;
+  int n_launch = 0;
+  while (remaining > 0) {
+    const int CC = remaining < cc_max ? remaining : cc_max;
+    const int N = (a.KWe * CC + 15) & ~15;
+    TileCfg2 t;
+    choose_tile2(d, a.S, a.KHe, a.KWe, N, CC, a.cin_pad, t);
+    if (!t.TH) return DMVS_ERR_UNSUPPORTED;
+    a.co_base = co_base;
+    a.CC = CC;
+    a.N = N;
+    a.TH = t.TH;
+    a.TW = t.TW;
+    a.in_rows = t.TH + a.KHe - 1;
+    a.in_cols = t.in_cols;
+    a.plane = t.plane;
+    a.box_units = a.in_rows * a.in_cols;
+    a.n_blk = t.n_blk;
+    a.acc_cols = t.n_blk * N;
+    a.R = t.R;
+    a.stage_f = 2 * t.plane * 4;
+    a.wslab_f = a.KHe * 2 * N * 4;
+    a.halo_f = t.halo_f;
+    a.inv_in_cols = 1.0f / (float)t.in_cols;
+    // packed slabs of this chunk: [hi | lo][KD][S*S phases][cin_pad/8][KHe][2][N][4]
+    const int64_t plane_w = (int64_t)d.KD * a.S * a.S * (a.cin_pad >> 3) * a.KHe * 2 * N * 4;
+    a.w_off = w_off;
+    a.w_plane = plane_w;
+    int cols = 32;
+    while (cols < 2 * a.acc_cols) cols <<= 1;
+    a.tmem_cols = cols;
+    a.tiles_x = ceil_div(d.Wo, t.TW);
+    a.tiles_y = ceil_div(d.Ho, t.TH);
+    const long tiles = (long)a.tiles_x * a.tiles_y * d.N * d.Do;
+    if (tiles > 0x7fffffffL) return DMVS_ERR_UNSUPPORTED;
+    a.total_tiles = (int)tiles;
+    const int grid = (int)(tiles < (long)kNumSMs ? tiles : (long)kNumSMs);
+    if (plan_out != nullptr) {
+      if (n_launch < plan_cap) {
+        int32_t* o = plan_out + 8 * n_launch;
+        o[0] = CC; o[1] = N; o[2] = t.TH; o[3] = t.TW; o[4] = t.n_blk; o[5] = t.R; o[6] = 1; o[7] = (int32_t)t.smem;
+      }
+    } else {
+      const int Hs = d.H, Ws = d.W;
+      if (tensor_map_encoder() == nullptr) return DMVS_ERR_UNSUPPORTED;
+      if (!make_activation_map(&a.map_x, d.x, d.C1, d.x_ps, Ws, Hs, d.D, d.N, 4, a.in_cols, a.in_rows, a.S)) return DMVS_ERR_UNSUPPORTED;
+      if (d.C2 > 0) {
+        if (!make_activation_map(&a.map_x2, d.x2, d.C2, d.x2_ps, Ws, Hs, d.D, d.N, 4, a.in_cols, a.in_rows, a.S))
+          return DMVS_ERR_UNSUPPORTED;
+      } else {
+        a.map_x2 = a.map_x;
+      }
+      KernelFn fn = d.in_stats != nullptr ? get_kernel<true>() : get_kernel<false>();
+      fn<<<grid, kWs2Threads, t.smem, st>>>(a);
+      const int rc = launch_status();
+      if (rc) return rc;
+    }
+    ++n_launch;
+    co_base += CC;
+    remaining -= CC;
+    w_off += 2 * plane_w;
+  }
+  return plan_out != nullptr ? n_launch : 0;
+}
+
+int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st) { return dispatch_conv_ws2(d, st, nullptr, 0); }
+int plan_conv_ws2(const dmvs_conv_desc& d, int32_t* out, int cap) { return dispatch_conv_ws2(d, nullptr, out, cap); }
+
+}  // namespace dmvs

@@ -51,6 +51,55 @@ __device__ __forceinline__ float remap_linear(const float* __restrict__ src, int
   return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1)), __fmul_rn(c, w2)), __fmul_rn(d, w3));
 }
 
+// One (reference pixel, source view) pair of check_geometric_consistency (filter.py:8-87): reprojected depth, the
+// float64 pixel distance and the float32 relative depth difference the thresholds are applied to, and the source
+// pixel coordinates.  Shared by the per-pair kernel and the fused per-view kernel.
+struct Reproj {
+  float drep;      // depth_reproj (before masking)
+  double dist;     // sqrt((x2d_reproj - x)^2 + (y2d_reproj - y)^2), float64 as numpy promotes float32 - int64
+  float rel;       // |depth_reproj - depth_ref| / depth_ref, float32
+  float xs, ys;    // x2d_src, y2d_src
+};
+
+__device__ __forceinline__ Reproj reproject_pixel(const GeoMats& m, const float* __restrict__ depth_src, int Hs, int Ws, int x, int y,
+                                                  float dref_f) {
+  const double dref = (double)dref_f;
+  // reference pixel -> reference camera -> source camera -> source pixel            (filter.py:19-31)
+  double rx, ry, rz;
+  mat3(m.Kref_inv, (double)x * dref, (double)y * dref, dref, rx, ry, rz);
+  double sx, sy, sz;
+  mat4_rows3(m.T_rs, rx, ry, rz, sx, sy, sz);
+  double kx, ky, kz;
+  mat3(m.Ksrc, sx, sy, sz, kx, ky, kz);
+  const double u = kx / kz, v = ky / kz;
+  Reproj r;
+  r.xs = (float)u;
+  r.ys = (float)v;
+  const float sampled = remap_linear(depth_src, Hs, Ws, r.xs, r.ys);                 // :32-33
+  // source pixel with the sampled depth -> back to the reference                     (:35-47)
+  const double sd = (double)sampled;
+  double qx, qy, qz;
+  mat3(m.Ksrc_inv, u * sd, v * sd, sd, qx, qy, qz);
+  double px, py, pz;
+  mat4_rows3(m.T_sr, qx, qy, qz, px, py, pz);
+  r.drep = (float)pz;
+  double ex, ey, ez;
+  mat3(m.Kref, px, py, pz, ex, ey, ez);
+  if (ex == 0.0) ex = 1e-5;
+  if (ey == 0.0) ey = 1e-5;
+  if (ez == 0.0) ez = 1e-5;
+  double xr = ex / ez, yr = ey / ez;
+  xr = fmin(fmax(xr, -1e8), 1e8);   // np.clip keeps NaN; fmin/fmax would drop it - NaN fails the threshold either way
+  yr = fmin(fmax(yr, -1e8), 1e8);
+  const float xr_f = (float)xr, yr_f = (float)yr;
+  // consistency measures                                                             (:75-79)
+  const double ddx = (double)xr_f - (double)x, ddy = (double)yr_f - (double)y;
+  r.dist = sqrt(ddx * ddx + ddy * ddy);
+  const float depth_diff = fabsf(__fsub_rn(r.drep, dref_f));
+  r.rel = __fdiv_rn(depth_diff, dref_f);
+  return r;
+}
+
 __global__ void geo_consistency_kernel(const float* __restrict__ depth_ref, const float* __restrict__ depth_src,
                                        const GeoMats m, float dmin, float dmax, double pix_thres, float depth_thres,
                                        uint8_t* __restrict__ mask, float* __restrict__ depth_reproj,
@@ -61,44 +110,14 @@ __global__ void geo_consistency_kernel(const float* __restrict__ depth_ref, cons
   if (i >= (int64_t)H * W) return;
   const int x = (int)(i % W), y = (int)(i / W);
   const float dref_f = __ldg(depth_ref + i);
-  const double dref = (double)dref_f;
-  // reference pixel -> reference camera -> source camera -> source pixel            (filter.py:19-31)
-  double rx, ry, rz;
-  mat3(m.Kref_inv, (double)x * dref, (double)y * dref, dref, rx, ry, rz);
-  double sx, sy, sz;
-  mat4_rows3(m.T_rs, rx, ry, rz, sx, sy, sz);
-  double kx, ky, kz;
-  mat3(m.Ksrc, sx, sy, sz, kx, ky, kz);
-  const double u = kx / kz, v = ky / kz;
-  const float xs = (float)u, ys = (float)v;
-  const float sampled = remap_linear(depth_src, Hs, Ws, xs, ys);                     // :32-33
-  // source pixel with the sampled depth -> back to the reference                     (:35-47)
-  const double sd = (double)sampled;
-  double qx, qy, qz;
-  mat3(m.Ksrc_inv, u * sd, v * sd, sd, qx, qy, qz);
-  double px, py, pz;
-  mat4_rows3(m.T_sr, qx, qy, qz, px, py, pz);
-  float drep = (float)pz;
-  double ex, ey, ez;
-  mat3(m.Kref, px, py, pz, ex, ey, ez);
-  if (ex == 0.0) ex = 1e-5;
-  if (ey == 0.0) ey = 1e-5;
-  if (ez == 0.0) ez = 1e-5;
-  double xr = ex / ez, yr = ey / ez;
-  xr = fmin(fmax(xr, -1e8), 1e8);   // np.clip keeps NaN; fmin/fmax would drop it - NaN fails the threshold either way
-  yr = fmin(fmax(yr, -1e8), 1e8);
-  const float xr_f = (float)xr, yr_f = (float)yr;
-  // consistency                                                                      (:75-86)
-  const double ddx = (double)xr_f - (double)x, ddy = (double)yr_f - (double)y;
-  const double dist = sqrt(ddx * ddx + ddy * ddy);
-  const float depth_diff = fabsf(__fsub_rn(drep, dref_f));
-  const float rel = __fdiv_rn(depth_diff, dref_f);
-  const bool ok = dist < pix_thres && rel < depth_thres && dref_f > dmin && dref_f < dmax;
+  const Reproj r = reproject_pixel(m, depth_src, Hs, Ws, x, y, dref_f);
+  float drep = r.drep;
+  const bool ok = r.dist < pix_thres && r.rel < depth_thres && dref_f > dmin && dref_f < dmax;   // :80-86
   if (!ok) drep = 0.0f;
   mask[i] = ok ? 1 : 0;
   depth_reproj[i] = drep;
-  if (x_src_out) x_src_out[i] = xs;
-  if (y_src_out) y_src_out[i] = ys;
+  if (x_src_out) x_src_out[i] = r.xs;
+  if (y_src_out) y_src_out[i] = r.ys;
   if (sum_reproj) sum_reproj[i] = __fadd_rn(sum_reproj[i], drep);   // sum(all_srcview_depth_ests), in view order
   if (count) count[i] += ok ? 1 : 0;
 }
@@ -131,6 +150,106 @@ __global__ void fuse_kernel(const float* __restrict__ depth_ref, const float* __
   xyz[i * 3 + 0] = (float)wx;
   xyz[i * 3 + 1] = (float)wy;
   xyz[i * 3 + 2] = (float)wz;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One launch per reference view: photometric mask, geometric consistency against EVERY source view (static thresholds,
+// filter.py:117-191, or the nine dynamic threshold pairs of the Tanks & Temples variant, :230-262,311-392), averaged
+// depth, geometric / final masks and the world-space point of every pixel.  The reference re-reads each source depth
+// map from disk and makes ~40 numpy passes per pair; here a thread owns a pixel, the source maps are gathered once
+// (4 taps each) and nothing intermediate is written.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxSrc = 16;
+constexpr int kDynLevels = 11;   // thresholds i / dh_dist, i / dh_rel_diff for i = dh_view_num .. 10
+
+struct FuseViewArgs {
+  const float* depth_ref;            // [H][W]
+  const float* depth_src[kMaxSrc];   // [Hs][Ws] each
+  const double* mats;                // [S][68] (device): GeoMats of every (reference, source) pair
+  int S, H, W, Hs, Ws;
+  const float* conf[3];
+  float photo_thres[3];
+  int n_conf;
+  FuseMats fm;
+  // static mode
+  float dmin, dmax;                  // check_geometric_consistency's range test on depth_ref (float32 compare)
+  double pix_thres;
+  float depth_thres;
+  int geo_thres;
+  // dynamic mode
+  int dyn_view_num;                  // 0: static mode
+  double dyn_pix[kDynLevels];        // i / dh_dist        (float64 compare with the float64 distance)
+  float dyn_rel[kDynLevels];         // i / dh_rel_diff    (float32 compare, NumPy's weak-scalar rule)
+  double avg_min, avg_max;           // dynamic mode: final mask also needs depth_min <= averaged depth <= depth_max
+  uint8_t* photo_mask;
+  uint8_t* geo_mask;
+  uint8_t* final_mask;
+  double* depth_avg;
+  float* xyz;
+};
+
+template <bool DYN>
+__global__ void __launch_bounds__(256) fuse_view_kernel(const __grid_constant__ FuseViewArgs a) {
+  __shared__ GeoMats mats_s[kMaxSrc];
+  {
+    double* dst = reinterpret_cast<double*>(mats_s);
+    for (int k = threadIdx.x; k < a.S * 68; k += blockDim.x) dst[k] = a.mats[k];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)a.H * a.W) return;
+  const int x = (int)(i % a.W), y = (int)(i / a.W);
+  const float dref_f = __ldg(a.depth_ref + i);
+  bool photo = true;
+  for (int c = 0; c < a.n_conf; ++c) photo = photo && (__ldg(a.conf[c] + i) > a.photo_thres[c]);
+  float sum = 0.0f;                  // python's sum(list): ((0 + d_0) + d_1) + ... in float32
+  int cnt = 0;                       // geo_mask_sum (static) / geo_mask_sum of the loosest test (dynamic)
+  int lvl[kDynLevels];
+#pragma unroll
+  for (int k = 0; k < kDynLevels; ++k) lvl[k] = 0;
+  for (int s = 0; s < a.S; ++s) {
+    const Reproj r = reproject_pixel(mats_s[s], a.depth_src[s], a.Hs, a.Ws, x, y, dref_f);
+    bool ok;
+    if (DYN) {
+      ok = false;
+#pragma unroll
+      for (int k = 0; k < kDynLevels; ++k) {
+        if (k >= a.dyn_view_num) {
+          const bool m = r.dist < a.dyn_pix[k] && r.rel < a.dyn_rel[k];
+          lvl[k] += m ? 1 : 0;
+          if (k == kDynLevels - 1) ok = m;     // depth_reproj is masked with the last (i = 10) test, filter.py:260
+        }
+      }
+    } else {
+      ok = r.dist < a.pix_thres && r.rel < a.depth_thres && dref_f > a.dmin && dref_f < a.dmax;
+    }
+    sum = __fadd_rn(sum, ok ? r.drep : 0.0f);
+    cnt += ok ? 1 : 0;
+  }
+  // (sum(depth_reproj) + ref_depth) / (geo_mask_sum + 1): float32 sum, float64 quotient      (filter.py:189, :383)
+  const double avg = (double)__fadd_rn(sum, dref_f) / (double)(cnt + 1);
+  bool geo;
+  if (DYN) {
+    geo = cnt >= 10;
+#pragma unroll
+    for (int k = 0; k < kDynLevels; ++k)
+      if (k >= a.dyn_view_num) geo = geo || lvl[k] >= k;
+  } else {
+    geo = cnt >= a.geo_thres;
+  }
+  bool fin = photo && geo;
+  if (DYN) fin = fin && avg >= a.avg_min && avg <= a.avg_max;
+  a.photo_mask[i] = photo ? 1 : 0;
+  a.geo_mask[i] = geo ? 1 : 0;
+  a.final_mask[i] = fin ? 1 : 0;
+  a.depth_avg[i] = avg;
+  double cx, cy, cz;
+  mat3(a.fm.Kref_inv, (double)x * avg, (double)y * avg, avg, cx, cy, cz);
+  double wx, wy, wz;
+  mat4_rows3(a.fm.Eref_inv, cx, cy, cz, wx, wy, wz);
+  a.xyz[i * 3 + 0] = (float)wx;
+  a.xyz[i * 3 + 1] = (float)wy;
+  a.xyz[i * 3 + 2] = (float)wz;
 }
 
 }  // namespace
@@ -171,5 +290,51 @@ extern "C" int dmvs_fuse_points(const float* depth_ref, const float* sum_reproj,
   const int64_t total = (int64_t)H * W;
   fuse_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       depth_ref, sum_reproj, count, photo_mask, geo_thres, m, depth_avg, geo_mask, final_mask, xyz, H, W);
+  return launch_status();
+}
+
+extern "C" int dmvs_fuse_view(const float* depth_ref, const float* const* depth_src, const double* mats_dev, int32_t S, int32_t H,
+                              int32_t W, int32_t Hs, int32_t Ws, const float* const* conf, const float* photo_thres,
+                              int32_t n_conf, const double* mats25, float depth_min, float depth_max, double pix_thres,
+                              float depth_thres, int32_t geo_thres, int32_t dyn_view_num, double dyn_dist, double dyn_rel,
+                              double avg_min, double avg_max, uint8_t* photo_mask, uint8_t* geo_mask, uint8_t* final_mask,
+                              double* depth_avg, float* xyz, void* stream) {
+  if (!depth_ref || !depth_src || !mats_dev || !mats25 || !photo_mask || !geo_mask || !final_mask || !depth_avg || !xyz)
+    return DMVS_ERR_ARG;
+  if (S < 0 || S > kMaxSrc || H <= 0 || W <= 0 || Hs <= 0 || Ws <= 0 || n_conf < 0 || n_conf > 3) return DMVS_ERR_ARG;
+  if (dyn_view_num < 0 || dyn_view_num >= kDynLevels) return DMVS_ERR_ARG;
+  if (n_conf > 0 && (!conf || !photo_thres)) return DMVS_ERR_ARG;
+  FuseViewArgs a = {};
+  a.depth_ref = depth_ref;
+  for (int s = 0; s < S; ++s) {
+    if (!depth_src[s]) return DMVS_ERR_ARG;
+    a.depth_src[s] = depth_src[s];
+  }
+  a.mats = mats_dev;
+  a.S = S; a.H = H; a.W = W; a.Hs = Hs; a.Ws = Ws;
+  a.n_conf = n_conf;
+  for (int c = 0; c < n_conf; ++c) {
+    if (!conf[c]) return DMVS_ERR_ARG;
+    a.conf[c] = conf[c];
+    a.photo_thres[c] = photo_thres[c];
+  }
+  const double* p = mats25;
+  for (int k = 0; k < 9; ++k) a.fm.Kref_inv[k] = *p++;
+  for (int k = 0; k < 16; ++k) a.fm.Eref_inv[k] = *p++;
+  a.dmin = depth_min; a.dmax = depth_max; a.pix_thres = pix_thres; a.depth_thres = depth_thres; a.geo_thres = geo_thres;
+  a.dyn_view_num = dyn_view_num;
+  for (int k = 0; k < kDynLevels; ++k) {
+    a.dyn_pix[k] = dyn_dist > 0 ? (double)k / dyn_dist : 0.0;
+    a.dyn_rel[k] = dyn_rel > 0 ? (float)((double)k / dyn_rel) : 0.0f;
+  }
+  a.avg_min = avg_min; a.avg_max = avg_max;
+  a.photo_mask = photo_mask; a.geo_mask = geo_mask; a.final_mask = final_mask; a.depth_avg = depth_avg; a.xyz = xyz;
+  const int64_t total = (int64_t)H * W;
+  const unsigned grid = (unsigned)ceil_div64(total, 256);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dyn_dist > 0)
+    fuse_view_kernel<true><<<grid, 256, 0, st>>>(a);
+  else
+    fuse_view_kernel<false><<<grid, 256, 0, st>>>(a);
   return launch_status();
 }

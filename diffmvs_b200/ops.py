@@ -17,6 +17,7 @@ import os
 
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
                     PREC_AUTO, PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, PREC_WS_TF32, PREC_WS_TF32X3,
+                    PREC_WS2_TF32X3,
                     RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
 # Arithmetic of the convolutions (storage is always fp32).  fp32-class modes (parity-safe, <= 4e-6 depth rel-L1):
@@ -27,7 +28,8 @@ from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU
 # Plain-TF32 modes (NOT parity-safe on the synthetic weights: 1e-3..3e-3 depth rel-L1, 2-6 % index flips):
 #   "tf32", "tc_tf32"  operands rounded to TF32 - the numerics cuDNN uses under torch defaults
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
-              "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO, "ws_tf32x3": PREC_WS_TF32X3, "ws_tf32": PREC_WS_TF32}
+              "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO, "ws_tf32x3": PREC_WS_TF32X3, "ws_tf32": PREC_WS_TF32,
+              "ws2_tf32x3": PREC_WS2_TF32X3}
 _precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "auto")]
 
 
@@ -47,7 +49,7 @@ def set_precision(name: str) -> None:
 _AUTOTUNE = os.environ.get("DMVS_AUTOTUNE", "1") != "0"
 _AUTOTUNE_WS = os.environ.get("DMVS_AUTO_WS", "1") != "0"
 _TUNED: dict = {}
-_BACKEND_BITS = ((1, PREC_FP32), (4, PREC_TC_TF32X3), (8, PREC_WS_TF32X3))
+_BACKEND_BITS = ((1, PREC_FP32), (4, PREC_TC_TF32X3), (8, PREC_WS_TF32X3), (16, PREC_WS2_TF32X3))
 
 
 def set_autotune(enabled: bool, use_ws: Optional[bool] = None) -> None:
@@ -338,8 +340,8 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
     d.w_t, d.w_tc, d.w_ws = _ptr(pc.w_t), _ptr(pc.w_tc), _ptr(pc.ws_slabs(stride, ph, pw))
     d.precision = _precision if pc.w_t is not None else PREC_FP32
-    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32) and pc.w_tc is None:
-        d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3) else PREC_TF32
+    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3) and pc.w_tc is None:
+        d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3, PREC_WS2_TF32X3) else PREC_TF32
     d.KD, d.KH, d.KW, d.stride = KD, KH, KW, stride
     d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
     d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 2
+#define DMVS_ABI_VERSION 3
 
 #define DMVS_ERR_ARG (-1)      /* null pointer / non-positive size / unsupported combination */
 #define DMVS_ERR_ALIGN (-2)    /* pointer or stride not aligned as documented */
@@ -52,6 +52,9 @@ extern "C" {
 #define DMVS_PREC_TC_TF32 4   /* as TF32 on the tcgen05/TMEM back end (stride-1 layers; others fall back to 2) */
 #define DMVS_PREC_WS_TF32X3 6 /* 3xTF32 on the width-stacked tcgen05 back end (conv_ws.cu) wherever it applies, FFMA elsewhere */
 #define DMVS_PREC_WS_TF32 7   /* plain TF32 on the width-stacked tcgen05 back end, legacy TF32 elsewhere */
+#define DMVS_PREC_WS2_TF32X3 8 /* 3xTF32, width-stacked tcgen05 arithmetic behind the TMA-fed pipeline (conv_ws2.cu): one
+                                  persistent CTA per SM, cp.async.bulk.tensor producer, split / MMA / epilogue warps, two
+                                  TMEM accumulator sets; conv_ws.cu for nearest-upsampled inputs, FFMA elsewhere */
 
 /* epilogue kinds */
 #define DMVS_EPI_STD 0
@@ -121,7 +124,7 @@ typedef struct dmvs_conv_desc {
 int dmvs_conv_f32(const dmvs_conv_desc* desc, void* stream);
 
 /* Which arithmetic back ends can run `desc` (bit 0: FFMA, bit 1: mma.sync, bit 2: tcgen05 with taps as descriptor
- * offsets, bit 3: tcgen05 width-stacked).  Used by the host-side per-layer autotuner (the counterpart of the
+ * offsets, bit 3: tcgen05 width-stacked, bit 4: tcgen05 width-stacked behind the TMA pipeline).  Used by the host-side per-layer autotuner (the counterpart of the
  * reference's `cudnn.benchmark = True`, test.py:18).  Launches nothing. */
 int dmvs_conv_backends(const dmvs_conv_desc* desc);
 
@@ -129,6 +132,8 @@ int dmvs_conv_backends(const dmvs_conv_desc* desc);
  * eight ints {CC, N, TH, TW, M blocks, ring depth, CTAs per SM, shared-memory bytes} are written to out (capacity
  * `cap` launches).  Returns the number of launches or DMVS_ERR_*.  Pointers in `desc` are only checked for alignment. */
 int dmvs_conv_ws_plan(const dmvs_conv_desc* desc, int32_t* out, int32_t cap);
+/* Same for the TMA-fed width-stacked back end (CTAs per SM is always 1). */
+int dmvs_conv_ws2_plan(const dmvs_conv_desc* desc, int32_t* out, int32_t cap);
 
 /* ConvTranspose3d(k=3, s=2, p=1, output_padding=1) + folded BN + ReLU + skip add
  * (module.Deconv3d as used by CostRegNet_small, module.py:110-144,436-437,445-446).
@@ -247,6 +252,22 @@ int dmvs_geo_consistency(const float* depth_ref, const float* depth_src, const d
 int dmvs_fuse_points(const float* depth_ref, const float* sum_reproj, const int32_t* count, const uint8_t* photo_mask,
                      int32_t geo_thres, const double* mats25, double* depth_avg, uint8_t* geo_mask, uint8_t* final_mask,
                      float* xyz, int32_t H, int32_t W, void* stream);
+
+/* One reference view of filter_depth (filter.py:117-212) or, when dyn_dist > 0, of filter_depth_dynamic (:230-262,
+ * 311-412) in ONE launch: photometric mask (conf[c] > photo_thres[c], float32), geometric consistency against all S
+ * source views (S <= 16), averaged depth, geometric / final masks and the world point of every pixel.
+ * depth_src: host array of S device pointers ([Hs][Ws] maps); mats_dev: DEVICE array [S][68] doubles, one mats68 block
+ * (see dmvs_geo_consistency) per source view; conf / photo_thres: host arrays of n_conf (<= 3) device pointers / floats.
+ * Static mode: pix_thres (float64 compare), depth_thres (float32), depth_min/max (float32 range test on depth_ref),
+ * geo_thres.  Dynamic mode: tests i/dyn_dist (float64) and i/dyn_rel (rounded to float32) for i = dyn_view_num..10, a
+ * pixel passes when >= i source views pass test i for some i; the final mask also requires avg_min <= averaged depth
+ * <= avg_max (float64).  Outputs as dmvs_fuse_points plus the photometric mask. */
+int dmvs_fuse_view(const float* depth_ref, const float* const* depth_src, const double* mats_dev, int32_t S, int32_t H,
+                   int32_t W, int32_t Hs, int32_t Ws, const float* const* conf, const float* photo_thres, int32_t n_conf,
+                   const double* mats25, float depth_min, float depth_max, double pix_thres, float depth_thres,
+                   int32_t geo_thres, int32_t dyn_view_num, double dyn_dist, double dyn_rel, double avg_min,
+                   double avg_max, uint8_t* photo_mask, uint8_t* geo_mask, uint8_t* final_mask, double* depth_avg,
+                   float* xyz, void* stream);
 
 #ifdef __cplusplus
 }

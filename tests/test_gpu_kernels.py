@@ -33,10 +33,10 @@ def _nchw(y):  # GPU [N,H,W,C] -> CPU NCHW
 
 
 PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3, "tc_tf32x3": 2e-5, "tc_tf32": 3e-3, "auto": 2e-5,
-            "ws_tf32x3": 2e-5, "ws_tf32": 3e-3}   # max-abs error relative to the output scale
+            "ws_tf32x3": 2e-5, "ws_tf32": 3e-3, "ws2_tf32x3": 2e-5}   # max-abs error relative to the output scale
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32", "tc_tf32x3", "tc_tf32", "auto", "ws_tf32x3", "ws_tf32"])
+@pytest.fixture(params=["fp32", "tf32x3", "tf32", "tc_tf32x3", "tc_tf32", "auto", "ws_tf32x3", "ws_tf32", "ws2_tf32x3"])
 def precision(request):
     old = ops.get_precision()
     ops.set_precision(request.param)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert sorted(_cabi.SIGNATURES) == declared, "ctypes table and header disagree"
     lib = _cabi.lib()
-    assert lib.dmvs_abi_version() == 2
+    assert lib.dmvs_abi_version() == _cabi.ABI_VERSION
     assert b"sm_100a" in lib.dmvs_build_info()
 
 

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from diffmvs_b200 import _cabi
 
-def plan(N, cin, cout, k, stride, dims, gn=False, passes3=True):
+def plan(N, cin, cout, k, stride, dims, gn=False, passes3=True, gen=1):
     d = _cabi.ConvDesc()
     D, H, W = dims
     kd, kh, kw = k
@@ -19,7 +19,8 @@ def plan(N, cin, cout, k, stride, dims, gn=False, passes3=True):
     if gn:
         d.in_stats, d.in_g1, d.in_g0 = 0x1000, 0x1000, 0x1000
     out = (C.c_int32 * 64)()
-    n = _cabi.lib().dmvs_conv_ws_plan(C.byref(d), out, 8)
+    fn = _cabi.lib().dmvs_conv_ws_plan if gen == 1 else _cabi.lib().dmvs_conv_ws2_plan
+    n = fn(C.byref(d), out, 8)
     return [tuple(out[8 * i:8 * i + 8]) for i in range(max(n, 0))], n
 
 if __name__ == "__main__":
@@ -35,7 +36,11 @@ if __name__ == "__main__":
         ("unet3.rb 8->8", 1, 8, 8, (1, 3, 3), 1, (1, 576, 800)),
         ("unet 32->32 @1/8", 1, 32, 32, (1, 3, 3), 1, (1, 144, 200)),
         ("pvw 4->8 3d", 6, 4, 8, (3, 3, 3), 1, (48, 144, 200)),
+        ("feat.inner2 16->64 1x1", 7, 16, 64, (1, 1, 1), 1, (1, 576, 800)),
+        ("feat.conv2.0 16->32 5x5s2", 7, 16, 32, (1, 5, 5), 2, (1, 576, 800)),
+        ("enc3 16->16", 1, 16, 16, (1, 3, 3), 1, (1, 576, 800)),
+        ("gru 64->64 1x5", 1, 64, 64, (1, 1, 5), 1, (1, 144, 200)),
     ]
     print("layer: per launch (CC, N, TH, TW, n_blk, R, ctas, smem)")
     for name, N, cin, cout, k, s, dims in LAYERS:
-        print(f"{name:28s}", plan(N, cin, cout, k, s, dims))
+        print(f"{name:28s}", plan(N, cin, cout, k, s, dims), " ws2:", plan(N, cin, cout, k, s, dims, gen=2)[0])
