@@ -13,7 +13,7 @@ from __future__ import annotations
 import os
 import re
 import sys
-from typing import Dict, List, Sequence, Tuple
+from typing import Optional, Dict, List, Sequence, Tuple
 
 import numpy as np
 
@@ -239,16 +239,35 @@ def load_sample(datapath: str, scan: str, ref_view: int, src_views: Sequence[int
     return sample
 
 
+def save_mask(filename: str, mask: np.ndarray) -> None:
+    """Boolean mask -> 8-bit PNG with 0 / 255 (data_io.py:161-164)."""
+    from PIL import Image
+    if mask.dtype != np.bool_:
+        raise ValueError("save_mask: boolean array expected")
+    Image.fromarray(mask.astype(np.uint8) * 255).save(filename)
+
+
 def save_outputs(outdir: str, filename: str, depth: np.ndarray, confs: Sequence[np.ndarray], cam: np.ndarray,
-                 depth_max, depth_min) -> None:
-    """Depth map, reference camera and confidence maps in the layout test.py:142-200 writes (what `filter.py`
-    consumes): `<outdir>/<scan>/depth_est/<id>.pfm`, `cams/<id>_cam.txt`, `conf<i>/<id>.pfm`."""
+                 depth_max, depth_min, img: Optional[np.ndarray] = None) -> None:
+    """Everything test.py:142-200 writes for one reference view, in the layout `filter.py` consumes:
+    `<outdir>/<scan>/depth_est/<id>.pfm`, `cams/<id>_cam.txt`, `conf<i>/<id>.pfm` and - when `img` ([3,H,W] RGB in
+    [0,1], the resized reference image the model saw) is given - `images/<id>.jpg` (test.py:160-162: clip(img*255) as
+    uint8, RGB -> BGR, `cv2.imwrite`), which `filter.py:113,316` reads for the point colours."""
     def path(kind, ext):
         p = os.path.join(outdir, filename.format(kind, ext))
         os.makedirs(p.rsplit("/", 1)[0], exist_ok=True)
         return p
     save_pfm(path("depth_est", ".pfm"), np.ascontiguousarray(depth, dtype=np.float32))
     write_cam(path("cams", "_cam.txt"), cam, depth_max, depth_min)
+    if img is not None:
+        import cv2
+        img = np.asarray(img)
+        if img.ndim != 3 or img.shape[0] != 3:
+            raise ValueError(f"save_outputs: img must be [3,H,W] (got {img.shape})")
+        if tuple(img.shape[1:]) != tuple(np.asarray(depth).shape[-2:]):
+            raise ValueError("save_outputs: image and depth map sizes differ (filter.py indexes one with the other's mask)")
+        u8 = np.clip(np.transpose(img, (1, 2, 0)) * 255, 0, 255).astype(np.uint8)
+        cv2.imwrite(path("images", ".jpg"), cv2.cvtColor(u8, cv2.COLOR_RGB2BGR))
     for i, c in enumerate(confs):
         save_pfm(path(f"conf{i}", ".pfm"), np.ascontiguousarray(c, dtype=np.float32))
 

@@ -82,3 +82,28 @@ def plane_scene(H=48, W=64, V=4, seed=0):
     confs = [rng.random((H, W), dtype=np.float32) for _ in range(3)]
     img = rng.random((H, W, 3), dtype=np.float32)
     return {"K": K, "E": Es, "depth": depths, "conf": confs, "img": img, "depth_min": 425.0, "depth_max": 935.0}
+
+
+def write_scan_dir(root: str, H=96, W=128, V=5, seed=4, n_conf=3):
+    """A tiny scan in the layout test.py:142-200 writes (through `scene_io.save_outputs`, image included) plus a
+    `pair.txt`: the plane scene above seen by V cameras, every view a reference with all others as sources.  Used by the
+    scan-level fusion tests and by `oracle/make_scan_golden.py` (which runs the REFERENCE's filter.py on it)."""
+    import os
+    import numpy as np
+    from diffmvs_b200 import scene_io
+    sc = plane_scene(H, W, V, seed)
+    rng = np.random.default_rng(100 + seed)
+    os.makedirs(root, exist_ok=True)
+    for v in range(V):
+        cam = np.zeros((2, 4, 4), dtype=np.float32)
+        cam[0] = sc["E"][v]
+        cam[1, :3, :3] = sc["K"]
+        confs = [rng.random((H, W), dtype=np.float32) for _ in range(n_conf)]
+        img = rng.random((3, H, W), dtype=np.float32)
+        scene_io.save_outputs(root, "{}/" + f"{v:0>8}" + "{}", sc["depth"][v], confs, cam, sc["depth_max"], sc["depth_min"], img=img)
+    with open(os.path.join(root, "pair.txt"), "w") as f:
+        f.write(f"{V}\n")
+        for v in range(V):
+            others = [u for u in range(V) if u != v]
+            f.write(f"{v}\n{len(others)} " + " ".join(f"{u} {100.0 - abs(u - v):.1f}" for u in others) + "\n")
+    return sc

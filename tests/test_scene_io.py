@@ -97,6 +97,37 @@ def test_save_outputs_layout_round_trips(tmp_path):
     assert np.array_equal(data_io.read_pfm(str(tmp_path / "scan1/conf2/00000007.pfm"))[0], confs[2])
     intr, ext, _, _ = data_io.read_camera_parameters(str(tmp_path / "scan1/cams/00000007_cam.txt"))
     assert np.array_equal(ext, cam[0]) and np.array_equal(intr, cam[1, :3, :3])
+    assert not (tmp_path / "scan1/images").exists()                       # no image given, none written
+
+
+def test_save_outputs_writes_the_reference_image(tmp_path):
+    """test.py:151-162 also writes the resized reference image to `images/<id>.jpg` (clip*255 as uint8, RGB -> BGR,
+    cv2.imwrite); filter.py:113,316 reads it with PIL for the point colours, so it must exist, have the depth map's
+    size and decode to the same RGB image the reference's own writer produces."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    img = rng.random((3, 32, 48), dtype=np.float32) * 1.2 - 0.1              # exercises the clip
+    depth = np.full((32, 48), 600.0, np.float32)
+    cam = np.load(os.path.join(G, "cam_params.npz"))["cam"]
+    data_io.save_outputs(str(tmp_path), "scan1/{}/00000003{}", depth, [depth * 0], cam, 935.0, 425.0, img=img)
+    path = str(tmp_path / "scan1/images/00000003.jpg")
+    back = data_io.read_img(path)                                          # PIL decode, [H,W,3] in [0,1]
+    assert back.shape == (32, 48, 3) and back.dtype == np.float32
+    # the reference's writer, verbatim arithmetic (test.py:160-162), on the same array
+    ref_path = str(tmp_path / "ref.jpg")
+    u8 = np.clip(np.transpose(img, (1, 2, 0)) * 255, 0, 255).astype(np.uint8)
+    cv2.imwrite(ref_path, cv2.cvtColor(u8, cv2.COLOR_RGB2BGR))
+    assert open(path, "rb").read() == open(ref_path, "rb").read()
+    with pytest.raises(ValueError):
+        data_io.save_outputs(str(tmp_path), "scan1/{}/00000004{}", depth, [], cam, 935.0, 425.0, img=img[:, :16])
+
+
+def test_written_scan_directory_is_what_the_reference_filter_reads(tmp_path):
+    """`oracle/make_scan_golden.py` ran the reference's `filter_depth` on a directory written by `save_outputs`; the
+    fixture it recorded exists and carries masks for every view (the GPU test compares against it)."""
+    g = np.load(os.path.join(os.path.dirname(G), "scan_fusion.npz"))
+    assert {f"cas_static_final_{v}" for v in range(5)} <= set(g.files)
+    assert g["cas_static_xyz"].shape[1] == 3 and len(g["cas_static_xyz"]) == len(g["cas_static_rgb"]) > 1000
 
 
 def test_ply_round_trip(tmp_path):
