@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant
   float* in_s = smem;
   float* w_s = in_s + a.in_rows * a.in_cols * a.CKP;
   float* gn_s = w_s + d.KH * d.KW * a.CK * COUT_S;   // [2][C1] when in_stats
-  __shared__ float stat_s[8];
+  __shared__ unsigned long long stat_s[8];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant
   const int iy0 = ty0 * S - d.pad_h;
   const int ix0 = tx0 * S - d.pad_w;
 
-  if (tid < 8) stat_s[tid] = 0.0f;
+  if (tid < 8) stat_s[tid] = 0ull;
   if (d.in_stats != nullptr) {
     for (int c = tid; c < d.C1; c += kThreads) groupnorm_affine(d, n, c, gn_s);
   }

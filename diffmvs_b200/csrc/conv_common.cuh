@@ -58,8 +58,8 @@ static __device__ __noinline__ float epilogue_value(const dmvs_conv_desc& d, flo
 // GroupNorm(4)+affine of the producer folded to a per-channel (scale, shift) pair for sample n.
 static __device__ __noinline__ void groupnorm_affine(const dmvs_conv_desc& d, int n, int c, float* gn_s) {
   const int g = c / (d.C1 / 4);
-  const double s = d.in_stats[(n * 4 + g) * 2 + 0];
-  const double q = d.in_stats[(n * 4 + g) * 2 + 1];
+  const double s = stat_value(d.in_stats[(n * 4 + g) * 2 + 0]);
+  const double q = stat_value(d.in_stats[(n * 4 + g) * 2 + 1]);
   const double mean = s * (double)d.in_inv_count;
   double var = q * (double)d.in_inv_count - mean * mean;
   var = var < 0.0 ? 0.0 : var;
@@ -126,7 +126,7 @@ __device__ __forceinline__ void stage_input_tile(const ConvArgs& a, float* in_s,
 // Fused epilogue over an output tile staged in shared memory as out_s[TH*32][COUT_S+4]: bias, residual,
 // activation / GRU blends, GroupNorm statistics, fully coalesced 128-bit stores.  All threads must call it.
 template <int TH, int COUT_S>
-__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* out_s, float* stat_s, int n, int od, int ty0,
+__device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* out_s, unsigned long long* stat_s, int n, int od, int ty0,
                                               int tx0) {
   constexpr int N4 = COUT_S / 4;
   constexpr int OP = COUT_S + 4;
@@ -198,8 +198,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* ou
     }
   }
   if (d.out_stats != nullptr) {
-    // lanes l, l+N4, l+2*N4, ... of a warp share a channel quad: fold them, then one shared atomic per
-    // (quad, element), then one double atomic per (group, moment) per CTA.
+    // lanes l, l+N4, l+2*N4, ... of a warp share a channel quad: fold them, then one shared integer atomic per
+    // (quad, element), then one global integer atomic per (group, moment) per CTA (fixed point: order independent).
     const int cpg = d.Cout / 4;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -212,12 +212,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvArgs& a, const float* ou
       const int c = cq + k;
       if (lane < N4 && c < d.Cout) {
         const int g = c / cpg;
-        atomicAdd(&stat_s[g * 2 + 0], s);
-        atomicAdd(&stat_s[g * 2 + 1], q);
+        atomicAdd(&stat_s[g * 2 + 0], stat_fixed(s));
+        atomicAdd(&stat_s[g * 2 + 1], stat_fixed(q));
       }
     }
     __syncthreads();
-    if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+    if (tid < 8) atomicAdd(reinterpret_cast<unsigned long long*>(d.out_stats) + n * 8 + tid, stat_s[tid]);
   }
 }
 

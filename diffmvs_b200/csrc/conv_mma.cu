@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const __grid_
   float* w_s0 = in_s0 + 2 * in_sz;                          // [2][KH*KW][COUT_S][CKP]
   float* out_s = w_s0 + 2 * w_sz;                           // [TH*32][OP]
   float* gn_s = out_s + TH * kTileW * OP;                   // [2][C1] when in_stats
-  __shared__ float stat_s[8];
+  __shared__ unsigned long long stat_s[8];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wc = warp % WC, wp = warp / WC;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kConvThreads, 2) conv_mma_kernel(const __grid_
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[p][mt][j][e] = 0.0f;
           }
-      if (tid < 8) stat_s[tid] = 0.0f;
+      if (tid < 8) stat_s[tid] = 0ull;
       __syncthreads();
       epilogue_tile<TH, COUT_S>(a, out_s, stat_s, n, od, ty0, tx0);
     }

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   float* gn_s = w_lo0 + (PASSES == 3 ? R * wslab_f : 0);      // [2][C1] when in_stats
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t mbar[2];   // stages alternate barriers: a parity wait may lag by one phase only
-  __shared__ float stat_s[8];
+  __shared__ unsigned long long stat_s[8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         float* out_s = pair0 + slot * a.stage_f;   // this stage's pair is dead now: [128][OP] staging
         int n, od, ty0, tx0;
         decode(cur.tile, n, od, ty0, tx0);
-        if (tid < 8) stat_s[tid] = 0.0f;
+        if (tid < 8) stat_s[tid] = 0ull;
         const int q4 = tid % N4;                 // fixed channel quad per thread in the write-out loop
         const int cq = a.co_base + q4 * 4;
         float bias[4] = {0.f, 0.f, 0.f, 0.f};
@@ -436,12 +436,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const int c = cq + k;
             if (lane < N4 && c < d.Cout) {
               const int g = c / cpg;
-              atomicAdd(&stat_s[g * 2 + 0], s);
-              atomicAdd(&stat_s[g * 2 + 1], q);
+              atomicAdd(&stat_s[g * 2 + 0], stat_fixed(s));
+              atomicAdd(&stat_s[g * 2 + 1], stat_fixed(q));
             }
           }
           __syncthreads();
-          if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+          if (tid < 8) atomicAdd(reinterpret_cast<unsigned long long*>(d.out_stats) + n * 8 + tid, stat_s[tid]);
           __syncthreads();
         }
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // TMEM reads done before the next tile's MMAs

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
   float* gn_s = halo_s + a.halo_f;                            // [2][C1] when GN
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t full_bar[R], empty_bar[R];
-  __shared__ float stat_s[8];
+  __shared__ unsigned long long stat_s[8];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
     const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
     const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
     const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
-    if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0.0f;
+    if (d.out_stats != nullptr && tid < 8) stat_s[tid] = 0ull;
     if (KWm1 > 0) {
       int blk = 0, cg = half;                                // items half, half + 2, ... as (block, channel group)
       while (cg >= ncg) { cg -= ncg; ++blk; }
@@ -530,8 +530,8 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
           const int c = c0 + 2 * j;
           if (lane == 0 && c < d.Cout) {
             const int g = c / cpg;
-            atomicAdd(&stat_s[g * 2 + 0], s);
-            atomicAdd(&stat_s[g * 2 + 1], q);
+            atomicAdd(&stat_s[g * 2 + 0], stat_fixed(s));
+            atomicAdd(&stat_s[g * 2 + 1], stat_fixed(q));
           }
         }
       }
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(kWsThreads, 2) conv_ws_kernel(const __grid_con
     }
     if (d.out_stats != nullptr) {
       asm volatile("bar.sync 1, 256;\n" ::: "memory");   // every worker's shared atomics are in
-      if (tid < 8) atomicAdd(d.out_stats + n * 8 + tid, (double)stat_s[tid]);
+      if (tid < 8) atomicAdd(reinterpret_cast<unsigned long long*>(d.out_stats) + n * 8 + tid, stat_s[tid]);
     }
   };
 

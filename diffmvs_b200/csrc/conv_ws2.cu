@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
   float* gn_s = halo0 + 2 * a.halo_f;                  // [2][C1] when GN
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(8) uint64_t tma_full[kMaxRing], op_full[kMaxRing], empty_bar[kMaxRing], acc_full[2], acc_empty[2];
-  __shared__ float stat_s[2][8];
+  __shared__ unsigned long long stat_s[2][8];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform in the compiler's eyes
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     prefetch_tensormap(&a.map_x);
     if (d.C2 > 0) prefetch_tensormap(&a.map_x2);
   }
-  if (tid < 16) stat_s[tid >> 3][tid & 7] = 0.0f;
+  if (tid < 16) stat_s[tid >> 3][tid & 7] = 0ull;
   fence_tc_before();
   __syncthreads();
   fence_tc_after();
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     // w % 4 of every M block.
     const int quadrant = warp & 3;
     const int etid = tid - 32 * kFirstEpiWarp;
-    auto epilogue = [&](auto nch_tag, int n, int od, int ty0, int tx0, uint32_t acc_base, float* halo, float* stat) {
+    auto epilogue = [&](auto nch_tag, int n, int od, int ty0, int tx0, uint32_t acc_base, float* halo, unsigned long long* stat) {
       constexpr int NCH = decltype(nch_tag)::value;
       const int ncg = a.CC / NCH;
       const int n_items = a.n_blk * ncg;                    // (block, channel group) pairs, block-major
@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
             const int c = c0 + 2 * j;
             if (lane == 0 && c < d.Cout) {
               const int g = c / cpg;
-              atomicAdd(&stat[g * 2 + 0], s);
-              atomicAdd(&stat[g * 2 + 1], q);
+              atomicAdd(&stat[g * 2 + 0], stat_fixed(s));
+              atomicAdd(&stat[g * 2 + 1], stat_fixed(q));
             }
           }
         }
@@ -476,8 +476,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       if (d.out_stats != nullptr) {
         asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // every epilogue warp's shared atomics are in
         if (etid < 8) {
-          atomicAdd(d.out_stats + n * 8 + etid, (double)stat[etid]);
-          stat[etid] = 0.0f;                                   // ready for the tile after next (same buffer)
+          atomicAdd(reinterpret_cast<unsigned long long*>(d.out_stats) + n * 8 + etid, stat[etid]);
+          stat[etid] = 0ull;                                   // ready for the tile after next (same buffer)
         }
       }
     };

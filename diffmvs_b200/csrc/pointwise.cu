@@ -7,7 +7,7 @@ namespace {
 
 // y = silu(GN(x) * g1 + g0) + res            (update.py:117-159, Block + ResnetBlock tail)
 __global__ void __launch_bounds__(256) groupnorm_silu_add_kernel(const float* __restrict__ x,
-                                                                 const double* __restrict__ stats,
+                                                                 const long long* __restrict__ stats,
                                                                  const float* __restrict__ g1,
                                                                  const float* __restrict__ g0,
                                                                  const float* __restrict__ res, int res_ps,
@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256) groupnorm_silu_add_kernel(const float* __
   const int cpg = C / 4;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const double s = stats[(n * 4 + g) * 2 + 0], q = stats[(n * 4 + g) * 2 + 1];
+    const double s = stat_value(stats[(n * 4 + g) * 2 + 0]), q = stat_value(stats[(n * 4 + g) * 2 + 1]);
     const double mean = s * (double)inv_count;
     double var = q * (double)inv_count - mean * mean;
     var = var < 0.0 ? 0.0 : var;
@@ -220,7 +220,7 @@ extern "C" const char* dmvs_build_info(void) {
          ", tcgen05/TMEM width-stacked + FFMA2 convolutions, fused warp/correlation";
 }
 
-extern "C" int dmvs_groupnorm_silu_add(const float* x, const double* stats, const float* g1, const float* g0,
+extern "C" int dmvs_groupnorm_silu_add(const float* x, const int64_t* stats, const float* g1, const float* g0,
                                        const float* res, int32_t res_ps, float* y, int32_t y_ps, int32_t N, int32_t HW,
                                        int32_t C, void* stream) {
   if (!x || !stats || !g1 || !g0 || !y || N <= 0 || HW <= 0 || C <= 0) return DMVS_ERR_ARG;
@@ -233,7 +233,7 @@ extern "C" int dmvs_groupnorm_silu_add(const float* x, const double* stats, cons
   dim3 grid(bx, N);
   const float inv_count = 1.0f / ((float)HW * (float)(C / 4));
   groupnorm_silu_add_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      x, stats, g1, g0, res, res_ps, y, y_ps, N, HW, C, inv_count);
+      x, reinterpret_cast<const long long*>(stats), g1, g0, res, res_ps, y, y_ps, N, HW, C, inv_count);
   return launch_status();
 }
 

@@ -285,7 +285,7 @@ class PackedConv:
 @dataclass
 class GroupNormIn:
     """GroupNorm(4)+affine+SiLU of the producer, applied while the consumer stages its input."""
-    stats: Tensor   # [N,4,2] float64
+    stats: Tensor   # [N,4,2] int64 fixed-point accumulators (2^-20 units) filled through `conv(..., out_stats=)`
     g1: Tensor      # [C]
     g0: Tensor      # [C]
 
@@ -356,6 +356,8 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         d.aux1, d.aux1_ps = _ptr(aux1), pixel_stride(aux1, "conv aux1")
     if aux2 is not None:
         d.aux2, d.aux2_ps = _ptr(aux2), pixel_stride(aux2, "conv aux2")
+    if out_stats is not None and out_stats.dtype != torch.int64:
+        raise ValueError("conv: out_stats must be a zero-initialised int64 [N,4,2] tensor (fixed-point accumulators)")
     d.out_stats = _ptr(out_stats)
     if d.precision == PREC_AUTO and _AUTOTUNE:
         key = (N, D, H, W, C1, C2, pc.cout, KD, KH, KW, stride, pd, ph, pw, int(in_up2), in_gn is not None, epi,

@@ -31,10 +31,11 @@ def _sub(sd: SD, prefix: str) -> SD:
 
 
 class StatsArena:
-    """Zero-initialised GroupNorm accumulators ([N,4,2] float64 slots) for one forward pass."""
+    """Zero-initialised GroupNorm accumulators ([N,4,2] int64 fixed-point slots, 2^-20 units; the kernels add integers, so
+    the statistics are independent of the order in which thread blocks arrive) for one forward pass."""
 
     def __init__(self, device, batch: int, slots: int):
-        self.buf = torch.zeros((slots, batch, 4, 2), device=device, dtype=torch.float64)
+        self.buf = torch.zeros((slots, batch, 4, 2), device=device, dtype=torch.int64)
         self.next = 0
 
     def slot(self) -> Tensor:

@@ -85,8 +85,9 @@ typedef struct dmvs_conv_desc {
   int32_t x_ps, x2_ps;      /* pixel strides of x / x2 in floats */
   int32_t in_up2;           /* 1: x is stored at (H/2, W/2) and nearest-upsampled on load (update.py:38-42) */
   /* optional GroupNorm(4 groups)+affine+SiLU applied to x on load (update.py:117-133):
-   * v = silu((v - mean_g) * rstd_g * in_g1[c] + in_g0[c]); stats = [N][4][2] doubles (sum, sumsq) */
-  const double* in_stats;
+   * v = silu((v - mean_g) * rstd_g * in_g1[c] + in_g0[c]); stats = [N][4][2] (sum, sumsq) as 64-bit fixed-point
+   * integers in units of 2^-20, the accumulators an earlier call filled through `out_stats` */
+  const int64_t* in_stats;
   const float* in_g1;
   const float* in_g0;
   float in_inv_count;       /* 1 / (elements per (sample, group)) */
@@ -118,7 +119,9 @@ typedef struct dmvs_conv_desc {
   const float* aux1;
   const float* aux2;
   int32_t aux1_ps, aux2_ps, gru_hidden;
-  double* out_stats;        /* optional [N][4][2] sum / sumsq of the written values per GroupNorm group */
+  int64_t* out_stats;       /* optional [N][4][2] sum / sumsq of the written values per GroupNorm group, accumulated as
+                               64-bit fixed point (2^-20 units; integer adds: the result is independent of the order in
+                               which CTAs arrive, runs are bit-reproducible); must be zeroed by the caller */
 } dmvs_conv_desc;
 
 int dmvs_conv_f32(const dmvs_conv_desc* desc, void* stream);
@@ -192,8 +195,9 @@ int dmvs_get_cost(const float* feats, const float* hom, const float* inv_depth, 
  * ------------------------------------------------------------------------------------------- */
 
 /* Block tail of ResnetBlock (update.py:117-159): y = silu(GN(x)*g1+g0) + res.
- * x [N][HW][C] raw conv output, stats [N][4][2]; res (pixel stride res_ps) or NULL. */
-int dmvs_groupnorm_silu_add(const float* x, const double* stats, const float* g1, const float* g0, const float* res,
+ * x [N][HW][C] raw conv output, stats [N][4][2] fixed-point accumulators (see dmvs_conv_desc.out_stats); res (pixel
+ * stride res_ps) or NULL. */
+int dmvs_groupnorm_silu_add(const float* x, const int64_t* stats, const float* g1, const float* g0, const float* res,
                             int32_t res_ps, float* y, int32_t y_ps, int32_t N, int32_t HW, int32_t C, void* stream);
 
 /* upsample_depth (module.py:237-248) + disp_to_depth (module.py:220-227) + depth_to_disp (:229-235).
