@@ -93,18 +93,39 @@ def _best_cpu_threads(cores: int) -> int:
     return best
 
 
+def _reference_kind() -> str:
+    """"reference" when the reference tree is mounted (build container: its own `CasDiffMVS` runs, unmodified),
+    "port" otherwise (GPU box: the oracle restatement, bit-identical to it on CPU - tests/test_oracle_golden.py)."""
+    from oracle import refimport
+    return "reference" if refimport.reference_available() else "port"
+
+
 def _oracle_forward_cpu(workload: str, threads: int):
-    """One CPU forward of the oracle port on `threads` host threads; returns a callable giving seconds."""
+    """One CPU forward of the reference algorithm on `threads` host threads; returns a callable giving seconds.
+    Runs `/root/reference`'s own module when that tree exists, the oracle port otherwise."""
     import torch
     from diffmvs_b200 import synth
     from oracle import diffmvs_ref as O
-    from oracle import spec
+    from oracle import refimport, spec
     torch.set_num_threads(threads)
     args = synth.workload_args(workload)
     sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
     imgs, proj, dv = synth.workload_inputs(workload)
     gen = torch.Generator().manual_seed(1)
     randn = lambda like: torch.randn(like.shape, generator=gen, dtype=torch.float32)
+    if refimport.reference_available():
+        ref_models = refimport.import_reference_models()
+        model = ref_models.CasDiffMVS(args, test=True).eval()
+        full = dict(model.state_dict())
+        full.update(sd)
+        model.load_state_dict(full, strict=True)
+
+        def run():
+            t0 = time.perf_counter()
+            with torch.no_grad():
+                model(imgs, proj, dv)
+            return time.perf_counter() - t0
+        return run
 
     def run():
         t0 = time.perf_counter()
@@ -114,9 +135,49 @@ def _oracle_forward_cpu(workload: str, threads: int):
     return run
 
 
+def _gpu_baseline(workload: str, dev, steps: int = 5):
+    """The reference algorithm on stock torch CUDA ops (cuDNN / ATen) on THIS GPU - what a user of the reference gets on
+    a B200 ("the real bar to beat"): the oracle restatement with device tensors, cudnn.benchmark on as in
+    test.py:18, once with torch's default TF32 convolutions and once in strict fp32."""
+    import torch
+    from diffmvs_b200 import synth
+    from oracle import diffmvs_ref as O
+    from oracle import spec
+    args = synth.workload_args(workload)
+    sd = {k: v.to(dev) for k, v in synth.synth_state_dict(spec.state_dict_shapes(args), 123).items()}
+    imgs, proj, dv = synth.workload_inputs(workload)
+    imgs, proj, dv = [i.to(dev) for i in imgs], {k: v.to(dev) for k, v in proj.items()}, dv.to(dev)
+    out = {"kind": "oracle restatement on stock torch CUDA ops (cuDNN/ATen), cudnn.benchmark=True, same GPU", "unit": UNIT}
+    old = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.benchmark = True
+    try:
+        for name, tf32 in (("tf32_default", True), ("fp32_strict", False)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            sampler = ClockSampler(dev.index or 0)
+            with torch.no_grad():
+                for _ in range(3):
+                    O.casdiffmvs_forward(sd, args, imgs, proj, dv)
+                torch.cuda.synchronize(dev)
+                sampler.start()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    O.casdiffmvs_forward(sd, args, imgs, proj, dv)
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": 1e3 / ms, "ms_per_step": ms, "steps": steps, "clocks": sampler.stop()}
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    del sd, imgs, proj, dv
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_reference(a):
-    """`--impl reference`: the reference algorithm on the host cores (oracle port; the Python reference cannot
-    travel to the GPU box and needs a CUDA device at import)."""
+    """`--impl reference`: the reference algorithm on the host cores - the reference's own module where its tree is
+    mounted, the oracle port on the GPU box (the Python reference cannot travel there)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -135,21 +196,25 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": _config(a.workload, 1, "reference algorithm on the host cores"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": _config(a.workload),
+        "parallelism": "reference algorithm on the host cores (rank 0 only)",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": _reference_kind(), "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def _config(workload, world, parallelism):
-    """The `config` object of the JSON line (same for both arms)."""
+def _config(workload):
+    """The `config` object of the JSON line: names the workload only, identical for both arms (how the work is spread
+    over GPUs is reported in the separate `parallelism` key)."""
     from diffmvs_b200 import synth
     variant, H, W, V, D0 = synth.WORKLOADS[workload]
     return {"workload": workload, "variant": variant, "image": [W, H], "views": V, "numdepth_initial": D0,
-            "numdepth": 384, "batch": 1, "l2": "inputs (155 MB at cfg3) and per-step working set exceed L2",
-            "parallelism": parallelism}
+            "numdepth": 384, "batch": 1,
+            "l2": (f"inputs ({V * 3 * H * W * 4 / 1e6:.0f} MB) and per-step working set exceed the 126 MB L2"
+                   if V * 3 * H * W * 4 > 126e6 else
+                   f"inputs ({V * 3 * H * W * 4 / 1e6:.1f} MB) fit in L2 and L2 is NOT flushed: not a headline configuration")}
 
 
 def run_ours(a):
@@ -187,12 +252,14 @@ def run_ours(a):
     d_proj = {k: v.to(dev) for k, v in proj.items()}
     d_dv = dv.to(dev)
     h2d = sum(t.numel() * 4 for t in h_imgs) + sum(t.numel() * 4 for t in h_proj.values()) + h_dv.numel() * 4
-    gather_buf = [torch.empty((1, H, W), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    n_maps = 1 + (3 if variant == "casdiffmvs" else 2)           # final depth + the full-resolution confidence maps
+    gather_buf = [torch.empty((n_maps, H, W), device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
 
     def step_resident():
         out = model(d_imgs, d_proj, d_dv)
-        if world > 1:   # single gather of the per-view result to rank 0
-            dist.gather(out["depth"][-1], gather_buf, dst=0)   # same exchange as sharding.gather_maps
+        if world > 1:   # single gather of the per-view results (depth + confidences) to rank 0
+            maps = torch.cat([out["depth"][-1]] + list(out["photometric_confidence"]), 0)
+            dist.gather(maps, gather_buf, dst=0)              # same exchange as sharding.gather_maps
         return out
 
     h_out = {}
@@ -304,34 +371,48 @@ def run_ours(a):
     value = world * a.steps / (ms_dev / 1e3)
     e2e_value = world * a.steps / (e2e_wall / 1e3)
     peak, peak_src = _peaks()
-    # dominant kernel family by device time
-    fam = {}
+    # Per-kernel device time of one eager step (CUDA events on the launch stream around every C-ABI call).  Convolution
+    # calls are attributed to the CUDA kernel behind the back end that ran them (conv_ws2_kernel, conv_ws_kernel,
+    # conv_kernel, ...); everything else to its own kernel.
+    kern = {}
     for (name, tag), r in summ.items():
-        f = fam.setdefault(name, {"ms": 0.0, "bytes": 0, "calls": 0})
-        f["ms"] += r["ms"]; f["bytes"] += r["bytes"]; f["calls"] += r["calls"]
-    tot_ms = sum(f["ms"] for f in fam.values()) or 1.0
-    top_name = max(fam, key=lambda k: fam[k]["ms"]) if fam else "n/a"
-    top = fam.get(top_name, {"ms": 1.0, "bytes": 0, "calls": 1})
-    achieved = top["bytes"] / (top["ms"] / 1e3) / 1e9 if top["ms"] > 0 else 0.0
-    # DRAM traffic of the same kernel family over one step, from the committed ncu capture (profiles/); per step, like
-    # the algorithmic bytes behind `achieved`
+        kname = tag.split("|", 1)[0] if name == "conv" and "|" in tag else name
+        k = kern.setdefault(kname, {"ms": 0.0, "bytes": 0, "calls": 0})
+        k["ms"] += r["ms"]; k["bytes"] += r["bytes"]; k["calls"] += r["calls"]
+    tot_ms = sum(k["ms"] for k in kern.values()) or 1.0
+    top_name = max(kern, key=lambda k: kern[k]["ms"]) if kern else "n/a"
+    top = kern.get(top_name, {"ms": 1.0, "bytes": 0, "calls": 1})
+    conv_names = [k for k in kern if k.startswith("conv")]
+    conv_ms = sum(kern[k]["ms"] for k in conv_names)
+    conv_bytes = sum(kern[k]["bytes"] for k in conv_names)
+    scale = (H * W * V) / (1152 * 1600 * 7)
+    contract_bytes = ALGO_BYTES_CFG3 * scale                  # per ref-view, ideal per-operator fusion
+    contract_gbs = contract_bytes / (ms_step / 1e3) / 1e9
+    # DRAM traffic of the convolution kernels over one step, from the committed ncu launch list (profiles/)
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "conv_dram_traffic.json")
-    if top_name == "conv" and a.workload == "cfg3" and os.path.exists(tpath):
+    if a.workload == "cfg3" and os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             traffic, traffic_src = float(tj["conv_dram_bytes_per_step"]), tj.get("source")
         except Exception:
             pass
+    top_gbs = top["bytes"] / (top["ms"] / 1e3) / 1e9 if top["ms"] > 0 else 0.0
     roofline = {
-        "bound": "hbm", "kernel": f"dmvs_{top_name} (all launches of one step)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-        "algorithmic_bytes": top["bytes"], "peak_source": peak_src,
-        "share_of_step": top["ms"] / tot_ms, "launches_per_step": top["calls"],
-        "whole_step": {"algorithmic_bytes": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7),
-                       "achieved": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7) / (ms_step / 1e3) / 1e9,
-                       "frac": ALGO_BYTES_CFG3 * (H * W * V) / (1152 * 1600 * 7) / (ms_step / 1e3) / 1e9 / peak},
-        "families_ms": {k: round(v["ms"], 3) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+        # headline: the whole step against SURVEY.md 8(d)'s contract figure (2.75 GB per ref-view at cfg3, scaled by
+        # H*W*V for other workloads) - what an ideally fused implementation would have to move
+        "bound": "hbm", "achieved": contract_gbs, "peak": peak, "unit": "GB/s", "frac": contract_gbs / peak,
+        "algorithmic_bytes": contract_bytes, "basis": "SURVEY 8(d) operator-boundary bytes of one ref-view / device time of one step",
+        "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": traffic_src, "traffic_scope": "all convolution kernels, one step",
+        # the dominant kernel on its own: layer-wise algorithmic bytes (inputs + outputs + weights of each launch)
+        "kernel": {"name": top_name, "launches_per_step": top["calls"], "avg_us": 1e3 * top["ms"] / max(top["calls"], 1),
+                   "algorithmic_bytes_per_launch": top["bytes"] / max(top["calls"], 1), "achieved": top_gbs,
+                   "frac": top_gbs / peak, "share_of_step": top["ms"] / tot_ms,
+                   "basis": "layer-wise bytes (every launch's own inputs + outputs), CUDA events per launch, eager step"},
+        "conv_family": {"ms": conv_ms, "algorithmic_bytes": conv_bytes, "achieved": conv_bytes / (conv_ms / 1e3) / 1e9 if conv_ms else 0.0,
+                        "frac": conv_bytes / (conv_ms / 1e3) / 1e9 / peak if conv_ms else 0.0, "share_of_step": conv_ms / tot_ms},
+        "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])},
     }
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
@@ -340,19 +421,32 @@ def run_ours(a):
         t = run()
         if t < 15.0:
             t = min(t, run())
-        cpu = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 ref-view at {a.workload} (one full step), oracle port (torch CPU fp32) on {cores} of "
+        kind = _reference_kind()
+        what = "the reference's own CasDiffMVS module" if kind == "reference" else "oracle port"
+        cpu = {"value": 1.0 / t, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"1 ref-view at {a.workload} (one full step), {what} (torch CPU fp32) on {cores} of "
                          f"{os.cpu_count()} host threads (fastest of a thread-count sweep)"}
+    gpu_base = None
+    if world == 1 and not a.no_gpu_baseline:
+        try:
+            gpu_base = _gpu_baseline(a.workload, dev)
+            gpu_base["speedup_vs_tf32_default"] = value / gpu_base["tf32_default"]["value"]
+            gpu_base["speedup_vs_fp32_strict"] = value / gpu_base["fp32_strict"]["value"]
+        except Exception as e:   # e.g. out of memory on a smaller part: report, do not fail the bench
+            gpu_base = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "precision": ops.get_precision(), "cuda_graph": not a.no_graph, "alt_modes": alt,
-        "config": _config(a.workload, world, f"ref-views sharded, {world} GPU(s), no data-path collective"),
+        "config": _config(a.workload),
+        "parallelism": f"ref-views sharded one per GPU per step over {world} GPU(s); no data-path collective, one NCCL gather "
+                       f"of depth + confidence maps to rank 0 per step",
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "gpu_baseline": gpu_base,
         "wall_ms_per_step": ms_wall / a.steps,
     }
     print(json.dumps(line), flush=True)
@@ -371,6 +465,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-modes", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch CUDA timing of the reference algorithm")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")
     ap.add_argument("--dump-tuned", default=None, help="write the per-layer autotuning table (JSON) to this path")
     ap.add_argument("--load-tuned", default=None, help="preload an autotuning table (use under a profiler, whose "

@@ -161,6 +161,11 @@ class Profiler:
 
 
 _PROFILER: Optional[Profiler] = None
+_LAST_CONV_BACKEND = PREC_FP32
+# C kernel behind each back-end code (what `cuobjdump` / ncu list for that launch)
+KERNEL_OF_BACKEND = {PREC_FP32: "conv_kernel", PREC_TF32X3: "conv_mma_kernel", PREC_TF32: "conv_mma_kernel",
+                     PREC_TC_TF32X3: "conv_tc_kernel", PREC_TC_TF32: "conv_tc_kernel", PREC_WS_TF32X3: "conv_ws_kernel",
+                     PREC_WS_TF32: "conv_ws_kernel", PREC_WS2_TF32X3: "conv_ws2_kernel", PREC_AUTO: "conv_kernel|conv_tc_kernel"}
 
 
 def set_profiler(p: Optional[Profiler]) -> None:
@@ -210,7 +215,8 @@ def _profiled(name: str):
             tag = ""
             if name == "conv":
                 pc = a[1]
-                tag = f"{pc.cin}->{pc.cout} k{'x'.join(map(str, pc.k))} s{k.get('stride', 1)} {tuple(out.shape[1:-1])}"
+                tag = (f"{KERNEL_OF_BACKEND.get(_LAST_CONV_BACKEND, '?')}|{pc.cin}->{pc.cout} k{'x'.join(map(str, pc.k))} "
+                       f"s{k.get('stride', 1)} {tuple(out.shape[1:-1])}")
             prof.records.append((name, tag, nbytes, e0, e1))
             return out
         wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
@@ -364,6 +370,8 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
                res_mode, int(res_up2), x_ps, x2_ps, y_ps)
         hit = _TUNED.get(key)
         d.precision = hit[0] if hit is not None else _tune(d, key)
+    global _LAST_CONV_BACKEND
+    _LAST_CONV_BACKEND = PREC_WS_TF32X3 if (d.precision == PREC_WS2_TF32X3 and in_up2) else d.precision
     check(_cabi.lib().dmvs_conv_f32(C.byref(d), _stream()), "dmvs_conv_f32")
     return out
 
