@@ -246,6 +246,9 @@ def run_ours(a):
     # each rank owns its own reference views (weak scaling: one ref-view per step per GPU)
     imgs, proj, dv = synth.workload_inputs(a.workload, seed=rank)
     h_imgs = [i.pin_memory() for i in imgs]
+    # the same images as 8-bit data (what a loader decodes from disk); the model divides by 255 on the device
+    h_imgs_u8 = [(i * 255).round().clamp(0, 255).to(torch.uint8).pin_memory() for i in imgs]
+    host = {"imgs": h_imgs}
     h_proj = {k: v.pin_memory() for k, v in proj.items()}
     h_dv = dv.pin_memory()
     d_imgs = [i.to(dev) for i in imgs]
@@ -276,7 +279,7 @@ def run_ours(a):
     def prefetch(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])      # the forward that read this slot has finished
-            slots[slot] = ([t.to(dev, non_blocking=True) for t in h_imgs],
+            slots[slot] = ([t.to(dev, non_blocking=True) for t in host["imgs"]],
                            {k: t.to(dev, non_blocking=True) for k, t in h_proj.items()},
                            h_dv.to(dev, non_blocking=True))
             ready[slot].record(copy_stream)
@@ -338,6 +341,15 @@ def run_ours(a):
         d2h = step_e2e()
         step_e2e()
         _, e2e_wall = timed(step_e2e, a.steps)
+        # the same loop fed with uint8 host images (extension of the public call: 4x fewer H2D bytes, ...)
+        host["imgs"] = h_imgs_u8
+        slots[0] = slots[1] = None
+        torch.cuda.synchronize()
+        for _ in range(3):               # new input signature: captures a second graph, then steady state
+            step_e2e()
+        _, e2e_u8_wall = timed(step_e2e, a.steps)
+        host["imgs"] = h_imgs
+        slots[0] = slots[1] = None
         # per-kernel-family device time over one more step (CUDA events on the launch stream)
         model.use_cuda_graph(False)          # per-call events need the eager path
         step_resident()                      # untimed: lets the caching allocator serve this stream without cudaMalloc
@@ -370,6 +382,8 @@ def run_ours(a):
     ms_step = ms_dev / a.steps
     value = world * a.steps / (ms_dev / 1e3)
     e2e_value = world * a.steps / (e2e_wall / 1e3)
+    e2e_u8_value = world * a.steps / (e2e_u8_wall / 1e3)
+    h2d_u8 = h2d - sum(t.numel() * 3 for t in h_imgs_u8)
     peak, peak_src = _peaks()
     # Per-kernel device time of one eager step (CUDA events on the launch stream around every C-ABI call).  Convolution
     # calls are attributed to the CUDA kernel behind the back end that ran them (conv_ws2_kernel, conv_ws_kernel,
@@ -443,6 +457,9 @@ def run_ours(a):
                        f"of depth + confidence maps to rank 0 per step",
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                   "note": "same call with uint8 host images (as decoded from disk), /255 on the device: depth maps "
+                           "bit-identical to the float32-image call (tests/test_gpu_kernels.py)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

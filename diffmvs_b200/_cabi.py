@@ -67,6 +67,7 @@ SIGNATURES = {
                                  C.c_int64, C.c_void_p]),
     "dmvs_upsample_nearest": (C.c_int, [f32p, i32, f32p, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_image_to_nhwc4": (C.c_int, [f32p, f32p, i32, i32, C.c_void_p]),
+    "dmvs_image_u8_to_nhwc4": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, i32, f32p, i32, i32, C.c_void_p]),
     "dmvs_geo_consistency": (C.c_int, [f32p, f32p, C.c_void_p, C.c_float, C.c_float, C.c_double, C.c_float, C.c_void_p, f32p,
                                        f32p, f32p, f32p, C.c_void_p, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_fuse_points": (C.c_int, [f32p, f32p, C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -568,7 +568,12 @@ def to_nhwc(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
 
 @_profiled("to_nhwc")
 def image_to_nhwc4(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    """RGB image batch [N,3,H,W] -> [N,H,W,4] (fourth channel zero)."""
+    """RGB image batch [N,3,H,W] -> [N,H,W,4] (fourth channel zero).  float32 images in [0,1] (what the reference's loader
+    yields) or uint8 images as decoded from disk (extension: scaled by 1/255 on the device with the loader's exact fp32
+    division, so results are bit-identical while the host->device copy is 4x smaller); a uint8 input may be a permuted
+    view of an interleaved [N,H,W,3] array."""
+    if x.dtype == torch.uint8:
+        return _image_u8_to_nhwc4(x, out)
     _req_cuda_f32(x, "image")
     N, Cc, H, W = x.shape
     if Cc != 3:
@@ -578,6 +583,24 @@ def image_to_nhwc4(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
     elif tuple(out.shape) != (N, H, W, 4) or not out.is_contiguous():
         raise ValueError("image_to_nhwc4: out must be a dense [N,H,W,4] tensor")
     check(_cabi.lib().dmvs_image_to_nhwc4(_ptr(x.contiguous()), _ptr(out), N, H * W, _stream()), "dmvs_image_to_nhwc4")
+    return out
+
+
+def _image_u8_to_nhwc4(x: Tensor, out: Optional[Tensor]) -> Tensor:
+    if not x.is_cuda:
+        raise ValueError("image: CUDA tensor required (there is no CPU path)")
+    N, Cc, H, W = x.shape
+    if Cc != 3:
+        raise ValueError(f"image_to_nhwc4: expected 3 channels, got {Cc}")
+    sn, sc, sh, sw = x.stride()
+    if sh != W * sw or (N > 1 and sn < 3 * H * W) or not ((sc == H * W and sw == 1) or (sc == 1 and sw == 3)):
+        x = x.contiguous()
+        sn, sc, sh, sw = x.stride()
+    if out is None:
+        out = torch.empty((N, H, W, 4), device=x.device, dtype=torch.float32)
+    elif tuple(out.shape) != (N, H, W, 4) or not out.is_contiguous():
+        raise ValueError("image_to_nhwc4: out must be a dense [N,H,W,4] tensor")
+    check(_cabi.lib().dmvs_image_u8_to_nhwc4(_ptr(x), sn, sc, sw, _ptr(out), N, H * W, _stream()), "dmvs_image_u8_to_nhwc4")
     return out
 
 

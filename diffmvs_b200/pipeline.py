@@ -442,7 +442,7 @@ class CasDiffMVSPlan:
         staged = sorted(set(missing) | {0})                  # ContextNet always needs the reference image
         x_st = torch.empty((len(staged), B, H, W, 4), device=dev, dtype=torch.float32)   # RGB + one zero channel
         for i, v in enumerate(staged):
-            ops.image_to_nhwc4(imgs[v].float(), out=x_st[i])
+            ops.image_to_nhwc4(imgs[v] if imgs[v].dtype == torch.uint8 else imgs[v].float(), out=x_st[i])
         if len(missing) == V:
             feats = self.feature(x_st.view(V * B, H, W, 4))
         else:
@@ -529,7 +529,7 @@ class CasDiffMVSPlan:
     # --------------------------------------------------------------------------------------------
     def forward_graphed(self, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor
                         ) -> Dict[str, List[Tensor]]:
-        key = (tuple(imgs[0].shape), len(imgs), tuple((k, tuple(v.shape)) for k, v in sorted(proj_matrices.items())),
+        key = (tuple(imgs[0].shape), imgs[0].dtype, len(imgs), tuple((k, tuple(v.shape)) for k, v in sorted(proj_matrices.items())),
                tuple(depth_values.shape), ops.get_precision())
         graphs = self.__dict__.setdefault("_graphs", {})
         g = graphs.get(key)
@@ -546,7 +546,8 @@ class GraphedForward:
 
     def __init__(self, plan: "CasDiffMVSPlan", imgs, proj_matrices, depth_values):
         dev = imgs[0].device
-        self.imgs = [torch.empty(i.shape, device=dev, dtype=torch.float32) for i in imgs]
+        self.imgs = [torch.empty(i.shape, device=dev, dtype=torch.uint8 if i.dtype == torch.uint8 else torch.float32)
+                     for i in imgs]
         self.proj = {k: torch.empty(v.shape, device=dev, dtype=torch.float32) for k, v in proj_matrices.items()}
         self.dv = torch.empty(depth_values.shape, device=dev, dtype=torch.float32)
         self._load(imgs, proj_matrices, depth_values)

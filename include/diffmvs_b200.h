@@ -232,6 +232,12 @@ int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int32_t B, int
  * fourth channel, the layout the first convolutions (module.py:332,364) stage with 128-bit copies. */
 int dmvs_image_to_nhwc4(const float* x, float* y, int32_t N, int32_t HW, void* stream);
 
+/* The same staging for 8-bit images as decoded from disk: y = float(x) / 255 (one IEEE fp32 division, bit-identical to
+ * the loader's `np.array(img, dtype=np.float32) / 255.`, datasets/data_io.py:166-170).  x is planar [N][3][HW] (c_stride =
+ * HW, p_stride = 1) or interleaved [N][HW][3] (c_stride = 1, p_stride = 3); n_stride = bytes between images. */
+int dmvs_image_u8_to_nhwc4(const uint8_t* x, int64_t n_stride, int64_t c_stride, int32_t p_stride, float* y, int32_t N,
+                           int32_t HW, void* stream);
+
 /* layout transposes between the reference's NCHW operator surface and channels-last */
 int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t N, int32_t C, int32_t HW, void* stream);
 int dmvs_nhwc_to_nchw(const float* x, int32_t x_ps, float* y, int32_t N, int32_t C, int32_t HW, void* stream);

@@ -400,3 +400,35 @@ def test_cpu_tensors_are_rejected():
     pc = packing.pack_weight(_rand(4, 4, 3, 3), None)
     with pytest.raises(ValueError):
         ops.conv(torch.zeros(1, 8, 8, 4), pc)
+
+
+def test_uint8_images_are_staged_bit_identically():
+    """8-bit images (extension): ops.image_to_nhwc4 divides by 255 on the device with the loader's exact fp32 division
+    (`np.array(img, dtype=np.float32) / 255.`, datasets/data_io.py:166-170) - planar and interleaved layouts - and the
+    whole model gives bit-identical depth maps for uint8 and float32 inputs."""
+    rng = np.random.default_rng(0)
+    hwc = rng.integers(0, 256, size=(2, 40, 56, 3), dtype=np.uint8)
+    ref = torch.from_numpy((hwc.astype(np.float32) / 255.0).astype(np.float32))            # the loader's arithmetic
+    u8 = torch.from_numpy(hwc).to(DEV)
+    for x in (u8.permute(0, 3, 1, 2), u8.permute(0, 3, 1, 2).contiguous()):                  # interleaved view / planar
+        y = ops.image_to_nhwc4(x)
+        assert torch.equal(y[..., :3].cpu(), ref) and torch.all(y[..., 3] == 0)
+    yf = ops.image_to_nhwc4(ref.permute(0, 3, 1, 2).contiguous().to(DEV))
+    assert torch.equal(yf, y)
+
+    from diffmvs_b200 import synth
+    from diffmvs_b200.models import CasDiffMVS
+    from oracle import spec
+    args = synth.workload_args("cas_tiny")
+    model = CasDiffMVS(args, test=True)
+    model.load_state_dict(synth.synth_state_dict(spec.state_dict_shapes(args), 123), strict=False)
+    model.to(DEV).eval()
+    imgs, proj, dv = synth.workload_inputs("cas_tiny")
+    imgs_u8 = [(i * 255).round().clamp(0, 255).to(torch.uint8) for i in imgs]
+    imgs_f = [i.float() / 255.0 for i in imgs_u8]
+    proj, dv = {k: v.to(DEV) for k, v in proj.items()}, dv.to(DEV)
+    torch.manual_seed(3)
+    a = model([i.to(DEV) for i in imgs_f], proj, dv)["depth"]
+    torch.manual_seed(3)
+    b = model([i.to(DEV) for i in imgs_u8], proj, dv)["depth"]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
