@@ -80,14 +80,14 @@ class CasDiffMVS(_PlannedModule):
 
         Extension (not in the reference): `return_features=True` adds `"features"`, the per-view FeatureNet pyramids;
         passing them back as `features=[pyramid or None per view]` on a later call skips FeatureNet for those views
-        (a scan re-uses every image as a source view of its neighbours).  Results are unchanged."""
+        (a scan re-uses every image as a source view of its neighbours).  `return_features` may also be a list of view
+        indices (e.g. `[0]`: only the new reference image's pyramid).  The returned pyramids are the caller's own
+        copies.  Results are unchanged; works with `use_cuda_graph()` (one captured graph per cache pattern)."""
         if not self.test or depth_gt_ms is not None:
             raise NotImplementedError("training-mode outputs (per-iteration lists, ground-truth injection) are out of "
                                       "scope: build with test=True (SURVEY.md section 2)")
         with torch.no_grad():
             plan = self.plan(imgs[0].device)
-            if features is not None or return_features:
-                return plan.forward(imgs, proj_matrices, depth_values, features=features, return_features=return_features)
             if getattr(self, "_use_graph", False):
-                return plan.forward_graphed(imgs, proj_matrices, depth_values)
-            return plan.forward(imgs, proj_matrices, depth_values)
+                return plan.forward_graphed(imgs, proj_matrices, depth_values, features, return_features)
+            return plan.forward(imgs, proj_matrices, depth_values, features=features, return_features=return_features)

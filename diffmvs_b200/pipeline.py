@@ -520,43 +520,54 @@ class CasDiffMVSPlan:
                     taps[f"{key}_hidden0"] = hidden
         out = {"depth": depths, "conf": [], "photometric_confidence": confs}
         if return_features:
-            out["features"] = [{k: f.view(V, B, *f.shape[1:])[v] for k, f in feats.items()} for v in range(V)]
+            # per-view copies (not views into the shared [V*B,...] buffers: a caller that caches one pyramid must not
+            # keep all V alive); `return_features` may list the view indices wanted (e.g. [0]: the new reference image)
+            want = range(V) if return_features is True else [int(v) for v in return_features]
+            out["features"] = [{k: f.view(V, B, *f.shape[1:])[v].clone() for k, f in feats.items()} if v in want else None
+                               for v in range(V)]
         return out
 
     # --------------------------------------------------------------------------------------------
     # CUDA-graph replay of the whole forward: ~800 kernel launches per
     # reference view become one graph launch, so the refinement loop runs with no host involvement.
     # --------------------------------------------------------------------------------------------
-    def forward_graphed(self, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor
+    def forward_graphed(self, imgs: Sequence[Tensor], proj_matrices: Dict[str, Tensor], depth_values: Tensor,
+                        features: Optional[Sequence[Optional[Dict[str, Tensor]]]] = None, return_features=False
                         ) -> Dict[str, List[Tensor]]:
+        cached = tuple(f is not None for f in features) if features is not None else ()
+        want = True if return_features is True else tuple(int(v) for v in return_features) if return_features else ()
         key = (tuple(imgs[0].shape), imgs[0].dtype, len(imgs), tuple((k, tuple(v.shape)) for k, v in sorted(proj_matrices.items())),
-               tuple(depth_values.shape), ops.get_precision())
+               tuple(depth_values.shape), ops.get_precision(), cached, want)
         graphs = self.__dict__.setdefault("_graphs", {})
         g = graphs.get(key)
         if g is None:
-            g = graphs[key] = GraphedForward(self, imgs, proj_matrices, depth_values)
-        return g(imgs, proj_matrices, depth_values)
+            g = graphs[key] = GraphedForward(self, imgs, proj_matrices, depth_values, features, return_features)
+        return g(imgs, proj_matrices, depth_values, features)
 
 
 class GraphedForward:
-    """One captured `CasDiffMVSPlan.forward` for a fixed input signature.  Inputs are copied into static
-    buffers, the graph is replayed, results are returned as fresh tensors (the caller owns them, as with the
-    eager path).  `torch.randn_like` inside the graph keeps drawing from the default CUDA generator (torch
-    advances its Philox offset per replay), so noise semantics are those of the eager path."""
+    """One captured `CasDiffMVSPlan.forward` for a fixed input signature (image size / dtype, view count, which views
+    come with cached feature pyramids).  Inputs are copied into static buffers, the graph is replayed, results are
+    returned as fresh tensors (the caller owns them, as with the eager path).  `torch.randn_like` inside the graph keeps
+    drawing from the default CUDA generator (torch advances its Philox offset per replay), so noise semantics are those
+    of the eager path."""
 
-    def __init__(self, plan: "CasDiffMVSPlan", imgs, proj_matrices, depth_values):
+    def __init__(self, plan: "CasDiffMVSPlan", imgs, proj_matrices, depth_values, features=None, return_features=False):
         dev = imgs[0].device
         self.imgs = [torch.empty(i.shape, device=dev, dtype=torch.uint8 if i.dtype == torch.uint8 else torch.float32)
                      for i in imgs]
         self.proj = {k: torch.empty(v.shape, device=dev, dtype=torch.float32) for k, v in proj_matrices.items()}
         self.dv = torch.empty(depth_values.shape, device=dev, dtype=torch.float32)
-        self._load(imgs, proj_matrices, depth_values)
+        self.feats = None if features is None else [None if f is None else {k: torch.empty_like(t) for k, t in f.items()}
+                                                    for f in features]
+        self._load(imgs, proj_matrices, depth_values, features)
         rng = torch.cuda.get_rng_state(dev)  # the warm-up must not consume the caller's noise stream
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        kw = dict(features=self.feats, return_features=return_features)
         with torch.cuda.stream(side):       # eager warm-up: autotunes every layer, fills the allocator
             for _ in range(2):
-                plan.forward(self.imgs, self.proj, self.dv)
+                plan.forward(self.imgs, self.proj, self.dv, **kw)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         torch.cuda.set_rng_state(rng, dev)
@@ -564,18 +575,28 @@ class GraphedForward:
         before = _cabi.lib().dmvs_launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = plan.forward(self.imgs, self.proj, self.dv)
+            self.out = plan.forward(self.imgs, self.proj, self.dv, **kw)
         self.launches = int(_cabi.lib().dmvs_launch_count() - before)
 
-    def _load(self, imgs, proj_matrices, depth_values):
+    def _load(self, imgs, proj_matrices, depth_values, features=None):
         for dst, src in zip(self.imgs, imgs):
             dst.copy_(src, non_blocking=True)
         for k, dst in self.proj.items():
             dst.copy_(proj_matrices[k], non_blocking=True)
         self.dv.copy_(depth_values, non_blocking=True)
+        if self.feats is not None:
+            for dst, src in zip(self.feats, features):
+                if dst is not None:
+                    for k, t in dst.items():
+                        if tuple(src[k].shape) != tuple(t.shape):
+                            raise ValueError(f"cached features ({tuple(src[k].shape)}) do not match this input ({tuple(t.shape)})")
+                        t.copy_(src[k], non_blocking=True)
 
-    def __call__(self, imgs, proj_matrices, depth_values):
-        self._load(imgs, proj_matrices, depth_values)
+    def __call__(self, imgs, proj_matrices, depth_values, features=None):
+        self._load(imgs, proj_matrices, depth_values, features)
         self.graph.replay()
         ops.count_replayed_launches(self.launches)
-        return {k: [t.clone() for t in v] for k, v in self.out.items()}
+        out = {k: [t.clone() for t in v] for k, v in self.out.items() if k != "features"}
+        if "features" in self.out:
+            out["features"] = [None if f is None else {k: t.clone() for k, t in f.items()} for f in self.out["features"]]
+        return out

@@ -293,31 +293,82 @@ def test_cuda_graph_replay_matches_eager():
     assert g3["depth"][-1].data_ptr() != g1["depth"][-1].data_ptr()   # results are the caller's own tensors
 
 
-def test_feature_cache_leaves_results_unchanged(monkeypatch):
-    """Cross-ref-view feature cache: pyramids returned by one call and passed back for all or
-    some views give the same depths as re-encoding every image."""
+def test_feature_cache_against_the_oracle(monkeypatch):
+    """Cross-ref-view feature cache against the CPU ORACLE, not against the uncached CUDA path:
+    reference view B = source view 1 of call A, its pyramids come from call A's `return_features` (computed there in
+    other batch positions); every cache pattern (full / partial / mixed / none) is checked against the oracle in eager
+    mode and against the eager call under CUDA-graph replay."""
     args = synth.workload_args("cas_tiny")
     sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
-    imgs, proj, dv = _to_dev(*synth.workload_inputs("cas_tiny"))
+    imgs, proj, dv = synth.workload_inputs("cas_tiny")
+    order = [1, 0, 2]                                           # call B: view 1 becomes the reference
+    imgs_b = [imgs[v] for v in order]
+    proj_b = {k: p[:, order].contiguous() for k, p in proj.items()}
+
+    def mk():
+        gen = torch.Generator().manual_seed(17)
+        return lambda like: torch.randn(like.shape, generator=gen, dtype=torch.float32)
+
+    with torch.no_grad():
+        ref = O.casdiffmvs_forward(sd, args, imgs_b, proj_b, dv, randn=mk())
     model = _build(args, sd)
-
-    def run(**kw):
-        torch.manual_seed(21)
-        return model(imgs, proj, dv, **kw)
-
-    base = run(return_features=True)
-    feats = base["features"]
-    assert len(feats) == len(imgs) and set(feats[0]) == {"stage1", "stage2", "stage3"}
-    full = run(features=feats)
-    partial = run(features=[None] + feats[1:])              # new reference image, cached sources
-    mixed = run(features=[feats[0], None] + feats[2:])
-    for other in (full, partial, mixed):
-        for a, b in zip(base["depth"], other["depth"]):
-            assert rel_l1(a, b) < 1e-6
+    d_imgs, d_proj, d_dv = _to_dev(imgs, proj, dv)
+    d_imgs_b, d_proj_b, _ = _to_dev(imgs_b, proj_b, dv)
+    with torch.no_grad():
+        a = model(d_imgs, d_proj, d_dv, return_features=True)
+    feats_a = a["features"]
+    assert len(feats_a) == 3 and set(feats_a[0]) == {"stage1", "stage2", "stage3"}
+    assert feats_a[0]["stage1"].data_ptr() != feats_a[1]["stage1"].data_ptr()       # the caller's own copies
+    feats_b = [feats_a[v] for v in order]
+    patterns = (("full", feats_b), ("partial", [None] + feats_b[1:]), ("mixed", [feats_b[0], None, feats_b[2]]), ("none", None))
+    # eager, noise replayed from the oracle run: every cache pattern against the oracle
+    for name, feats in patterns:
+        _patch_noise(monkeypatch, mk())
+        with torch.no_grad():
+            out = model(d_imgs_b, d_proj_b, d_dv, features=feats)
+        for i, (d, r) in enumerate(zip(out["depth"], ref["depth"])):
+            e = rel_l1(d, r)
+            REPORT.append(("cas_tiny", f"feature cache [{name}] depth[{i}] vs oracle", e))
+            assert e < DEPTH_TOL, (name, i, e)
+    monkeypatch.undo()
+    # CUDA-graph replay (noise from the CUDA generator, which a graph can consume): equal to the eager call with the same
+    # seed for every pattern (a different batch size may pick another back end: last-ulp differences allowed)
+    for name, feats in patterns:
+        model.use_cuda_graph(False)
+        torch.manual_seed(31)
+        eager = model(d_imgs_b, d_proj_b, d_dv, features=feats)
+        model.use_cuda_graph(True)
+        torch.manual_seed(31)
+        graphed = model(d_imgs_b, d_proj_b, d_dv, features=feats)      # captures, then replays
+        torch.manual_seed(31)
+        again = model(d_imgs_b, d_proj_b, d_dv, features=feats)
+        for x, y, z in zip(eager["depth"], graphed["depth"], again["depth"]):
+            assert rel_l1(y, x) < 1e-5 and torch.equal(y, z), name
+    model.use_cuda_graph(False)
     with pytest.raises(ValueError):
-        bad = [dict(f) for f in feats]
+        bad = [dict(f) for f in feats_b]
         bad[1]["stage1"] = bad[1]["stage1"][:, :-1]
-        run(features=bad)
+        model(d_imgs_b, d_proj_b, d_dv, features=bad)
+
+
+def test_scan_runner_reuses_pyramids():
+    """`scan.ScanRunner`: a sliding window of reference views encodes each image once; outputs equal the uncached call."""
+    from diffmvs_b200.scan import ScanRunner
+    args = synth.workload_args("cas_tiny")
+    sd = synth.synth_state_dict(spec.state_dict_shapes(args), 123)
+    model = _build(args, sd)
+    imgs, proj, dv = _to_dev(*synth.workload_inputs("cas_tiny"))
+    pool = imgs + [i.flip(-1).contiguous() for i in imgs]                 # six distinct images
+    runner = ScanRunner(model, capacity=8)
+    for start in range(4):
+        ids = [start, start + 1, start + 2]
+        batch = [pool[i] for i in ids]
+        torch.manual_seed(100 + start)
+        got = runner(ids, batch, proj, dv)
+        torch.manual_seed(100 + start)
+        want = model(batch, proj, dv)
+        assert all(rel_l1(x, y) < 1e-5 for x, y in zip(got["depth"], want["depth"]))
+    assert runner.cache.misses == 6 and runner.cache.hits == 6       # 3 new images in the first call, then one per call
 
 
 def test_zz_report():
