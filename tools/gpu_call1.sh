@@ -12,5 +12,5 @@ tail -40 $O/pytest_gpu.log
 timeout 600 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-alt-modes > $O/bench_cfg4.log 2>&1
 echo "bench cfg4 rc=$?" >> $O/bench_cfg4.log
 tail -2 $O/bench_cfg4.log | cut -c1-1500
-timeout 600 python bench.py --steps 10 --warmup 3 --no-alt-modes --no-cpu-baseline > $O/bench_cfg3.log 2>&1
+timeout 600 python bench.py --steps 10 --warmup 3 --no-alt-modes --no-cpu-baseline --no-gpu-baseline > $O/bench_cfg3.log 2>&1
 tail -1 $O/bench_cfg3.log | cut -c1-600
