@@ -120,10 +120,50 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(int N, int iters, int tap
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "r"(tmem_cols));
 }
 
+// 1b. the same with consecutive MMAs spread round-robin over G accumulators (independent chains): separates a
+// dependent-accumulation latency from a per-instruction issue floor
+__global__ void __launch_bounds__(128) mma_chain_kernel(int N, int iters, int G, int kslices, long long* cycles_out) {
+  extern __shared__ __align__(1024) float smem[];
+  const int plane = 2048;
+  float* A_s = smem;                          // [2*kslices][plane][4]
+  float* B_s = smem + 2 * kslices * plane * 4;   // [2*kslices][N][4]
+  __shared__ uint32_t tmem_base;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 2 * kslices * (plane + N) * 4; i += 128) smem[i] = (float)((i * 37) % 19 - 9) * 0.125f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;\n"); }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tb = tmem_base;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(N);
+    const uint64_t da0 = umma_desc(smem_u32(A_s), plane * 16, 128, 0), db0 = umma_desc(smem_u32(B_s), N * 16, 128, 0);
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int g = it % G;
+      for (int ks = 0; ks < kslices; ++ks)   // kslices back-to-back K=8 MMAs into the same accumulator (a K=8*kslices stage)
+        umma_tf32(tb + (uint32_t)(g * N), da0 + (uint32_t)(ks * 2 * plane + (it & 7) * 128), db0 + (uint32_t)(ks * 2 * N), idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    const long long t1 = clock64();
+    if (blockIdx.x == 0) *cycles_out = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tb), "r"(512));
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // 2. TMA tile streaming
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kRing = 4;
+constexpr int kRing = 2;
 __global__ void __launch_bounds__(64) tma_stream_kernel(const __grid_constant__ CUtensorMap map, int C, int bc, int TH, int TW, int in_rows,
                                                         int in_cols, int tiles_x, int tiles_y, int total_tiles, float* sink) {
   extern __shared__ __align__(1024) float smem[];
@@ -289,6 +329,24 @@ int main() {
       CHECK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
       printf("mma M128 N%3d K8 tf32 SS, %d CTA/SM: %.1f clk per MMA (CTA 0)  [A read 4096 B + B read %d B]\n", N, ctas,
              (double)cyc / (iters * taps), N * 32);
+    }
+  }
+
+  // ---- 1b. dependent chain vs independent accumulators ----
+  CHECK(cudaFuncSetAttribute(mma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  for (int N : {32, 48, 96}) {
+    for (int kslices : {1, 2}) {
+      for (int G : {1, 2, 3, 4, 8}) {
+        if (G * N > 512) continue;
+        const int iters = 1200;
+        const size_t smem = (size_t)2 * kslices * (2048 + N) * 16;
+        mma_chain_kernel<<<sms, 128, smem>>>(N, iters, G, kslices, d_cyc);
+        CHECK(cudaDeviceSynchronize());
+        long long cyc;
+        CHECK(cudaMemcpy(&cyc, d_cyc, 8, cudaMemcpyDeviceToHost));
+        printf("mma chain N%3d, %d K-slices per accumulator visit, %d accumulators round-robin: %.1f clk per MMA\n", N, kslices, G,
+               (double)cyc / (iters * kslices));
+      }
     }
   }
 
