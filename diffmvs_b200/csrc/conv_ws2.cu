@@ -2,15 +2,17 @@
 // layouts of conv_ws.cu (kernel-row taps stacked along N, 3xTF32, shift-add epilogue - see the header of that file)
 // behind a fully asynchronous, role-specialised pipeline:
 //
-//   warp 0      TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
+//   warp 16     TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
 //                              hardware zero fill = the convolution's padding) + cp.async.bulk of the stage's weight
 //                              slabs, all completing on tma_full[slot] (mbarrier transaction count)
-//   warps 2-9   split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
+//   warps 8-15  split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
 //                              fence.proxy.async and one arrival per warp on op_full[slot]
-//   warp 1      MMA issuer     one elected lane issues the row MMAs x3 passes into one of TWO TMEM accumulator sets;
-//                              tcgen05.commit frees the ring slot (empty[slot]) and, after a tile's last stage,
-//                              publishes the accumulators (acc_full[set])
-//   warps 10-13 epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
+//   warps 0-3   MMA issuers    FOUR issuing threads, one per scheduler, M blocks dealt round-robin: measured on B200
+//                              (profiles/r2_pipe_probe*.txt) a single thread sustains one tcgen05.mma per ~70-100 clk
+//                              of its own descriptor arithmetic, while an M128 x N48 x K8 TF32 MMA occupies the tensor
+//                              pipe for 24 clk - one issuer starves it.  Each issuer commits to empty[slot] (ring slot
+//                              free) and, after a tile's last stage, to acc_full[set] (accumulators complete)
+//   warps 4-7   epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
 //                              t+1 fill the other set; acc_empty[set] hands the set back
 //
 // One persistent CTA per SM; the ring is R = 2..4 stages deep, a stage = (tile, depth tap, stride phase, 8 input
@@ -27,11 +29,13 @@ namespace {
 
 using namespace tc;
 
-constexpr int kSplitWarps = 8;
-constexpr int kEpiWarps = 4;                                       // warp % 4 = TMEM lane quadrant
-constexpr int kFirstSplitWarp = 2;
-constexpr int kFirstEpiWarp = kFirstSplitWarp + kSplitWarps;      // 10: 10 % 4 = 2, 11 -> 3, 12 -> 0, 13 -> 1
-constexpr int kWs2Threads = 32 * (kFirstEpiWarp + kEpiWarps);     // 448
+constexpr int kMmaWarps = 4;                                       // warps 0-3: one MMA-issuing thread per scheduler
+constexpr int kEpiWarps = 4;                                       // warps 4-7: warp % 4 = TMEM lane quadrant
+constexpr int kSplitWarps = 8;                                     // warps 8-15
+constexpr int kFirstEpiWarp = kMmaWarps;
+constexpr int kFirstSplitWarp = kFirstEpiWarp + kEpiWarps;
+constexpr int kTmaWarp = kFirstSplitWarp + kSplitWarps;           // warp 16
+constexpr int kWs2Threads = 32 * (kTmaWarp + 1);                  // 544
 constexpr int kSplitThreads = 32 * kSplitWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kMaxRing = 4;
@@ -96,10 +100,10 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&tma_full[i], 1);
       mbar_init(&op_full[i], kSplitWarps);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kMmaWarps);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_full[i], kMmaWarps);
       mbar_init(&acc_empty[i], kEpiWarps);
     }
     mbar_init_fence();
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
 
   Stage cur = first_stage_of((int)blockIdx.x);
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // =============================== TMA producer ==================================================================
     if (elect_one()) {
       int slot = 0, use = 0;
@@ -171,12 +175,16 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         if (++slot == a.R) { slot = 0; ++use; }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ====================================================================
+  } else if (warp < kMmaWarps) {
+    // =============================== MMA issuers ===================================================================
+    // warp w issues the MMAs of M blocks w, w + 4, ...; the descriptors' upper words are constant, the lower words
+    // (start address field) advance by plain 32-bit adds, so one kernel row costs a handful of scalar instructions
     const bool leader = elect_one();
     const uint32_t idesc = idesc_tf32_m128(N);
     const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
     const uint32_t b_step = 2u * (uint32_t)N;                // one kernel row of weights, in 16-byte units
+    const uint32_t a_hiword = (uint32_t)(umma_desc(0, lbo_a, 128) >> 32), b_hiword = (uint32_t)(umma_desc(0, lbo_b, 128) >> 32);
+    const uint32_t a_lbo = (uint32_t)umma_desc(0, lbo_a, 128), b_lbo = (uint32_t)umma_desc(0, lbo_b, 128);   // LBO field, address 0
     int slot = 0, use = 0;
     int acc = 0, acc_use = 0;                                // accumulator set of the current tile / earlier uses of that set
     bool tile_start = true;
@@ -187,11 +195,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       }
       mbar_wait(&op_full[slot], (uint32_t)(use & 1));        // operands of this stage are split and fenced
       fence_tc_after();
-      float* a_hi = hi0 + slot * a.stage_f;
-      float* a_lo = lo0 + slot * a.stage_f;
-      const uint64_t dah0 = umma_desc(smem_u32(a_hi), lbo_a, 128), dal0 = umma_desc(smem_u32(a_lo), lbo_a, 128);
-      const uint64_t dbh0 = umma_desc(smem_u32(w_hi0 + slot * a.wslab_f), lbo_b, 128);
-      const uint64_t dbl0 = umma_desc(smem_u32(w_lo0 + slot * a.wslab_f), lbo_b, 128);
+      const uint32_t ah = a_lbo | (smem_u32(hi0 + slot * a.stage_f) >> 4), al = a_lbo | (smem_u32(lo0 + slot * a.stage_f) >> 4);
+      const uint32_t bh = b_lbo | (smem_u32(w_hi0 + slot * a.wslab_f) >> 4), bl = b_lbo | (smem_u32(w_lo0 + slot * a.wslab_f) >> 4);
       const int pa = a.S == 2 ? (cur.phase >> 1) : 0;
       uint32_t rows = 0;   // kernel rows present in this phase: shift khe <-> kernel row S*(khe + smin_h) + pa + pad_h
       for (int khe = 0; khe < a.KHe; ++khe) {
@@ -199,25 +204,27 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         if (kh >= 0 && kh < d.KH) rows |= 1u << khe;
       }
       const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
-      for (int blk = 0; blk < a.n_blk; ++blk) {
-        const uint32_t d_tmem = acc_base + (uint32_t)(blk * N);
-        uint32_t accum = tile_start ? 0u : 1u;
-        uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
-        for (int khe = 0; khe < a.KHe; ++khe, a_off += (uint32_t)a.in_cols, b_off += b_step) {
-          if (!((rows >> khe) & 1u)) continue;
-          if (leader) {
-            umma_tf32(d_tmem, dal0 + a_off, dbh0 + b_off, idesc, accum);
-            umma_tf32(d_tmem, dah0 + a_off, dbl0 + b_off, idesc, 1u);
-            umma_tf32(d_tmem, dah0 + a_off, dbh0 + b_off, idesc, 1u);
+      if (leader) {
+        for (int blk = warp; blk < a.n_blk; blk += kMmaWarps) {
+          const uint32_t d_tmem = acc_base + (uint32_t)(blk * N);
+          uint32_t accum = tile_start ? 0u : 1u;
+          uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
+          uint32_t r = rows;
+#pragma unroll 1
+          for (int khe = 0; khe < a.KHe; ++khe, a_off += (uint32_t)a.in_cols, b_off += b_step, r >>= 1) {
+            if (!(r & 1u)) continue;
+            umma_tf32_w(d_tmem, al + a_off, a_hiword, bh + b_off, b_hiword, idesc, accum);
+            umma_tf32_w(d_tmem, ah + a_off, a_hiword, bl + b_off, b_hiword, idesc, 1u);
+            umma_tf32_w(d_tmem, ah + a_off, a_hiword, bh + b_off, b_hiword, idesc, 1u);
+            accum = 1u;
           }
-          accum = 1u;
         }
       }
       const Stage nxt = advance(cur);
       const bool tile_end = nxt.tile != cur.tile;
       if (leader) {
-        umma_commit(&empty_bar[slot]);                        // slot reusable once every MMA issued so far has retired
-        if (tile_end) umma_commit(&acc_full[acc]);            // ... and the tile's accumulators are complete
+        umma_commit(&empty_bar[slot]);                        // this issuer's MMAs on the slot have retired (4 arrivals free it)
+        if (tile_end) umma_commit(&acc_full[acc]);            // ... and its share of the tile's accumulators is complete
       }
       __syncwarp();
       tile_start = tile_end;
@@ -225,7 +232,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       cur = nxt;
       if (++slot == a.R) { slot = 0; ++use; }
     }
-  } else if (warp < kFirstEpiWarp) {
+  } else if (warp >= kFirstSplitWarp) {
     // =============================== split workers ================================================================
     const int wtid = tid - 32 * kFirstSplitWarp;
     int slot = 0, use = 0, gn_n = -1;

@@ -33,6 +33,17 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t
       : "memory");
 }
 
+// the same with the descriptors given as (lower word, upper word) pairs: the upper words (SBO, version, layout) are
+// loop invariant, the lower words (start address, LBO) advance by 32-bit adds
+__device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // arrives on `bar` once every MMA issued so far by this thread has retired (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
