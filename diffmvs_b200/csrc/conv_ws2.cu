@@ -2,18 +2,22 @@
 // layouts of conv_ws.cu (kernel-row taps stacked along N, 3xTF32, shift-add epilogue - see the header of that file)
 // behind a fully asynchronous, role-specialised pipeline:
 //
-//   warp 16     TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
+//   warp 20     TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
 //                              hardware zero fill = the convolution's padding) + cp.async.bulk of the stage's weight
 //                              slabs, all completing on tma_full[slot] (mbarrier transaction count)
-//   warps 8-15  split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
+//   warps 12-19 split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
 //                              fence.proxy.async and one arrival per warp on op_full[slot]
 //   warps 0-3   MMA issuers    FOUR issuing threads, one per scheduler, M blocks dealt round-robin: measured on B200
 //                              (profiles/r2_pipe_probe*.txt) a single thread sustains one tcgen05.mma per ~70-100 clk
 //                              of its own descriptor arithmetic, while an M128 x N48 x K8 TF32 MMA occupies the tensor
 //                              pipe for 24 clk - one issuer starves it.  Each issuer commits to empty[slot] (ring slot
 //                              free) and, after a tile's last stage, to acc_full[set] (accumulators complete)
-//   warps 4-7   epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
-//                              t+1 fill the other set; acc_empty[set] hands the set back
+//   warps 4-11  epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
+//                              t+1 fill the other set; acc_empty[set] hands the set back.  Two warps per TMEM lane
+//                              quadrant and a specialised straight-line path for the common bias/ReLU/residual case:
+//                              a single warp executes its ~150-400 dependent instructions per 32x16 output block at
+//                              ~6 clk each (ncu: stall_wait / short_scoreboard), so the epilogue - not the tensor pipe
+//                              - bounds the layers with few input channels unless it is both short and parallel
 //
 // One persistent CTA per SM; the ring is R = 2..4 stages deep, a stage = (tile, depth tap, stride phase, 8 input
 // channels).  Compared with conv_ws.cu nothing in a CTA waits for global-memory latency any more: the producer runs up
@@ -30,12 +34,12 @@ namespace {
 using namespace tc;
 
 constexpr int kMmaWarps = 4;                                       // warps 0-3: one MMA-issuing thread per scheduler
-constexpr int kEpiWarps = 4;                                       // warps 4-7: warp % 4 = TMEM lane quadrant
-constexpr int kSplitWarps = 8;                                     // warps 8-15
+constexpr int kEpiWarps = 8;                                       // warps 4-11: warp % 4 = TMEM lane quadrant, two warps per quadrant
+constexpr int kSplitWarps = 8;                                     // warps 12-19
 constexpr int kFirstEpiWarp = kMmaWarps;
 constexpr int kFirstSplitWarp = kFirstEpiWarp + kEpiWarps;
-constexpr int kTmaWarp = kFirstSplitWarp + kSplitWarps;           // warp 16
-constexpr int kWs2Threads = 32 * (kTmaWarp + 1);                  // 544
+constexpr int kTmaWarp = kFirstSplitWarp + kSplitWarps;           // warp 20
+constexpr int kWs2Threads = 32 * (kTmaWarp + 1);                  // 672
 constexpr int kSplitThreads = 32 * kSplitWarps;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kMaxRing = 4;
@@ -63,6 +67,7 @@ struct alignas(64) Ws2Args {
   int wslab_f;           // floats per weight slab (KHe * 2 * N * 4)
   int halo_f;            // floats of ONE halo exchange buffer (two are allocated, alternating per tile)
   int vec_y, vec_res, vec_bias;
+  int fast_epi;          // 1: the epilogue's straight-line path applies (see the kernel)
   float inv_in_cols;
   int64_t w_off;         // offset (floats) of this launch's hi slabs inside w_ws
   int64_t w_plane;       // distance (floats) from a hi slab to its lo twin
@@ -299,54 +304,82 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     // lane quadrant / next M block (a small shared "halo", written in a first pass).  Warp w handles TMEM lane quadrant
     // w % 4 of every M block.
     const int quadrant = warp & 3;
+    const int half = (warp - kFirstEpiWarp) >> 2;          // the two warps of a quadrant take alternate work items
     const int etid = tid - 32 * kFirstEpiWarp;
-    auto epilogue = [&](auto nch_tag, int n, int od, int ty0, int tx0, uint32_t acc_base, float* halo, unsigned long long* stat) {
+    // FAST: the straight-line path - standard epilogue with optional bias, optional residual (before or after the
+    // activation), ReLU on all channels or none, every access a full 128-bit vector (host-checked)
+    auto epilogue = [&](auto nch_tag, auto kwe_tag, auto fast_tag, int n, int od, int ty0, int tx0, uint32_t acc_base,
+                        uint32_t halo_sa, unsigned long long* stat) {
       constexpr int NCH = decltype(nch_tag)::value;
+      constexpr int KWT = decltype(kwe_tag)::value;         // 1, 3 or 0 (= run-time kernel width)
+      constexpr bool FAST = decltype(fast_tag)::value;
+      const int KWe = KWT ? KWT : a.KWe, KWm1 = KWe - 1;
       const int ncg = a.CC / NCH;
       const int n_items = a.n_blk * ncg;                    // (block, channel group) pairs, block-major
-      const int KWe = a.KWe, KWm1 = KWe - 1;
       const int halo_q = KWm1 * KWm1 * NCH;                 // floats per (item, quadrant)
       const bool plain = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || d.act == DMVS_ACT_RELU);
       const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
       const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
+      const uint32_t tquad = acc_base + ((uint32_t)(quadrant * 32) << 16);
       if (KWm1 > 0) {
-        int blk = 0, cg = 0;
+        int blk = 0, cg = half;                              // items half, half + 2, ...
+        while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
-        for (int it = 0; it < n_items; ++it) {              // pass 1: rows other quadrants will need
-          const uint32_t trow = acc_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * NCH);
-          float* hq = halo + (it * 4 + quadrant) * halo_q;
-#pragma unroll 1
-          for (int kw = 1; kw < KWe; ++kw) {
-            float v[NCH];
-            tmem_ld<NCH>(trow + (uint32_t)(kw * a.CC), v);
+        for (int it = half; it < n_items; it += 2) {        // pass 1: the first KW-1 rows of this quadrant, for its predecessor
+          const uint32_t trow = tquad + (uint32_t)(blk * N + cg * NCH);
+          const uint32_t hq = halo_sa + (uint32_t)((it * 4 + quadrant) * halo_q) * 4u;
+          if (KWT == 3) {
+            float v1[NCH], v2[NCH];
+            tmem_ld<NCH>(trow + (uint32_t)a.CC, v1);
+            tmem_ld<NCH>(trow + (uint32_t)(2 * a.CC), v2);
             tmem_wait_ld();
-            tmem_pin(v);
-            if (lane < kw) {
-              float* dst = hq + ((kw - 1) * KWm1 + lane) * NCH;
+            tmem_pin(v1);
+            tmem_pin(v2);
+            if (lane < 2) {
+              if (lane == 0) {
 #pragma unroll
-              for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < NCH; j += 4) sts128(hq + (uint32_t)j * 4u, make_float4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]));
+              }
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4)
+                sts128(hq + (uint32_t)((2 + lane) * NCH + j) * 4u, make_float4(v2[j], v2[j + 1], v2[j + 2], v2[j + 3]));
+            }
+          } else {
+#pragma unroll 1
+            for (int kw = 1; kw < KWe; ++kw) {
+              float v[NCH];
+              tmem_ld<NCH>(trow + (uint32_t)(kw * a.CC), v);
+              tmem_wait_ld();
+              tmem_pin(v);
+              if (lane < kw) {
+#pragma unroll
+                for (int j = 0; j < NCH; j += 4)
+                  sts128(hq + (uint32_t)(((kw - 1) * KWm1 + lane) * NCH + j) * 4u, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+              }
             }
           }
-          if (++cg == ncg) { cg = 0; ++blk; }
+          cg += 2;
+          while (cg >= ncg) { cg -= ncg; ++blk; }
         }
         asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // epilogue warps only: halo visible
       }
-      int blk = 0, cg = 0;
+      int blk = 0, cg = half;
+      while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
-      for (int it = 0; it < n_items; ++it) {                // pass 2: shift-add, fused epilogue, store
-        const uint32_t trow = acc_base + ((uint32_t)(quadrant * 32) << 16) + (uint32_t)(blk * N + cg * NCH);
+      for (int it = half; it < n_items; it += 2) {          // pass 2: shift-add, fused epilogue, store
+        const uint32_t trow = tquad + (uint32_t)(blk * N + cg * NCH);
         const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
-        const float* hn = halo + ((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q;
+        const uint32_t hn = halo_sa + (uint32_t)(((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q) * 4u;
         // value of tap kw for this lane's output: row of lane + kw (shuffle) or the halo of the next quadrant / block
         auto shift_in = [&](float (&v)[NCH], int kw) {
 #pragma unroll
           for (int j = 0; j < NCH; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
           if (lane + kw >= 32) {
             if (have_next) {
-              const float* src = hn + ((kw - 1) * KWm1 + (lane + kw - 32)) * NCH;
+              const uint32_t src = hn + (uint32_t)(((kw - 1) * KWm1 + (lane + kw - 32)) * NCH) * 4u;
 #pragma unroll
               for (int j = 0; j < NCH; j += 4) {
-                const float4 h4 = *reinterpret_cast<const float4*>(src + j);
+                const float4 h4 = lds128(src + (uint32_t)j * 4u);
                 v[j] = h4.x; v[j + 1] = h4.y; v[j + 2] = h4.z; v[j + 3] = h4.w;
               }
             } else {
@@ -355,6 +388,13 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
             }
           }
         };
+        const int c0 = a.co_base + cg * NCH;                  // first absolute output channel of this lane
+        const int p = blk * 128 + quadrant * 32 + lane;
+        const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
+        const int px = p - py * a.in_cols;
+        const int oy = ty0 + py, ox = tx0 + px;
+        const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && (FAST || c0 < d.Cout);
+        const int64_t opix = (img_base + oy) * d.Wo + ox;
         float acc[NCH];
         if (KWe == 3) {
           float v1[NCH], v2[NCH];
@@ -384,16 +424,51 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
             for (int j = 0; j < NCH; ++j) acc[j] += v[j];
           }
         }
-        const int c0 = a.co_base + cg * NCH;                  // first absolute output channel of this lane
-        const int p = blk * 128 + quadrant * 32 + lane;
-        const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
-        const int px = p - py * a.in_cols;
-        const int oy = ty0 + py, ox = tx0 + px;
-        const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && c0 < d.Cout;
         float ps[NCH / 2], pq[NCH / 2];                       // per channel pair: sum, sum of squares
 #pragma unroll
         for (int j = 0; j < NCH / 2; ++j) ps[j] = pq[j] = 0.0f;
-        if (valid) {
+        if (FAST) {
+          if (valid) {
+            if (d.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4) {
+                const float4 b4 = ldg4(d.bias + c0 + j);
+                acc[j] += b4.x; acc[j + 1] += b4.y; acc[j + 2] += b4.z; acc[j + 3] += b4.w;
+              }
+            }
+            const bool relu = d.act == DMVS_ACT_RELU;
+            if (d.res_mode != DMVS_RES_NONE) {
+              int64_t rpix = opix;
+              if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
+              const float* rp = d.res + rpix * d.res_ps + c0;
+              const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
+#pragma unroll
+              for (int j = 0; j < NCH; j += 4) {
+                const float4 r4 = ldg4(rp + j);
+                const float r[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  float x = pre_act ? acc[j + k] + r[k] : acc[j + k];
+                  if (relu) x = fmaxf(x, 0.0f);
+                  acc[j + k] = pre_act ? x : x + r[k];
+                }
+              }
+            } else if (relu) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) acc[k] = fmaxf(acc[k], 0.0f);
+            }
+            float* yp = d.y + opix * d.y_ps + c0;
+#pragma unroll
+            for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (d.out_stats != nullptr) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                ps[k >> 1] += acc[k];
+                pq[k >> 1] += acc[k] * acc[k];
+              }
+            }
+          }
+        } else if (valid) {
           const bool full = c0 + NCH <= d.Cout;
           if (d.bias != nullptr) {
             if (a.vec_bias && full) {
@@ -408,7 +483,6 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
                 if (c0 + k < d.Cout) acc[k] += __ldg(d.bias + c0 + k);
             }
           }
-          const int64_t opix = (img_base + oy) * d.Wo + ox;
           int64_t rpix = opix;
           if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
           if (plain) {   // bias (+ residual before / after) + optional ReLU, inline
@@ -432,7 +506,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
                 if (c0 + k >= relu_from) x = fmaxf(x, 0.0f);
                 acc[k] = pre_act ? x : x + r[k];
               }
-            } else if (relu_from <= c0) {                     // the common case: ReLU on every channel
+            } else if (relu_from <= c0) {                     // ReLU on every channel
 #pragma unroll
               for (int k = 0; k < NCH; ++k) acc[k] = fmaxf(acc[k], 0.0f);
             } else if (relu_from < c0 + NCH) {
@@ -469,16 +543,17 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           const int cpg = d.Cout >> 2;
 #pragma unroll
           for (int j = 0; j < NCH / 2; ++j) {
-            const float s = warp_sum(ps[j]), q = warp_sum(pq[j]);
+            const float sv = warp_sum(ps[j]), qv = warp_sum(pq[j]);
             const int c = c0 + 2 * j;
             if (lane == 0 && c < d.Cout) {
               const int g = c / cpg;
-              atomicAdd(&stat[g * 2 + 0], stat_fixed(s));
-              atomicAdd(&stat[g * 2 + 1], stat_fixed(q));
+              atomicAdd(&stat[g * 2 + 0], stat_fixed(sv));
+              atomicAdd(&stat[g * 2 + 1], stat_fixed(qv));
             }
           }
         }
-        if (++cg == ncg) { cg = 0; ++blk; }
+        cg += 2;
+        while (cg >= ncg) { cg -= ncg; ++blk; }
       }
       if (d.out_stats != nullptr) {
         asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // every epilogue warp's shared atomics are in
@@ -486,6 +561,18 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           atomicAdd(reinterpret_cast<unsigned long long*>(d.out_stats) + n * 8 + etid, stat[etid]);
           stat[etid] = 0ull;                                   // ready for the tile after next (same buffer)
         }
+      }
+    };
+    auto run_epilogue = [&](auto nch_tag, int n, int od, int ty0, int tx0, uint32_t acc_base, uint32_t halo_sa,
+                            unsigned long long* stat) {
+      using T = std::true_type;
+      using F = std::false_type;
+      if (a.fast_epi) {
+        if (a.KWe == 3) epilogue(nch_tag, std::integral_constant<int, 3>{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+        else if (a.KWe == 1) epilogue(nch_tag, std::integral_constant<int, 1>{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+        else epilogue(nch_tag, std::integral_constant<int, 0>{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+      } else {
+        epilogue(nch_tag, std::integral_constant<int, 0>{}, F{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
       }
     };
 
@@ -496,11 +583,11 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       mbar_wait(&acc_full[acc], (uint32_t)((t_local >> 1) & 1));
       fence_tc_after();
       const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
-      float* halo = halo0 + acc * a.halo_f;
+      const uint32_t halo_sa = smem_u32(halo0 + acc * a.halo_f);
       if ((a.CC & 15) == 0)
-        epilogue(std::integral_constant<int, 16>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo, stat_s[acc]);
+        run_epilogue(std::integral_constant<int, 16>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo_sa, stat_s[acc]);
       else
-        epilogue(std::integral_constant<int, 8>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo, stat_s[acc]);
+        run_epilogue(std::integral_constant<int, 8>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo_sa, stat_s[acc]);
       fence_tc_before();                                     // TMEM reads ordered before the hand-back
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -638,6 +725,9 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
     a.co_base = co_base;
     a.CC = CC;
     a.N = N;
+    // straight-line epilogue: standard bias / residual / ReLU-on-all-channels arithmetic on whole 128-bit vectors
+    a.fast_epi = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || (d.act == DMVS_ACT_RELU && d.act_c0 <= 0)) && a.vec_y &&
+                 (d.bias == nullptr || a.vec_bias) && (d.res_mode == DMVS_RES_NONE || a.vec_res) && co_base + CC <= d.Cout;
     a.TH = t.TH;
     a.TW = t.TW;
     a.in_rows = t.TH + a.KHe - 1;

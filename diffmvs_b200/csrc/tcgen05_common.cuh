@@ -61,6 +61,16 @@ __device__ __forceinline__ void fence_tc_after() { asm volatile("tcgen05.fence::
 // generic-proxy writes of this thread become visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+// 128-bit shared-memory accesses by 32-bit shared address (a generic pointer costs an S2UR + address conversion per use)
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+
 // ---- mbarriers ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
