@@ -49,6 +49,7 @@ SIGNATURES = {
     "dmvs_conv_backends": (C.c_int, [C.POINTER(ConvDesc)]),
     "dmvs_conv_ws_plan": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i32]),
     "dmvs_conv_ws2_plan": (C.c_int, [C.POINTER(ConvDesc), C.POINTER(C.c_int32), i32]),
+    "dmvs_conv_ws2_timeline": (C.c_int, [C.POINTER(C.c_int64), i32]),
     "dmvs_deconv3d_f32": (C.c_int, [f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_compose_homographies": (C.c_int, [f32p, f32p, i32, i32, C.c_void_p]),
     "dmvs_warp_volume": (C.c_int, [f32p, i32, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]),

@@ -346,6 +346,11 @@ extern "C" int dmvs_conv_ws2_plan(const dmvs_conv_desc* dp, int32_t* out, int32_
   return plan_conv_ws2(*dp, out, cap);
 }
 
+extern "C" int dmvs_conv_ws2_timeline(int64_t* out, int32_t count) {
+  if (out == nullptr || count <= 0) return DMVS_ERR_ARG;
+  return read_ws2_debug(reinterpret_cast<long long*>(out), count);
+}
+
 extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   if (dp == nullptr) return DMVS_ERR_ARG;
   const dmvs_conv_desc& d = *dp;

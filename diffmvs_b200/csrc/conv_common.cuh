@@ -236,5 +236,6 @@ int plan_conv_ws(const dmvs_conv_desc& d, int32_t* out, int cap);   // tile plan
 bool conv_ws2_supported(const dmvs_conv_desc& d);
 int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t stream);
 int plan_conv_ws2(const dmvs_conv_desc& d, int32_t* out, int cap);
+int read_ws2_debug(long long* host_out, int count);   // DMVS_WS2_DBG=1: clock stamps of CTA 0 of the last ws2 launch
 
 }  // namespace dmvs

@@ -71,7 +71,18 @@ struct alignas(64) Ws2Args {
   float inv_in_cols;
   int64_t w_off;         // offset (floats) of this launch's hi slabs inside w_ws
   int64_t w_plane;       // distance (floats) from a hi slab to its lo twin
+  long long* dbg;        // optional pipeline timeline of CTA 0 (DMVS_WS2_DBG=1): [kDbgRoles][kDbgSlots] clock64 stamps
 };
+
+constexpr int kDbgRoles = 12, kDbgSlots = 64;
+// stamps: 0 producer: stage issued | 1 split: stage landed | 2 split: stage split | 3 MMA: operands ready |
+//         4 MMA: stage issued | 5 epilogue: accumulators ready | 6 epilogue: tile stored | 7 MMA: waited for accumulator set
+//         8 epilogue: halo rows loaded | 9 epilogue: halo barrier passed | 10 first item's accumulators in registers |
+//         11 first item stored
+#define WS2_STAMP(role, idx)                                                                                  \
+  do {                                                                                                        \
+    if (a.dbg != nullptr && blockIdx.x == 0 && (idx) < kDbgSlots && lane == 0) a.dbg[(role) * kDbgSlots + (idx)] = clock64(); \
+  } while (0)
 
 struct Stage {
   int tile, kd, phase, chunk;
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
   if (warp == kTmaWarp) {
     // =============================== TMA producer ==================================================================
     if (elect_one()) {
-      int slot = 0, use = 0;
+      int slot = 0, use = 0, n_issued = 0;
       const uint32_t box_bytes = (uint32_t)a.box_units * 16u, w_bytes = (uint32_t)a.wslab_f * 4u;
       while (cur.tile < a.total_tiles) {
         if (use > 0) mbar_wait(&empty_bar[slot], (uint32_t)((use - 1) & 1));   // the MMAs that read this slot have retired
@@ -176,6 +187,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         const float* wsrc = d.w_ws + a.w_off + (int64_t)((cur.kd * nphase + cur.phase) * nchunks + cur.chunk) * a.wslab_f;
         bulk_load(w_hi0 + slot * a.wslab_f, wsrc, w_bytes, &tma_full[slot]);
         bulk_load(w_lo0 + slot * a.wslab_f, wsrc + a.w_plane, w_bytes, &tma_full[slot]);
+        if (a.dbg != nullptr && blockIdx.x == 0 && n_issued < kDbgSlots) a.dbg[0 * kDbgSlots + n_issued] = clock64();
+        ++n_issued;
         cur = advance(cur);
         if (++slot == a.R) { slot = 0; ++use; }
       }
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     const uint32_t b_step = 2u * (uint32_t)N;                // one kernel row of weights, in 16-byte units
     const uint32_t a_hiword = (uint32_t)(umma_desc(0, lbo_a, 128) >> 32), b_hiword = (uint32_t)(umma_desc(0, lbo_b, 128) >> 32);
     const uint32_t a_lbo = (uint32_t)umma_desc(0, lbo_a, 128), b_lbo = (uint32_t)umma_desc(0, lbo_b, 128);   // LBO field, address 0
-    int slot = 0, use = 0;
+    int slot = 0, use = 0, n_stage = 0;
     int acc = 0, acc_use = 0;                                // accumulator set of the current tile / earlier uses of that set
     bool tile_start = true;
     while (cur.tile < a.total_tiles) {
@@ -198,8 +211,10 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         mbar_wait(&acc_empty[acc], (uint32_t)((acc_use - 1) & 1));
         fence_tc_after();
       }
+      if (warp == 0) WS2_STAMP(7, n_stage);
       mbar_wait(&op_full[slot], (uint32_t)(use & 1));        // operands of this stage are split and fenced
       fence_tc_after();
+      if (warp == 0) WS2_STAMP(3, n_stage);
       const uint32_t ah = a_lbo | (smem_u32(hi0 + slot * a.stage_f) >> 4), al = a_lbo | (smem_u32(lo0 + slot * a.stage_f) >> 4);
       const uint32_t bh = b_lbo | (smem_u32(w_hi0 + slot * a.wslab_f) >> 4), bl = b_lbo | (smem_u32(w_lo0 + slot * a.wslab_f) >> 4);
       const int pa = a.S == 2 ? (cur.phase >> 1) : 0;
@@ -232,6 +247,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         if (tile_end) umma_commit(&acc_full[acc]);            // ... and its share of the tile's accumulators is complete
       }
       __syncwarp();
+      if (warp == 0) WS2_STAMP(4, n_stage);
+      ++n_stage;
       tile_start = tile_end;
       if (tile_end && ++acc == 2) { acc = 0; ++acc_use; }
       cur = nxt;
@@ -240,7 +257,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
   } else if (warp >= kFirstSplitWarp) {
     // =============================== split workers ================================================================
     const int wtid = tid - 32 * kFirstSplitWarp;
-    int slot = 0, use = 0, gn_n = -1;
+    int slot = 0, use = 0, gn_n = -1, n_stage = 0;
     while (cur.tile < a.total_tiles) {
       if (GN && cur.n != gn_n) {                             // GroupNorm affine of the producer is per sample
         asm volatile("bar.sync 1, %0;\n" ::"n"(kSplitThreads) : "memory");
@@ -249,6 +266,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         gn_n = cur.n;
       }
       mbar_wait(&tma_full[slot], (uint32_t)(use & 1));       // raw tile (and weights) of this stage have landed
+      if (warp == kFirstSplitWarp) WS2_STAMP(1, n_stage);
       float* hi = hi0 + slot * a.stage_f;
       float* lo = lo0 + slot * a.stage_f;
       const int iy0 = cur.ty0 + a.smin_h, ix0 = cur.tx0 + a.smin_w;   // GN layers are stride 1
@@ -294,6 +312,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       fence_async_smem();
       __syncwarp();                                          // one arrival per warp: the lanes' writes are ordered before it
       if (lane == 0) mbar_arrive(&op_full[slot]);
+      if (warp == kFirstSplitWarp) WS2_STAMP(2, n_stage);
+      ++n_stage;
       cur = advance(cur);
       if (++slot == a.R) { slot = 0; ++use; }
     }
@@ -306,13 +326,18 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     const int quadrant = warp & 3;
     const int half = (warp - kFirstEpiWarp) >> 2;          // the two warps of a quadrant take alternate work items
     const int etid = tid - 32 * kFirstEpiWarp;
+    int dbg_tile = 0;                                      // tile index for the timeline stamps
     // FAST: the straight-line path - standard epilogue with optional bias, optional residual (before or after the
     // activation), ReLU on all channels or none, every access a full 128-bit vector (host-checked)
-    auto epilogue = [&](auto nch_tag, auto kwe_tag, auto fast_tag, int n, int od, int ty0, int tx0, uint32_t acc_base,
-                        uint32_t halo_sa, unsigned long long* stat) {
+    // ALIGNED: the staged tile is exactly 32 positions wide, so a TMEM lane quadrant is one tile row and the lanes whose
+    // shuffle sources would wrap into the next quadrant are the row's halo columns - never valid outputs: no halo
+    // exchange, no barrier, and (row, column) of a lane need no division
+    auto epilogue = [&](auto nch_tag, auto kwe_tag, auto fast_tag, auto aligned_tag, int n, int od, int ty0, int tx0,
+                        uint32_t acc_base, uint32_t halo_sa, unsigned long long* stat) {
       constexpr int NCH = decltype(nch_tag)::value;
       constexpr int KWT = decltype(kwe_tag)::value;         // 1, 3 or 0 (= run-time kernel width)
       constexpr bool FAST = decltype(fast_tag)::value;
+      constexpr bool ALIGNED = decltype(aligned_tag)::value;
       const int KWe = KWT ? KWT : a.KWe, KWm1 = KWe - 1;
       const int ncg = a.CC / NCH;
       const int n_items = a.n_blk * ncg;                    // (block, channel group) pairs, block-major
@@ -321,7 +346,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       const int relu_from = d.act == DMVS_ACT_RELU ? d.act_c0 : 0x7fffffff;
       const int64_t img_base = (int64_t)(n * d.Do + od) * d.Ho;
       const uint32_t tquad = acc_base + ((uint32_t)(quadrant * 32) << 16);
-      if (KWm1 > 0) {
+      if (!ALIGNED && KWm1 > 0) {
         int blk = 0, cg = half;                              // items half, half + 2, ...
         while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
@@ -361,7 +386,9 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           cg += 2;
           while (cg >= ncg) { cg -= ncg; ++blk; }
         }
+        if (warp == kFirstEpiWarp) WS2_STAMP(8, dbg_tile);
         asm volatile("bar.sync 2, %0;\n" ::"n"(kEpiThreads) : "memory");   // epilogue warps only: halo visible
+        if (warp == kFirstEpiWarp) WS2_STAMP(9, dbg_tile);
       }
       int blk = 0, cg = half;
       while (cg >= ncg) { cg -= ncg; ++blk; }
@@ -374,7 +401,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         auto shift_in = [&](float (&v)[NCH], int kw) {
 #pragma unroll
           for (int j = 0; j < NCH; ++j) v[j] = __shfl_down_sync(0xffffffffu, v[j], kw);
-          if (lane + kw >= 32) {
+          if (!ALIGNED && lane + kw >= 32) {
             if (have_next) {
               const uint32_t src = hn + (uint32_t)(((kw - 1) * KWm1 + (lane + kw - 32)) * NCH) * 4u;
 #pragma unroll
@@ -390,8 +417,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         };
         const int c0 = a.co_base + cg * NCH;                  // first absolute output channel of this lane
         const int p = blk * 128 + quadrant * 32 + lane;
-        const int py = (int)(((float)p + 0.5f) * a.inv_in_cols);
-        const int px = p - py * a.in_cols;
+        const int py = ALIGNED ? blk * 4 + quadrant : (int)(((float)p + 0.5f) * a.inv_in_cols);
+        const int px = ALIGNED ? lane : p - py * a.in_cols;
         const int oy = ty0 + py, ox = tx0 + px;
         const bool valid = px < a.TW && py < a.TH && oy < d.Ho && ox < d.Wo && (FAST || c0 < d.Cout);
         const int64_t opix = (img_base + oy) * d.Wo + ox;
@@ -405,6 +432,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           tmem_pin(acc);
           tmem_pin(v1);
           tmem_pin(v2);
+          if (warp == kFirstEpiWarp && it == half) WS2_STAMP(10, dbg_tile);
           shift_in(v1, 1);
           shift_in(v2, 2);
 #pragma unroll
@@ -413,6 +441,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           tmem_ld<NCH>(trow, acc);
           tmem_wait_ld();
           tmem_pin(acc);
+          if (warp == kFirstEpiWarp && it == half) WS2_STAMP(10, dbg_tile);
 #pragma unroll 1
           for (int kw = 1; kw < KWe; ++kw) {
             float v[NCH];
@@ -552,6 +581,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
             }
           }
         }
+        if (warp == kFirstEpiWarp && it == half) WS2_STAMP(11, dbg_tile);
         cg += 2;
         while (cg >= ncg) { cg -= ncg; ++blk; }
       }
@@ -567,12 +597,20 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
                             unsigned long long* stat) {
       using T = std::true_type;
       using F = std::false_type;
-      if (a.fast_epi) {
-        if (a.KWe == 3) epilogue(nch_tag, std::integral_constant<int, 3>{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
-        else if (a.KWe == 1) epilogue(nch_tag, std::integral_constant<int, 1>{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
-        else epilogue(nch_tag, std::integral_constant<int, 0>{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+      using K0 = std::integral_constant<int, 0>;
+      using K1 = std::integral_constant<int, 1>;
+      using K3 = std::integral_constant<int, 3>;
+      if (a.fast_epi && a.in_cols == 32) {
+        if (a.KWe == 3) epilogue(nch_tag, K3{}, T{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+        else if (a.KWe == 1) epilogue(nch_tag, K1{}, T{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+        else epilogue(nch_tag, K0{}, T{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+      } else if (a.fast_epi) {
+        if (a.KWe == 3) epilogue(nch_tag, K3{}, T{}, F{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+        else epilogue(nch_tag, K0{}, T{}, F{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+      } else if (a.in_cols == 32) {
+        epilogue(nch_tag, K0{}, F{}, T{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
       } else {
-        epilogue(nch_tag, std::integral_constant<int, 0>{}, F{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
+        epilogue(nch_tag, K0{}, F{}, F{}, n, od, ty0, tx0, acc_base, halo_sa, stat);
       }
     };
 
@@ -582,6 +620,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       const int acc = t_local & 1;
       mbar_wait(&acc_full[acc], (uint32_t)((t_local >> 1) & 1));
       fence_tc_after();
+      if (warp == kFirstEpiWarp) WS2_STAMP(5, t_local);
+      dbg_tile = t_local;
       const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
       const uint32_t halo_sa = smem_u32(halo0 + acc * a.halo_f);
       if ((a.CC & 15) == 0)
@@ -591,6 +631,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       fence_tc_before();                                     // TMEM reads ordered before the hand-back
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (warp == kFirstEpiWarp) WS2_STAMP(6, t_local);
     }
   }
   fence_tc_before();
@@ -637,6 +678,12 @@ void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int C
   const size_t smem_limit = 224 * 1024;
   const int max_blk = 256 / N;
   const size_t wslab_f = (size_t)KHe * 2 * N * 4;
+  // Staged tiles exactly 32 positions wide (TW = 33 - KWe output columns) make a TMEM lane quadrant one tile row: the
+  // epilogue then needs no halo exchange between quadrants, no barrier and no index division (measured: the epilogue
+  // warps' instruction issue, not the tensor pipe, bounds the layers with few input channels).  Used whenever the
+  // image is at least that wide; the general shapes remain for narrow maps.
+  static const int no_align = getenv("DMVS_WS2_NOALIGN") ? atoi(getenv("DMVS_WS2_NOALIGN")) : 0;
+  const bool aligned = !no_align && KWe <= 8 && d.Wo >= 33 - KWe;
   for (int th = 32; th >= 1; th >>= 1) {
     if (th > 1 && th / 2 >= d.Ho) continue;          // a shorter tile already covers the image height
     if (force_th && th != force_th) continue;
@@ -647,8 +694,13 @@ void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int C
       if (tw_max > 250) tw_max = 250;
       if (tw_max * S + (KWe - 1) * S > 256) tw_max = 256 / S - (KWe - 1);   // TMA box limit
       if (tw_max < 1 || (tw_max < 8 && tw_max < d.Wo)) continue;
-      const int ntx = ceil_div(d.Wo, tw_max);
-      const int TW = ceil_div(d.Wo, ntx);
+      int ntx = ceil_div(d.Wo, tw_max);
+      int TW = ceil_div(d.Wo, ntx);
+      if (aligned) {
+        if (cols_max < 32 || th * 32 > nb * 128 || (nb > 1 && th * 32 <= (nb - 1) * 128)) continue;   // exactly nb blocks of 4 rows
+        TW = 33 - KWe;
+        ntx = ceil_div(d.Wo, TW);
+      }
       const int in_cols = TW + KWe - 1;
       const int in_rows = th + KHe - 1;
       if (in_rows * S > 256) continue;
@@ -690,6 +742,16 @@ void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int C
 }
 
 }  // namespace
+
+// Pipeline timeline (tuning aid): with DMVS_WS2_DBG=1 every launch stamps CTA 0's first stages into a device buffer
+long long* ws2_debug_buffer() {
+  static long long* buf = nullptr;
+  static const bool on = getenv("DMVS_WS2_DBG") && atoi(getenv("DMVS_WS2_DBG")) != 0;
+  if (on && buf == nullptr) {
+    if (cudaMalloc(&buf, sizeof(long long) * kDbgRoles * kDbgSlots) != cudaSuccess) buf = nullptr;
+  }
+  return on ? buf : nullptr;
+}
 
 bool conv_ws2_supported(const dmvs_conv_desc& d) {
   if (!conv_ws_supported(d)) return false;
@@ -753,6 +815,8 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
     const long tiles = (long)a.tiles_x * a.tiles_y * d.N * d.Do;
     if (tiles > 0x7fffffffL) return DMVS_ERR_UNSUPPORTED;
     a.total_tiles = (int)tiles;
+    a.dbg = plan_out != nullptr ? nullptr : ws2_debug_buffer();
+    if (a.dbg != nullptr) cudaMemsetAsync(a.dbg, 0, sizeof(long long) * kDbgRoles * kDbgSlots, st);
     const int grid = (int)(tiles < (long)kNumSMs ? tiles : (long)kNumSMs);
     if (plan_out != nullptr) {
       if (n_launch < plan_cap) {
@@ -780,6 +844,14 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
     w_off += 2 * plane_w;
   }
   return plan_out != nullptr ? n_launch : 0;
+}
+
+int read_ws2_debug(long long* host_out, int count) {
+  long long* buf = ws2_debug_buffer();
+  if (buf == nullptr) return 0;
+  const int n = count < kDbgRoles * kDbgSlots ? count : kDbgRoles * kDbgSlots;
+  if (cudaMemcpy(host_out, buf, sizeof(long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return n;
 }
 
 int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st) { return dispatch_conv_ws2(d, st, nullptr, 0); }

@@ -137,6 +137,11 @@ int dmvs_conv_backends(const dmvs_conv_desc* desc);
 int dmvs_conv_ws_plan(const dmvs_conv_desc* desc, int32_t* out, int32_t cap);
 /* Same for the TMA-fed width-stacked back end (CTAs per SM is always 1). */
 int dmvs_conv_ws2_plan(const dmvs_conv_desc* desc, int32_t* out, int32_t cap);
+/* Tuning aid: with DMVS_WS2_DBG=1 in the environment the TMA-fed kernel stamps the SM clock of CTA 0's first 64 pipeline
+ * events per role (8 roles x 64 slots: stage issued / landed / split / operands ready / MMAs issued / accumulators ready /
+ * tile stored / accumulator set free); this call synchronises and copies the stamps of the last launch.  Returns the
+ * number of values written, 0 when the facility is off. */
+int dmvs_conv_ws2_timeline(int64_t* out, int32_t count);
 
 /* ConvTranspose3d(k=3, s=2, p=1, output_padding=1) + folded BN + ReLU + skip add
  * (module.Deconv3d as used by CostRegNet_small, module.py:110-144,436-437,445-446).
