@@ -217,6 +217,58 @@ def _config(workload):
                    f"inputs ({V * 3 * H * W * 4 / 1e6:.1f} MB) fit in L2 and L2 is NOT flushed: not a headline configuration")}
 
 
+def _fusion_leg(a, dev, world, rank, H, W, V, timed):
+    """Depth filter + fusion of the scan the ranks just reconstructed (north_star: "a single
+    NCCL gather for the fused point cloud only").  Every rank owns the depth / confidence maps of its reference views;
+    a step = one NCCL all_gather of the depth maps (a reference view's source views may live on other ranks), one fused
+    filter launch per owned reference view against its V-1 neighbours, and the single variable-length NCCL gather of
+    the fused points to rank 0.  Synthetic scan: a tilted plane seen by laterally shifted cameras (tests/helpers)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from diffmvs_b200 import fusion, sharding
+    from tests.helpers import plane_scene
+    per_rank = 2
+    n_views = per_rank * world
+    sc = plane_scene(H, W, n_views, 7)
+    mine = list(sharding.shard_views(n_views, rank, world))
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    local_depth = torch.stack([t(sc["depth"][v]) for v in mine], 0)
+    confs = [t(c) for c in sc["conf"]]
+    img = t(sc["img"])
+    counts = [len(sharding.shard_views(n_views, r, world)) for r in range(world)]
+    n_src = min(V - 1, n_views - 1)
+    neighbours = {v: [u for u in sorted(range(n_views), key=lambda u: (abs(u - v), u)) if u != v][:n_src] for v in mine}
+    mats = {v: torch.from_numpy(np.stack([fusion.pair_matrices(sc["K"], sc["E"][v], sc["K"], sc["E"][u]) for u in neighbours[v]])).to(dev)
+            for v in mine}
+    state = {}
+
+    def step():
+        all_depth = sharding.all_gather_maps(local_depth, counts) if world > 1 else local_depth
+        pts, cols = [], []
+        for i, v in enumerate(mine):
+            src = [(all_depth[u], sc["K"], sc["E"][u]) for u in neighbours[v]]
+            out = fusion.fuse_view(local_depth[i], sc["K"], sc["E"][v], sc["depth_max"], sc["depth_min"], confs, [0.3, 0.5, 0.5], src,
+                                   ref_img=img, geo_mask_thres=min(3, n_src), mats=mats[v])
+            pts.append(out["points"])
+            cols.append(out["colors"])
+        p, c = torch.cat(pts, 0), torch.cat(cols, 0)
+        if world > 1:
+            p, c = sharding.gather_points(p, c, dst=0)
+        state["n"] = 0 if p is None else int(p.shape[0])
+
+    for _ in range(3):
+        step()
+    steps = max(3, a.steps // 2)
+    ms, _ = timed(step, steps)
+    return {"value": n_views * steps / (ms / 1e3), "unit": "fused ref-views/s", "ms_per_step": ms / steps,
+            "ref_views_per_step": n_views, "source_views": n_src, "points_on_rank0": state.get("n"),
+            "all_gather_bytes_per_step": (n_views * H * W * 4) if world > 1 else 0,
+            "exchange": "NCCL all_gather of depth maps + one variable-length NCCL gather of 15-byte point records" if world > 1
+                        else "single GPU: no exchange",
+            "kernel": "fuse_view_kernel (one launch per reference view: all source views, masks, averaged depth, points)"}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -375,6 +427,12 @@ def run_ours(a):
                     "cached_pyramids_per_step": (runner.cache.hits - h0) / a.steps,
                     "note": "FeatureNet pyramids of already-seen images are reused across reference views (scan.ScanRunner, "
                             "LRU on the device); depth maps equal the uncached call (tests/test_gpu_model.py)"}
+        fusion_leg = None
+        if not a.no_fusion:
+            try:
+                fusion_leg = _fusion_leg(a, dev, world, rank, H, W, V, timed)
+            except Exception as e:      # cv2 / test helpers missing: report, do not fail the bench
+                fusion_leg = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         # per-kernel-family device time over one more step (CUDA events on the launch stream)
         model.use_cuda_graph(False)          # per-call events need the eager path
         step_resident()                      # untimed: lets the caching allocator serve this stream without cudaMalloc
@@ -389,7 +447,7 @@ def run_ours(a):
         alt = {}
         if world == 1 and not a.no_alt_modes:
             base = ops.get_precision()
-            for mode in ("tf32x3", "tf32", "fp32"):
+            for mode in ("fp32", "ws_tf32x3", "ws_tf32"):
                 if mode == base:
                     continue
                 ops.set_precision(mode)
@@ -490,6 +548,7 @@ def run_ours(a):
         "cpu_baseline": cpu,
         "gpu_baseline": gpu_base,
         "scan_mode": scan,
+        "fusion": fusion_leg,
         "wall_ms_per_step": ms_wall / a.steps,
     }
     print(json.dumps(line), flush=True)
@@ -508,6 +567,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt-modes", action="store_true")
+    ap.add_argument("--no-fusion", action="store_true", help="skip the depth-filter / point-cloud fusion leg")
     ap.add_argument("--no-scan-mode", action="store_true", help="skip the feature-cache (scan mode) timing")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-torch CUDA timing of the reference algorithm")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of one CUDA graph")

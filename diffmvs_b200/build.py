@@ -28,8 +28,16 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
+LEGACY = os.environ.get("DMVS_BUILD_LEGACY", "0") not in ("", "0")
+
+
 def sources():
-    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    """Kernel sources of the shipped library.  `csrc/legacy/` (the round-1 mma.sync and tap-offset tcgen05 convolution
+    back ends, off every shipped configuration) is compiled only with DMVS_BUILD_LEGACY=1."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    if LEGACY:
+        srcs += sorted(glob.glob(os.path.join(CSRC, "legacy", "*.cu")))
+    return srcs
 
 
 def _stale() -> bool:
@@ -48,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
     common = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
-              "-I", CSRC] + ARCH_FLAGS
+              "-I", CSRC] + ARCH_FLAGS + (["-DDMVS_LEGACY_BACKENDS=1"] if LEGACY else [])
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []

@@ -195,6 +195,15 @@ KernelFn pick_kernel(int chunk, int px, int s, int* co_t, int* wc) {
 
 
 }  // namespace
+
+#ifndef DMVS_LEGACY_BACKENDS
+// The round-1 back ends (mma.sync implicit GEMM, tap-offset tcgen05) live in csrc/legacy/ and are only built with
+// DMVS_BUILD_LEGACY=1: no shipped configuration selects them (the autotuner never picked them at cfg3 / cfg4).
+int dispatch_conv_mma(const dmvs_conv_desc&, cudaStream_t) { return DMVS_ERR_UNSUPPORTED; }
+bool conv_tc_supported(const dmvs_conv_desc&) { return false; }
+int dispatch_conv_tc(const dmvs_conv_desc&, cudaStream_t) { return DMVS_ERR_UNSUPPORTED; }
+#endif
+
 }  // namespace dmvs
 
 using namespace dmvs;
@@ -220,17 +229,17 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     return DMVS_ERR_ARG;
   if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
   if (d.precision == DMVS_PREC_AUTO) {
-    // fp32-class arithmetic, back end chosen per layer: the tcgen05 kernel wins where one MMA instruction carries
-    // enough work (>= 32 output channels per CTA), the FFMA kernel elsewhere (profiles/r1_conv_backends.txt)
-    // measured rule (profiles/r1_conv_backends.txt): the persistent tcgen05 kernel pays off on 3x3-or-larger kernels with
-    // >= 5 GMAC of work and >= 24 output channels (or >= 16 when the reduction is long, e.g. 7x7x64)
-    const int taps = d.KD * d.KH * d.KW;
-    const double macs = (double)taps * (d.C1 + d.C2) * d.Cout * d.N * d.Do * d.Ho * d.Wo;
-    const bool wide = d.Cout >= 24 || (d.Cout >= 16 && (long)taps * (d.C1 + d.C2) >= 2048);
-    if (d.w_tc && conv_tc_supported(d) && taps >= 9 && macs >= 5e9 && wide) {
-      dmvs_conv_desc alt = d;
-      alt.precision = DMVS_PREC_TC_TF32X3;
-      return dispatch_conv_tc(alt, static_cast<cudaStream_t>(stream));
+    // fp32-class arithmetic, back end chosen per layer without measuring (the host-side autotuner measures instead,
+    // ops._tune): the TMA-fed tcgen05 kernel for every layer it supports with at least 0.25 GMAC of work and 8 input
+    // channels (measured: profiles/r2_*), the first-generation kernel for nearest-upsampled inputs, FFMA elsewhere
+    const double macs = (double)d.KD * d.KH * d.KW * (d.C1 + d.C2) * d.Cout * d.N * d.Do * d.Ho * d.Wo;
+    if (macs >= 2.5e8 && d.C1 + d.C2 >= 8) {
+      if (conv_ws2_supported(d)) return dispatch_conv_ws2(d, static_cast<cudaStream_t>(stream));
+      if (conv_ws_supported(d)) {
+        dmvs_conv_desc alt = d;
+        alt.precision = DMVS_PREC_WS_TF32X3;
+        return dispatch_conv_ws(alt, static_cast<cudaStream_t>(stream));
+      }
     }
   } else if (d.precision == DMVS_PREC_WS2_TF32X3) {
     // TMA-fed width-stacked kernel where it applies, the first-generation one for nearest-upsampled inputs, FFMA elsewhere
@@ -250,11 +259,13 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     const double macs = (double)kred * d.Cout * d.N * d.Do * d.Ho * d.Wo;
     if (conv_ws_supported(d) && kred >= ws_min_k && macs >= ws_min_macs)
       return dispatch_conv_ws(d, static_cast<cudaStream_t>(stream));
+#ifdef DMVS_LEGACY_BACKENDS
     if (d.precision == DMVS_PREC_WS_TF32 && d.w_t) {
       dmvs_conv_desc alt = d;
       alt.precision = DMVS_PREC_TF32;
       return dispatch_conv_mma(alt, static_cast<cudaStream_t>(stream));
     }
+#endif
     // fall through to the FFMA kernel
   } else if (d.precision != DMVS_PREC_FP32) {
     if (d.precision < DMVS_PREC_FP32 || d.precision > DMVS_PREC_TC_TF32) return DMVS_ERR_ARG;
@@ -355,8 +366,10 @@ extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   if (dp == nullptr) return DMVS_ERR_ARG;
   const dmvs_conv_desc& d = *dp;
   int mask = 1;                                        // bit 0: FFMA kernel (always)
+#ifdef DMVS_LEGACY_BACKENDS
   if (d.w_t) mask |= 2;                                // bit 1: legacy mma.sync kernel
   if (d.w_tc && conv_tc_supported(d)) mask |= 4;       // bit 2: tcgen05 kernel, taps as descriptor offsets
+#endif
   if (conv_ws_supported(d)) mask |= 8;       // bit 3: tcgen05 kernel, kernel-row taps stacked along N
   if (conv_ws2_supported(d)) mask |= 16;     // bit 4: the same arithmetic behind the TMA-fed pipeline (conv_ws2.cu)
   return mask;

@@ -723,7 +723,7 @@ void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int C
         const double split_issue = 2.0 * in_rows * in_cols * (d.in_stats ? 60.0 : 26.0) / 32.0 / 4.0;   // 8 warps on 4 schedulers
         double stage_clk = mma_clk > port_clk ? mma_clk : port_clk;
         if (split_issue > stage_clk) stage_clk = split_issue;
-        const double fill = r >= 4 ? 0.0 : (r == 3 ? 150.0 : 700.0);        // exposed load latency per stage when the ring is shallow
+        const double fill = r >= 4 ? 0.0 : (r == 3 ? 40.0 : 700.0);        // exposed load latency per stage when the ring is shallow
         const double epi = (double)n_blk * (CC / 8) * (60.0 + 37.0 * KWe) * 2.0 + 300.0;   // 4 epilogue warps, overlapped
         double tile = stages * (stage_clk + fill + 60.0);
         if (epi > tile) tile = epi;

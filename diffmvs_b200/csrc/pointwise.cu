@@ -231,7 +231,11 @@ extern "C" uint64_t dmvs_launch_count(void) { return g_launch_count; }
 
 extern "C" const char* dmvs_build_info(void) {
   return "diffmvs_b200 kernels: sm_100a, CUDA " DMVS_STR(__CUDACC_VER_MAJOR__) "." DMVS_STR(__CUDACC_VER_MINOR__)
-         ", tcgen05/TMEM width-stacked + FFMA2 convolutions, fused warp/correlation";
+         ", TMA-fed tcgen05/TMEM width-stacked + FFMA2 convolutions, fused warp/correlation"
+#ifdef DMVS_LEGACY_BACKENDS
+         ", legacy back ends (mma.sync, tap-offset tcgen05)"
+#endif
+      ;
 }
 
 extern "C" int dmvs_groupnorm_silu_add(const float* x, const int64_t* stats, const float* g1, const float* g0,

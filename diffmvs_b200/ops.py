@@ -20,21 +20,33 @@ from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU
                     PREC_WS2_TF32X3,
                     RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
-# Arithmetic of the convolutions (storage is always fp32).  fp32-class modes (parity-safe, <= 4e-6 depth rel-L1):
-#   "auto"  (default)  per layer: tcgen05/TMEM 3xTF32 kernel for the FLOP-heavy stride-1 layers, FFMA2 kernel elsewhere
+# Arithmetic of the convolutions (storage is always fp32).  fp32-class modes (parity-safe, <= 5e-6 depth rel-L1):
+#   "auto"  (default)  per layer the fastest of the back ends below, measured on first use (like cudnn.benchmark)
 #   "fp32"             CUDA-core kernel everywhere (packed fp32x2 FMAs)
-#   "tf32x3"           legacy mma.sync tensor cores with hi/lo operand split
-#   "tc_tf32x3"        tcgen05 kernel wherever it applies (stride 1), mma.sync 3xTF32 for strided layers
-# Plain-TF32 modes (NOT parity-safe on the synthetic weights: 1e-3..3e-3 depth rel-L1, 2-6 % index flips):
-#   "tf32", "tc_tf32"  operands rounded to TF32 - the numerics cuDNN uses under torch defaults
+#   "ws2_tf32x3"       TMA-fed width-stacked tcgen05/TMEM kernel (conv_ws2.cu) wherever it applies, 3xTF32 operand split
+#   "ws_tf32x3"        the first-generation width-stacked tcgen05 kernel (conv_ws.cu; still used for upsampled inputs)
+# Plain-TF32 mode (NOT parity-safe on the synthetic weights: 1e-3..3e-3 depth rel-L1, 2-6 % index flips):
+#   "ws_tf32"          operands rounded to TF32 - the numerics cuDNN uses under torch defaults
+# "tf32x3", "tf32", "tc_tf32x3", "tc_tf32": the round-1 mma.sync / tap-offset tcgen05 back ends (csrc/legacy/), only in a
+# library built with DMVS_BUILD_LEGACY=1 (`legacy_backends()`); no shipped configuration uses them.
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
               "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO, "ws_tf32x3": PREC_WS_TF32X3, "ws_tf32": PREC_WS_TF32,
               "ws2_tf32x3": PREC_WS2_TF32X3}
 _precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "auto")]
 
 
+LEGACY_MODES = ("tf32x3", "tf32", "tc_tf32x3", "tc_tf32")
+
+
+def legacy_backends() -> bool:
+    """True when the loaded library was built with the round-1 back ends (DMVS_BUILD_LEGACY=1)."""
+    return b"legacy back ends" in _cabi.lib().dmvs_build_info()
+
+
 def set_precision(name: str) -> None:
     global _precision
+    if name in LEGACY_MODES and not legacy_backends():
+        raise ValueError(f"precision mode {name!r} needs a library built with DMVS_BUILD_LEGACY=1 (csrc/legacy/)")
     _precision = PRECISIONS[name]
 
 

@@ -36,7 +36,17 @@ PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3, "tc_tf32x3": 2e-5, "tc_t
             "ws_tf32x3": 2e-5, "ws_tf32": 3e-3, "ws2_tf32x3": 2e-5}   # max-abs error relative to the output scale
 
 
-@pytest.fixture(params=["fp32", "tf32x3", "tf32", "tc_tf32x3", "tc_tf32", "auto", "ws_tf32x3", "ws_tf32", "ws2_tf32x3"])
+def _modes():
+    modes = ["fp32", "auto", "ws_tf32x3", "ws_tf32", "ws2_tf32x3"]
+    try:                       # the round-1 back ends only exist in a DMVS_BUILD_LEGACY=1 library
+        if ops.legacy_backends():
+            modes += list(ops.LEGACY_MODES)
+    except Exception:
+        pass
+    return modes
+
+
+@pytest.fixture(params=_modes())
 def precision(request):
     old = ops.get_precision()
     ops.set_precision(request.param)
