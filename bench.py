@@ -228,8 +228,7 @@ def _fusion_leg(a, dev, world, rank, H, W, V, timed):
     import torch.distributed as dist
     from diffmvs_b200 import fusion, sharding
     from tests.helpers import plane_scene
-    per_rank = 2
-    n_views = per_rank * world
+    n_views = max(V, 2 * world)          # every reference view has V-1 source views, as in the depth-estimation step
     sc = plane_scene(H, W, n_views, 7)
     mine = list(sharding.shard_views(n_views, rank, world))
     t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
