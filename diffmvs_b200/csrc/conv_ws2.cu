@@ -34,8 +34,8 @@ namespace {
 using namespace tc;
 
 constexpr int kMmaWarps = 4;                                       // warps 0-3: one MMA-issuing thread per scheduler
-constexpr int kEpiWarps = 8;                                       // warps 4-11: warp % 4 = TMEM lane quadrant, two warps per quadrant
-constexpr int kSplitWarps = 8;                                     // warps 12-19
+constexpr int kEpiWarps = 16;                                      // warps 4-19: warp % 4 = TMEM lane quadrant, four warps per quadrant
+constexpr int kSplitWarps = 7;                                     // warps 20-26
 constexpr int kFirstEpiWarp = kMmaWarps;
 constexpr int kFirstSplitWarp = kFirstEpiWarp + kEpiWarps;
 constexpr int kTmaWarp = kFirstSplitWarp + kSplitWarps;           // warp 20
@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     // lane quadrant / next M block (a small shared "halo", written in a first pass).  Warp w handles TMEM lane quadrant
     // w % 4 of every M block.
     const int quadrant = warp & 3;
-    const int half = (warp - kFirstEpiWarp) >> 2;          // the two warps of a quadrant take alternate work items
+    const int half = (warp - kFirstEpiWarp) >> 2;          // the warps of a quadrant take work items round-robin
+    constexpr int kPerQuad = kEpiWarps / 4;
     const int etid = tid - 32 * kFirstEpiWarp;
     int dbg_tile = 0;                                      // tile index for the timeline stamps
     // FAST: the straight-line path - standard epilogue with optional bias, optional residual (before or after the
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         int blk = 0, cg = half;                              // items half, half + 2, ...
         while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
-        for (int it = half; it < n_items; it += 2) {        // pass 1: the first KW-1 rows of this quadrant, for its predecessor
+        for (int it = half; it < n_items; it += kPerQuad) {        // pass 1: the first KW-1 rows of this quadrant, for its predecessor
           const uint32_t trow = tquad + (uint32_t)(blk * N + cg * NCH);
           const uint32_t hq = halo_sa + (uint32_t)((it * 4 + quadrant) * halo_q) * 4u;
           if (KWT == 3) {
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
               }
             }
           }
-          cg += 2;
+          cg += kPerQuad;
           while (cg >= ncg) { cg -= ncg; ++blk; }
         }
         if (warp == kFirstEpiWarp) WS2_STAMP(8, dbg_tile);
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       int blk = 0, cg = half;
       while (cg >= ncg) { cg -= ncg; ++blk; }
 #pragma unroll 1
-      for (int it = half; it < n_items; it += 2) {          // pass 2: shift-add, fused epilogue, store
+      for (int it = half; it < n_items; it += kPerQuad) {   // pass 2: shift-add, fused epilogue, store
         const uint32_t trow = tquad + (uint32_t)(blk * N + cg * NCH);
         const bool have_next = quadrant < 3 || blk + 1 < a.n_blk;
         const uint32_t hn = halo_sa + (uint32_t)(((quadrant < 3 ? it : it + ncg) * 4 + ((quadrant + 1) & 3)) * halo_q) * 4u;
@@ -582,7 +583,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           }
         }
         if (warp == kFirstEpiWarp && it == half) WS2_STAMP(11, dbg_tile);
-        cg += 2;
+        cg += kPerQuad;
         while (cg >= ncg) { cg -= ncg; ++blk; }
       }
       if (d.out_stats != nullptr) {
@@ -624,10 +625,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       dbg_tile = t_local;
       const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
       const uint32_t halo_sa = smem_u32(halo0 + acc * a.halo_f);
-      if ((a.CC & 15) == 0)
-        run_epilogue(std::integral_constant<int, 16>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo_sa, stat_s[acc]);
-      else
-        run_epilogue(std::integral_constant<int, 8>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo_sa, stat_s[acc]);
+      run_epilogue(std::integral_constant<int, 8>{}, s.n, s.od, s.ty0, s.tx0, acc_base, halo_sa, stat_s[acc]);
       fence_tc_before();                                     // TMEM reads ordered before the hand-back
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
