@@ -30,6 +30,48 @@ def _sub(sd: SD, prefix: str) -> SD:
     return {k[n:]: v for k, v in sd.items() if k.startswith(prefix + ".")}
 
 
+class Branch:
+    """An independent launch sequence run on a side stream: `b = Branch(fn)` starts it after everything already
+    enqueued on the current stream, `b.join()` makes the current stream wait for it and returns fn's result.  Under
+    CUDA-graph capture the side stream becomes a parallel branch of the graph, so small independent layers (mask heads,
+    the two encoder branches, a ResnetBlock's 1x1 residual convolution, ContextNet next to FeatureNet) overlap instead
+    of each paying its own fill/drain latency on a mostly idle GPU.  Results are unchanged (same kernels, same order
+    within a branch).  Memory: a branch may allocate temporaries (they are freed and reused in its own stream order) but
+    should write results that outlive the join into buffers allocated by the caller, or keep them alive until the next
+    forward.  DMVS_BRANCHES=0 runs everything on one stream."""
+    _pool: Dict[int, List["torch.cuda.Stream"]] = {}
+    _busy: Dict[int, int] = {}
+    enabled = __import__("os").environ.get("DMVS_BRANCHES", "1") != "0"
+
+    def __init__(self, fn: Callable):
+        self.stream = None
+        if not Branch.enabled:
+            self.result = fn()
+            return
+        dev = torch.cuda.current_device()
+        pool = Branch._pool.setdefault(dev, [])
+        k = Branch._busy.get(dev, 0)
+        while len(pool) <= k:
+            pool.append(torch.cuda.Stream(device=dev))
+        Branch._busy[dev] = k + 1
+        self.dev, self.stream = dev, pool[k]
+        cur = torch.cuda.current_stream(dev)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self.stream.wait_event(fork)
+        with torch.cuda.stream(self.stream):
+            self.result = fn()
+            self.done = torch.cuda.Event()
+            self.done.record(self.stream)
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self.done)
+            Branch._busy[self.dev] -= 1
+            self.stream = None
+        return self.result
+
+
 class StatsArena:
     """Zero-initialised GroupNorm accumulators ([N,4,2] int64 fixed-point slots, 2^-20 units; the kernels add integers, so
     the statistics are independent of the order in which thread blocks arrive) for one forward pass."""
@@ -192,7 +234,8 @@ class InitialCostPlan:
         """feats [V,B,H,W,C], context [B,H,W,cd] (already ReLU'd), hom [B,V-1,12], plane_depth [B,D].
         Returns mask [B,H,W,36], norm inverse depth [B,H,W], depth [B,H,W], view weights [B,V-1,H,W], conf [B,H,W]."""
         V, B, H, W, _ = feats.shape
-        mask = self.mask(context)
+        mask = torch.empty((B, H, W, self.mask2.cout), device=context.device, dtype=torch.float32)
+        mask_branch = Branch(lambda: ops.conv(ops.conv(context, self.mask0, act=ACT_RELU), self.mask2, out=mask))
         cor = ops.plane_sweep_corr(feats, hom, plane_depth, self.G)          # [B*(V-1),D,H,W,G]
         vw = self.view_weights(cor)                                          # [B*(V-1),H,W]
         vol = ops.aggregate_views(cor, vw, B)
@@ -200,6 +243,7 @@ class InitialCostPlan:
         n, depth, conf, fl = ops.depth_regression(logits, depth_min, depth_max, want_floor=taps is not None)
         if taps is not None:
             taps.update(stage1_cor=cor, stage1_volume=vol, stage1_logits=logits, stage1_floor=fl)
+        mask_branch.join()
         return mask, n, depth, vw.view(B, V - 1, H, W), conf
 
 
@@ -220,14 +264,18 @@ class ResnetBlockPlan:
 
     def __call__(self, x: Tensor, arena: StatsArena, x2: Optional[Tensor] = None) -> Tensor:
         s1, s2 = arena.slot(), arena.slot()
-        y1 = ops.conv(x, self.conv1, x2=x2, out_stats=s1)
-        y2 = ops.conv(y1, self.conv2, in_gn=GroupNormIn(s1, *self.aff1), out_stats=s2)
-        if self.res is not None:
-            res = ops.conv(x, self.res, x2=x2)
+        side = None
+        if self.res is not None:     # the 1x1 residual convolution is independent of the two 3x3 convolutions
+            res = torch.empty(tuple(x.shape[:-1]) + (self.res.cout,), device=x.device, dtype=torch.float32)
+            side = Branch(lambda: ops.conv(x, self.res, x2=x2, out=res))
         else:
             if x2 is not None:
                 raise ValueError("identity residual with a concatenated input")
             res = x
+        y1 = ops.conv(x, self.conv1, x2=x2, out_stats=s1)
+        y2 = ops.conv(y1, self.conv2, in_gn=GroupNormIn(s1, *self.aff1), out_stats=s2)
+        if side is not None:
+            side.join()
         return ops.groupnorm_silu_add(y2, GroupNormIn(s2, *self.aff2), res)
 
 
@@ -293,8 +341,9 @@ class EncoderPlan:
     def __call__(self, cost: Tensor, samples: Tensor, out: Tensor) -> None:
         B, H, W, _ = cost.shape
         cd = torch.empty((B, H, W, 2 * self.ctx), device=cost.device, dtype=torch.float32)
+        side = Branch(lambda: ops.conv(ops.conv(samples, self.d1, act=ACT_RELU), self.d2, act=ACT_RELU, out=cd[..., self.ctx:]))
         ops.conv(ops.conv(cost, self.c1, act=ACT_RELU), self.c2, act=ACT_RELU, out=cd[..., :self.ctx])
-        ops.conv(ops.conv(samples, self.d1, act=ACT_RELU), self.d2, act=ACT_RELU, out=cd[..., self.ctx:])
+        side.join()
         ops.conv(cd, self.out, act=ACT_RELU, out=out)
 
 
@@ -339,7 +388,8 @@ class UpdateBlockPlan:
         ctx = self.ctx
         # the reference draws randn_like(inv_depth) with inv_depth [B,1,H,W] on the default generator
         noise = torch.randn_like(inv0.view(B, 1, H, W))
-        mask = self.mask(ubuf[..., :ctx])
+        mask_out = torch.empty((B, H, W, self.mask2.cout), device=inv0.device, dtype=torch.float32)
+        mask_branch = Branch(lambda: ops.conv(ops.conv(ubuf[..., :ctx], self.mask0, act=ACT_RELU), self.mask2, out=mask_out))
         delta = torch.empty_like(inv0)
         inv = torch.empty_like(inv0)
         depth = torch.empty_like(inv0)
@@ -378,7 +428,8 @@ class UpdateBlockPlan:
             step_noise = torch.randn_like(inv0.view(B, 1, H, W))
             ops.ddim_step(img, delta, step_noise, f("sqrt_recip_alphas_cumprod", time),
                           f("sqrt_recipm1_alphas_cumprod", time), float(a_next.sqrt()), float(c), float(sigma), self.scale)
-        return mask, cur_hidden, inv, head[..., 1:2], depth
+        mask_branch.join()
+        return mask_out, cur_hidden, inv, head[..., 1:2], depth
 
 
 # ------------------------------------------------------------------------------------------------
@@ -443,6 +494,7 @@ class CasDiffMVSPlan:
         x_st = torch.empty((len(staged), B, H, W, 4), device=dev, dtype=torch.float32)   # RGB + one zero channel
         for i, v in enumerate(staged):
             ops.image_to_nhwc4(imgs[v] if imgs[v].dtype == torch.uint8 else imgs[v].float(), out=x_st[i])
+        ctx_branch = Branch(lambda: self.context.trunk(x_st[0]))        # ContextNet (one image) next to FeatureNet (V images)
         if len(missing) == V:
             feats = self.feature(x_st.view(V * B, H, W, 4))
         else:
@@ -462,7 +514,8 @@ class CasDiffMVSPlan:
                         raise ValueError(f"cached features of view {v} ({tuple(src.shape)}) do not match this input")
                     buf[v * B:(v + 1) * B].copy_(src)
                 feats[key] = buf
-        ctx_feats = self.context.trunk(x_st[0])
+        ctx_feats = ctx_branch.join()
+        self._keep = ctx_feats          # side-stream allocations stay alive until the next forward replaces them
 
         slots = sum(b.stats_slots() for b in self.blocks.values())
         arena = StatsArena(dev, B, max(slots, 1))
