@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "diffmvs_b200.h"
 
@@ -84,6 +85,43 @@ struct SmemOptIn {
     }
   }
 };
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched through launch_pdl may become resident while its
+// predecessor on the stream is still draining; its on-chip prologue (barrier init, TMEM allocation,
+// descriptor prefetch, index arithmetic) then overlaps the predecessor's tail and the launch latency.
+// Contract: such a kernel calls pdl_sync() before its FIRST access to global memory, and nothing
+// before that point reads or writes global memory.  griddepcontrol.wait returns only when every
+// prerequisite grid has completed and its writes are visible, so no ordering between kernels changes.
+// DMVS_PDL=0 launches everything fully serialised (A/B switch).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DMVS_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+}
 
 inline int launch_status() {
   ++g_launch_count;

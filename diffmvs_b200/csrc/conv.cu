@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_kernel(const __grid_constant
   const int wc = warp % WC;
   const int wp = warp / WC;
 
+  pdl_sync();
   const int n = blockIdx.z / d.Do;
   const int od = blockIdx.z - n * d.Do;
   const int ty0 = blockIdx.y * TH;
@@ -338,7 +339,7 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     a.in_cols = (kTileW - 1) * S + d.KW;
     dim3 grid(ceil_div(d.Wo, kTileW), ceil_div(d.Ho, th), d.N * d.Do);
     if (grid.y > 65535 || grid.z > 65535) return DMVS_ERR_UNSUPPORTED;
-    fn<<<grid, kThreads, smem, st>>>(a);
+    launch_pdl(fn, grid, dim3(kThreads), smem, st, a);
     int rc = launch_status();
     if (rc) return rc;
     co_base += chunk;
@@ -387,6 +388,7 @@ template <int COUT>
 __global__ void __launch_bounds__(128) deconv3d_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                        const float* __restrict__ bias, const float* __restrict__ skip,
                                                        float* __restrict__ y, int N, int D, int H, int W, int Cin) {
+  pdl_sync();
   extern __shared__ __align__(16) float ws[];  // [27][Cin][COUT]
   const int wtotal = 27 * Cin * COUT;
   for (int i = threadIdx.x; i < wtotal; i += blockDim.x) ws[i] = __ldg(w + i);
@@ -457,11 +459,11 @@ extern "C" int dmvs_deconv3d_f32(const float* x, const float* w, const float* bi
   if (Cout == 8) {
     static SmemOptIn opt_in;
     opt_in.ensure(deconv3d_kernel<8>, 100 * 1024);
-    deconv3d_kernel<8><<<blocks, 128, smem, st>>>(x, w, bias, skip, y, N, D, H, W, Cin);
+    launch_pdl(deconv3d_kernel<8>, dim3(blocks), dim3(128), smem, st, x, w, bias, skip, y, N, D, H, W, Cin);
   } else {
     static SmemOptIn opt_in;
     opt_in.ensure(deconv3d_kernel<16>, 100 * 1024);
-    deconv3d_kernel<16><<<blocks, 128, smem, st>>>(x, w, bias, skip, y, N, D, H, W, Cin);
+    launch_pdl(deconv3d_kernel<16>, dim3(blocks), dim3(128), smem, st, x, w, bias, skip, y, N, D, H, W, Cin);
   }
   return launch_status();
 }

@@ -864,22 +864,7 @@ int dispatch_conv_ws(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_out
       }
     } else {
       KernelFn fn = passes == 3 ? pick_r<3>(t.R, d.in_stats != nullptr) : pick_r<1>(t.R, d.in_stats != nullptr);
-      static const int use_pdl = getenv("DMVS_PDL") ? atoi(getenv("DMVS_PDL")) : 0;
-      if (use_pdl) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kWsThreads);
-        cfg.dynamicSmemBytes = t.smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, fn, a);
-      } else {
-        fn<<<grid, kWsThreads, t.smem, st>>>(a);
-      }
+      launch_pdl(fn, dim3(grid), dim3(kWsThreads), t.smem, st, a);
       const int rc = launch_status();
       if (rc) return rc;
     }

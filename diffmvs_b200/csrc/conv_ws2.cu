@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
   fence_tc_before();
   __syncthreads();
   fence_tc_after();
+  pdl_sync();   // everything above is on-chip set-up; the producing kernel's outputs are read from here on
   const uint32_t tmem_base = tmem_base_s;
   const int nchunks = a.cin_pad >> 3;
   const int nphase = a.S * a.S;
@@ -832,7 +833,7 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
         a.map_x2 = a.map_x;
       }
       KernelFn fn = d.in_stats != nullptr ? get_kernel<true>() : get_kernel<false>();
-      fn<<<grid, kWs2Threads, t.smem, st>>>(a);
+      launch_pdl(fn, dim3(grid), dim3(kWs2Threads), t.smem, st, a);
       const int rc = launch_status();
       if (rc) return rc;
     }

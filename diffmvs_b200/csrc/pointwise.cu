@@ -13,6 +13,7 @@ __global__ void __launch_bounds__(256) groupnorm_silu_add_kernel(const float* __
                                                                  const float* __restrict__ res, int res_ps,
                                                                  float* __restrict__ y, int y_ps, int N, int HW, int C,
                                                                  float inv_count) {
+  pdl_sync();
   extern __shared__ float ab[];  // [2][C] for sample n = blockIdx.y
   const int n = blockIdx.y;
   const int cpg = C / 4;
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) upsample_depth_kernel(const float* __rest
                                                              const float* __restrict__ depth_max,
                                                              float* __restrict__ raw_up, float* __restrict__ depth_up,
                                                              float* __restrict__ norm_up, int B, int H, int W, int r) {
+  pdl_sync();
   const int Ho = H * r, Wo = W * r;
   const int64_t total = (int64_t)B * Ho * Wo;
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) refine_update_kernel(int mode, const floa
                                                             const float* __restrict__ depth_min,
                                                             const float* __restrict__ depth_max,
                                                             float* __restrict__ depth, int B, int HW) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * HW) return;
   const float base = __ldg(inv0 + i);
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) refine_update_kernel(int mode, const floa
 __global__ void ddim_step_kernel(float* __restrict__ img, const float* __restrict__ delta,
                                  const float* __restrict__ noise, float k_recip, float k_recipm1, float sqrt_a_next,
                                  float c, float sigma, float scale, int64_t count) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
   const float dl = __ldg(delta + i);
@@ -136,6 +140,7 @@ __global__ void ddim_step_kernel(float* __restrict__ img, const float* __restric
 
 __global__ void upsample_nearest_kernel(const float* __restrict__ x, int x_ps, float* __restrict__ y, int B, int H, int W,
                                         int f) {
+  pdl_sync();
   const int Ho = H * f, Wo = W * f;
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= (int64_t)B * Ho * Wo) return;
@@ -148,6 +153,7 @@ __global__ void upsample_nearest_kernel(const float* __restrict__ x, int x_ps, f
 
 // [N][C][HW] -> [N][HW][C] through a 32x32 shared tile (both sides coalesced)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int y_ps, int C, int HW) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -165,6 +171,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restri
 // C <= 4 (images): one thread per pixel, C coalesced plane reads, one packed write
 __global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, float* __restrict__ y, int y_ps, int C, int HW,
                                           int64_t total) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t n = i / HW;
@@ -177,6 +184,7 @@ __global__ void nchw_to_nhwc_small_kernel(const float* __restrict__ x, float* __
 // RGB image planes [N][3][HW] -> [N][HW][4] with a zero fourth channel: one aligned 16-byte store per pixel, so
 // the first convolution of FeatureNet / ContextNet can stage its input with 128-bit asynchronous copies.
 __global__ void image_to_nhwc4_kernel(const float* __restrict__ x, float4* __restrict__ y, int HW, int64_t total) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t n = i / HW;
@@ -190,6 +198,7 @@ __global__ void image_to_nhwc4_kernel(const float* __restrict__ x, float4* __res
 // or interleaved [N][HW][3] (c_stride = 1, p_stride = 3): 4x fewer bytes over PCIe than fp32 images.
 __global__ void image_u8_to_nhwc4_kernel(const uint8_t* __restrict__ x, int64_t n_stride, int64_t c_stride, int p_stride,
                                          float4* __restrict__ y, int HW, int64_t total) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t n = i / HW;
@@ -200,6 +209,7 @@ __global__ void image_u8_to_nhwc4_kernel(const uint8_t* __restrict__ x, int64_t 
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int x_ps, float* __restrict__ y, int C, int HW) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -250,7 +260,7 @@ extern "C" int dmvs_groupnorm_silu_add(const float* x, const int64_t* stats, con
   const int bx = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
   dim3 grid(bx, N);
   const float inv_count = 1.0f / ((float)HW * (float)(C / 4));
-  groupnorm_silu_add_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(groupnorm_silu_add_kernel, dim3(grid), dim3(256), 2 * C * sizeof(float), static_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<const long long*>(stats), g1, g0, res, res_ps, y, y_ps, N, HW, C, inv_count);
   return launch_status();
 }
@@ -263,7 +273,7 @@ extern "C" int dmvs_upsample_depth(const float* n, const float* mask, int32_t ma
   if ((depth_up || norm_up) && (!depth_min || !depth_max)) return DMVS_ERR_ARG;
   if (mask_ps < 9 * ratio * ratio) return DMVS_ERR_ARG;
   const int64_t total = (int64_t)B * H * W * ratio * ratio;
-  upsample_depth_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(upsample_depth_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       n, mask, mask_ps, depth_min, depth_max, raw_up, depth_up, norm_up, B, H, W, ratio);
   return launch_status();
 }
@@ -277,7 +287,7 @@ extern "C" int dmvs_refine_update(int32_t mode, const float* inv0, const float* 
   if (mode == 1 && (!noise_or_upd || upd_ps <= 0)) return DMVS_ERR_ARG;
   if (depth && (!depth_min || !depth_max)) return DMVS_ERR_ARG;
   const int64_t total = (int64_t)B * HW;
-  refine_update_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(refine_update_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       mode, inv0, noise_or_upd, upd_ps, scale, delta, inv, inv_slot, slot_ps, depth_min, depth_max, depth, B, HW);
   return launch_status();
 }
@@ -285,7 +295,7 @@ extern "C" int dmvs_refine_update(int32_t mode, const float* inv0, const float* 
 extern "C" int dmvs_ddim_step(float* img, const float* delta, const float* noise, float k_recip, float k_recipm1,
                               float sqrt_a_next, float c, float sigma, float scale, int64_t count, void* stream) {
   if (!img || !delta || !noise || count <= 0) return DMVS_ERR_ARG;
-  ddim_step_kernel<<<(unsigned)ceil_div64(count, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(ddim_step_kernel, dim3((unsigned)ceil_div64(count, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       img, delta, noise, k_recip, k_recipm1, sqrt_a_next, c, sigma, scale, count);
   return launch_status();
 }
@@ -294,7 +304,7 @@ extern "C" int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int
                                      int32_t factor, void* stream) {
   if (!x || !y || B <= 0 || H <= 0 || W <= 0 || factor <= 0 || x_ps <= 0) return DMVS_ERR_ARG;
   const int64_t total = (int64_t)B * H * W * factor * factor;
-  upsample_nearest_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_ps, y, B, H,
+  launch_pdl(upsample_nearest_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, x_ps, y, B, H,
                                                                                                          W, factor);
   return launch_status();
 }
@@ -304,13 +314,13 @@ extern "C" int dmvs_nchw_to_nhwc(const float* x, float* y, int32_t y_ps, int32_t
   if (!x || !y || N <= 0 || C <= 0 || HW <= 0 || y_ps < C) return DMVS_ERR_ARG;
   if (C <= 4) {
     const int64_t total = (int64_t)N * HW;
-    nchw_to_nhwc_small_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, y_ps, C,
+    launch_pdl(nchw_to_nhwc_small_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, y, y_ps, C,
                                                                                                              HW, total);
     return launch_status();
   }
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
   if (grid.z > 65535 || grid.y > 65535) return DMVS_ERR_UNSUPPORTED;
-  nchw_to_nhwc_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, y, y_ps, C, HW);
+  launch_pdl(nchw_to_nhwc_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), x, y, y_ps, C, HW);
   return launch_status();
 }
 
@@ -318,7 +328,7 @@ extern "C" int dmvs_image_to_nhwc4(const float* x, float* y, int32_t N, int32_t 
   if (!x || !y || N <= 0 || HW <= 0) return DMVS_ERR_ARG;
   if (!aligned16(y)) return DMVS_ERR_ALIGN;
   const int64_t total = (int64_t)N * HW;
-  image_to_nhwc4_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(image_to_nhwc4_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<float4*>(y), HW, total);
   return launch_status();
 }
@@ -328,7 +338,7 @@ extern "C" int dmvs_image_u8_to_nhwc4(const uint8_t* x, int64_t n_stride, int64_
   if (!x || !y || N <= 0 || HW <= 0 || c_stride <= 0 || p_stride <= 0) return DMVS_ERR_ARG;
   if (!aligned16(y)) return DMVS_ERR_ALIGN;
   const int64_t total = (int64_t)N * HW;
-  image_u8_to_nhwc4_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(image_u8_to_nhwc4_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       x, n_stride, c_stride, p_stride, reinterpret_cast<float4*>(y), HW, total);
   return launch_status();
 }
@@ -338,6 +348,6 @@ extern "C" int dmvs_nhwc_to_nchw(const float* x, int32_t x_ps, float* y, int32_t
   if (!x || !y || N <= 0 || C <= 0 || HW <= 0 || x_ps < C) return DMVS_ERR_ARG;
   dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N), block(32, 8);
   if (grid.z > 65535 || grid.y > 65535) return DMVS_ERR_UNSUPPORTED;
-  nhwc_to_nchw_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(x, x_ps, y, C, HW);
+  launch_pdl(nhwc_to_nchw_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), x, x_ps, y, C, HW);
   return launch_status();
 }

@@ -57,6 +57,7 @@ __device__ bool invert4(const double A[4][4], double inv[4][4]) {
 }
 
 __global__ void compose_homographies_kernel(const float* __restrict__ proj, float* __restrict__ hom, int B, int V) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * (V - 1)) return;
   const int b = i / (V - 1), v = 1 + i % (V - 1);
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(256) warp_volume_kernel(const float* __restric
                                                           const float* __restrict__ hom,
                                                           const float* __restrict__ depth, float* __restrict__ out,
                                                           int B, int C, int Hs, int Ws, int D, int H, int W) {
+  pdl_sync();
   // one thread per (b, d, y, x, 4-channel group)
   const int c4n = (C + 3) / 4;
   const int64_t total = (int64_t)B * D * H * W * c4n;
@@ -249,6 +251,7 @@ __global__ void __launch_bounds__(256) plane_sweep_kernel(const float* __restric
                                                           const float* __restrict__ hom,
                                                           const float* __restrict__ plane_depth,
                                                           float* __restrict__ cor, int B, int V, int D, int H, int W) {
+  pdl_sync();
   constexpr int VEC = C / (4 * LPP);
   constexpr int LPG = LPP / G;  // lanes per group
   static_assert(VEC >= 1 && LPG >= 1 && C % (4 * LPP) == 0 && LPP % G == 0, "bad split");
@@ -299,6 +302,7 @@ __global__ void __launch_bounds__(256) plane_sweep_kernel(const float* __restric
 }
 
 __global__ void view_weight_max_kernel(const float* __restrict__ logit, float* __restrict__ w, int N, int D, int HW) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * HW) return;
   const int n = (int)(i / HW), p = (int)(i % HW);
@@ -310,6 +314,7 @@ __global__ void view_weight_max_kernel(const float* __restrict__ logit, float* _
 
 __global__ void aggregate_views_kernel(const float* __restrict__ cor, const float* __restrict__ w,
                                        float* __restrict__ vol, int B, int V1, int D, int HW, int G4) {
+  pdl_sync();
   // G == 4: one float4 per (b, d, p)
   const int64_t total = (int64_t)B * D * HW;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,6 +347,7 @@ __global__ void depth_regression_kernel(const float* __restrict__ logits, const 
                                         const float* __restrict__ depth_max, float* __restrict__ norm_inv,
                                         float* __restrict__ depth, float* __restrict__ conf,
                                         int32_t* __restrict__ floor_idx, int B, int D, int HW) {
+  pdl_sync();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * HW) return;
   const int b = (int)(i / HW), p = (int)(i % HW);
@@ -385,6 +391,7 @@ __global__ void __launch_bounds__(256) get_cost_kernel(const float* __restrict__
                                                        int cost_ps, float* __restrict__ samples, int samp_ps, int B,
                                                        int V, int H, int W, int wshift, float interval,
                                                        float min_radius, float max_radius) {
+  pdl_sync();
   constexpr int VEC = C / (4 * LPP);
   constexpr int LPG = LPP / G;
   static_assert(VEC >= 1 && LPG >= 1 && C % (4 * LPP) == 0 && LPP % G == 0, "bad split");
@@ -492,7 +499,7 @@ using namespace dmvs;
 extern "C" int dmvs_compose_homographies(const float* proj, float* hom, int32_t B, int32_t V, void* stream) {
   if (!proj || !hom || B <= 0 || V < 2) return DMVS_ERR_ARG;
   const int n = B * (V - 1);
-  compose_homographies_kernel<<<ceil_div(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(proj, hom, B, V);
+  launch_pdl(compose_homographies_kernel, dim3(ceil_div(n, 64)), dim3(64), 0, static_cast<cudaStream_t>(stream), proj, hom, B, V);
   return launch_status();
 }
 
@@ -504,7 +511,7 @@ extern "C" int dmvs_warp_volume(const float* src, int32_t src_ps, const float* h
   const int64_t total = (int64_t)B * D * H * W * ((C + 3) / 4);
   const int64_t want = ceil_div64(total, 256);
   const int blocks = (int)(want < (int64_t)kNumSMs * 32 ? want : (int64_t)kNumSMs * 32);
-  warp_volume_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_ps, hom, depth, out, B, C, Hs, Ws,
+  launch_pdl(warp_volume_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), src, src_ps, hom, depth, out, B, C, Hs, Ws,
                                                                            D, H, W);
   return launch_status();
 }
@@ -520,13 +527,13 @@ extern "C" int dmvs_plane_sweep_corr(const float* feats, const float* hom, const
   if (G != 4) return DMVS_ERR_UNSUPPORTED;
   if (C == 48) {
     dim3 grid(ceil_div(HW, 256 / 4), V - 1, B);
-    plane_sweep_kernel<48, 4, 4><<<grid, 256, 0, st>>>(feats, hom, plane_depth, cor, B, V, D, H, W);
+    launch_pdl(plane_sweep_kernel<48, 4, 4>, dim3(grid), dim3(256), 0, st, feats, hom, plane_depth, cor, B, V, D, H, W);
   } else if (C == 32) {
     dim3 grid(ceil_div(HW, 256 / 8), V - 1, B);
-    plane_sweep_kernel<32, 4, 8><<<grid, 256, 0, st>>>(feats, hom, plane_depth, cor, B, V, D, H, W);
+    launch_pdl(plane_sweep_kernel<32, 4, 8>, dim3(grid), dim3(256), 0, st, feats, hom, plane_depth, cor, B, V, D, H, W);
   } else if (C == 16) {
     dim3 grid(ceil_div(HW, 256 / 4), V - 1, B);
-    plane_sweep_kernel<16, 4, 4><<<grid, 256, 0, st>>>(feats, hom, plane_depth, cor, B, V, D, H, W);
+    launch_pdl(plane_sweep_kernel<16, 4, 4>, dim3(grid), dim3(256), 0, st, feats, hom, plane_depth, cor, B, V, D, H, W);
   } else {
     return DMVS_ERR_UNSUPPORTED;
   }
@@ -536,7 +543,7 @@ extern "C" int dmvs_plane_sweep_corr(const float* feats, const float* hom, const
 extern "C" int dmvs_view_weight_max(const float* logit, float* w, int32_t N, int32_t D, int32_t HW, void* stream) {
   if (!logit || !w || N <= 0 || D <= 0 || HW <= 0) return DMVS_ERR_ARG;
   const int64_t total = (int64_t)N * HW;
-  view_weight_max_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logit, w, N, D, HW);
+  launch_pdl(view_weight_max_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), logit, w, N, D, HW);
   return launch_status();
 }
 
@@ -545,7 +552,7 @@ extern "C" int dmvs_aggregate_views(const float* cor, const float* w, float* vol
   if (!cor || !w || !vol || B <= 0 || V1 <= 0 || D <= 0 || HW <= 0) return DMVS_ERR_ARG;
   if (G != 4) return DMVS_ERR_UNSUPPORTED;
   const int64_t total = (int64_t)B * D * HW;
-  aggregate_views_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cor, w, vol, B, V1,
+  launch_pdl(aggregate_views_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), cor, w, vol, B, V1,
                                                                                                         D, HW, G);
   return launch_status();
 }
@@ -556,7 +563,7 @@ extern "C" int dmvs_depth_regression(const float* logits, const float* depth_min
   if (!logits || !depth_min || !depth_max || !norm_inv || !depth || !conf || B <= 0 || D <= 0 || HW <= 0)
     return DMVS_ERR_ARG;
   const int64_t total = (int64_t)B * HW;
-  depth_regression_kernel<<<(unsigned)ceil_div64(total, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_pdl(depth_regression_kernel, dim3((unsigned)ceil_div64(total, 128)), dim3(128), 0, static_cast<cudaStream_t>(stream), 
       logits, depth_min, depth_max, norm_inv, depth, conf, floor_idx, B, D, HW);
   return launch_status();
 }
@@ -569,7 +576,7 @@ int launch_get_cost(int D, const float* feats, const float* hom, const float* in
                     float rmax, cudaStream_t st) {
   dim3 grid(ceil_div(H * W, 256 / LPP), B);
 #define DMVS_GC(DD)                                                                                               \
-  get_cost_kernel<C, 4, LPP, DD><<<grid, 256, 0, st>>>(feats, hom, inv_depth, conf, conf_ps, view_w, depth_min, depth_max, cost, \
+  launch_pdl(get_cost_kernel<C, 4, LPP, DD>, dim3(grid), dim3(256), 0, st, feats, hom, inv_depth, conf, conf_ps, view_w, depth_min, depth_max, cost, \
                                                        cost_ps, samples, samp_ps, B, V, H, W, wshift, interval, rmin, rmax)
   switch (D) {
     case 1: DMVS_GC(1); break;
