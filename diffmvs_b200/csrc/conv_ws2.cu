@@ -68,6 +68,9 @@ struct alignas(64) Ws2Args {
   int halo_f;            // floats of ONE halo exchange buffer (two are allocated, alternating per tile)
   int vec_y, vec_res, vec_bias;
   int fast_epi;          // 1: the epilogue's straight-line path applies (see the kernel)
+  int pair;              // 1: <= 4 input channels, kernel rows paired along K (see dispatch_conv_ws2): one quad plane per
+                         //    stage, the MMA's second K quad is the same plane one tile row further down
+  int KHm;               // row-MMAs per (block, stage): KHe, or ceil(KHe / 2) when paired
   float inv_in_cols;
   int64_t w_off;         // offset (floats) of this launch's hi slabs inside w_ws
   int64_t w_plane;       // distance (floats) from a hi slab to its lo twin
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
   extern __shared__ __align__(1024) float smem[];
   const int N = a.N;
   float* hi0 = smem;                                   // [R][stage_f]   raw tile lands here, split in place -> hi
-  float* lo0 = hi0 + a.R * a.stage_f;                  // [R][stage_f]
+  float* lo0 = hi0 + a.R * a.stage_f;                  // [R][stage_f]   (stage_f = one or two quad planes)
   float* w_hi0 = lo0 + a.R * a.stage_f;                // [R][wslab_f]
   float* w_lo0 = w_hi0 + a.R * a.wslab_f;              // [R][wslab_f]
   float* halo0 = w_lo0 + a.R * a.wslab_f;              // [2][halo_f]
@@ -171,13 +174,14 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       const uint32_t box_bytes = (uint32_t)a.box_units * 16u, w_bytes = (uint32_t)a.wslab_f * 4u;
       while (cur.tile < a.total_tiles) {
         if (use > 0) mbar_wait(&empty_bar[slot], (uint32_t)((use - 1) & 1));   // the MMAs that read this slot have retired
-        mbar_arrive_expect_tx(&tma_full[slot], 2u * box_bytes + 2u * w_bytes);
+        mbar_arrive_expect_tx(&tma_full[slot], (a.pair ? 1u : 2u) * box_bytes + 2u * w_bytes);
         const int pa = a.S == 2 ? (cur.phase >> 1) : 0, pb = a.S == 2 ? (cur.phase & 1) : 0;
         const int iy0 = a.S * (cur.ty0 + a.smin_h) + pa, ix0 = a.S * (cur.tx0 + a.smin_w) + pb;
         const int id = cur.od * a.S + cur.kd - d.pad_d;
         float* dst = hi0 + slot * a.stage_f;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
+          if (q == 1 && a.pair) break;
           const int ch = cur.chunk * 8 + q * 4;
           // channels past C1+C2 (cin_pad rounding) are out of bounds of the tensor map: zero filled
           if (ch < d.C1 || d.C2 == 0)
@@ -200,7 +204,9 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     // (start address field) advance by plain 32-bit adds, so one kernel row costs a handful of scalar instructions
     const bool leader = elect_one();
     const uint32_t idesc = idesc_tf32_m128(N);
-    const uint32_t lbo_a = (uint32_t)a.plane * 16u, lbo_b = (uint32_t)N * 16u;
+    // paired rows: K quad 1 of the A operand is quad 0 one tile row further down (kernel row 2*khp + 1)
+    const uint32_t lbo_a = (uint32_t)(a.pair ? a.in_cols : a.plane) * 16u, lbo_b = (uint32_t)N * 16u;
+    const uint32_t a_step = (uint32_t)(a.pair ? 2 * a.in_cols : a.in_cols);
     const uint32_t b_step = 2u * (uint32_t)N;                // one kernel row of weights, in 16-byte units
     const uint32_t a_hiword = (uint32_t)(umma_desc(0, lbo_a, 128) >> 32), b_hiword = (uint32_t)(umma_desc(0, lbo_b, 128) >> 32);
     const uint32_t a_lbo = (uint32_t)umma_desc(0, lbo_a, 128), b_lbo = (uint32_t)umma_desc(0, lbo_b, 128);   // LBO field, address 0
@@ -224,6 +230,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
         const int kh = a.S * (khe + a.smin_h) + pa + d.pad_h;
         if (kh >= 0 && kh < d.KH) rows |= 1u << khe;
       }
+      if (a.pair) rows = (1u << a.KHm) - 1u;                  // stride 1: every kernel-row pair is present
       const uint32_t acc_base = tmem_base + (uint32_t)(acc * a.acc_cols);
       if (leader) {
         for (int blk = warp; blk < a.n_blk; blk += kMmaWarps) {
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           uint32_t a_off = (uint32_t)(blk * 128), b_off = 0;
           uint32_t r = rows;
 #pragma unroll 1
-          for (int khe = 0; khe < a.KHe; ++khe, a_off += (uint32_t)a.in_cols, b_off += b_step, r >>= 1) {
+          for (int khe = 0; khe < a.KHm; ++khe, a_off += a_step, b_off += b_step, r >>= 1) {
             if (!(r & 1u)) continue;
             umma_tf32_w(d_tmem, al + a_off, a_hiword, bh + b_off, b_hiword, idesc, accum);
             umma_tf32_w(d_tmem, ah + a_off, a_hiword, bl + b_off, b_hiword, idesc, 1u);
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       const int iy0 = cur.ty0 + a.smin_h, ix0 = cur.tx0 + a.smin_w;   // GN layers are stride 1
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
+        if (q == 1 && a.pair) break;
         float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), g0 = g1;
         bool ch_ok = false;
         if (GN) {
@@ -669,14 +677,17 @@ inline int ws_cc_max(int KW) {
 // accumulator sets) is scored with a small throughput model - per tile the slower of the tensor pipe and the
 // shared-memory port (MMA operand reads + split pass + TMA writes), plus a fixed per-tile cost - times the number of
 // tile waves over the SMs.  Deeper rings win ties.
-void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int CC, int cin_pad, TileCfg2& best) {
+void choose_tile2(const dmvs_conv_desc& d, int S, int KHe_in, int KWe, int N, int CC, int cin_pad, bool pair, TileCfg2& best) {
+  const int KHm = pair ? (KHe_in + 1) / 2 : KHe_in;      // row-MMAs per (block, stage)
+  const int KHe = pair ? 2 * KHm : KHe_in;                // staged rows beyond the tile height + 1 (paired: rounded up to even)
   static const int force_th = getenv("DMVS_WS2_TH") ? atoi(getenv("DMVS_WS2_TH")) : 0;   // tuning aids
   static const int force_r = getenv("DMVS_WS2_R") ? atoi(getenv("DMVS_WS2_R")) : 0;
   static const int force_nb = getenv("DMVS_WS2_NB") ? atoi(getenv("DMVS_WS2_NB")) : 0;
   const int nchunks = cin_pad >> 3;
   const size_t smem_limit = 224 * 1024;
   const int max_blk = 256 / N;
-  const size_t wslab_f = (size_t)KHe * 2 * N * 4;
+  const size_t wslab_f = (size_t)KHm * 2 * N * 4;
+  const int quads = pair ? 1 : 2;
   // Staged tiles exactly 32 positions wide (TW = 33 - KWe output columns) make a TMEM lane quadrant one tile row: the
   // epilogue then needs no halo exchange between quadrants, no barrier and no index division (measured: the epilogue
   // warps' instruction issue, not the tensor pipe, bounds the layers with few input channels).  Used whenever the
@@ -706,20 +717,20 @@ void choose_tile2(const dmvs_conv_desc& d, int S, int KHe, int KWe, int N, int C
       const int n_blk = ceil_div(th * in_cols, 128);
       if (n_blk > max_blk) continue;
       const int plane = (n_blk * 128 + (KHe - 1) * in_cols + 8 + 7) & ~7;
-      const size_t stage_f = (size_t)2 * plane * 4;
+      const size_t stage_f = (size_t)quads * plane * 4;
       const size_t halo_f = ((size_t)n_blk * (CC / 8) * 4 * (KWe - 1) * (KWe - 1) * 8 + 31) & ~(size_t)31;
       for (int r = kMaxRing; r >= 2; --r) {
         if (force_r && r != force_r) continue;
         const size_t need = (r * (2 * stage_f + 2 * wslab_f) + 2 * halo_f + 2 * (size_t)d.C1 + 64) * 4;
         if (need > smem_limit) continue;
         const int stages = nchunks * d.KD * S * S;
-        const double rows_per_stage = (double)d.KH / S;                      // kernel rows per phase (average)
+        const double rows_per_stage = pair ? (double)KHm : (double)d.KH / S;   // row-MMAs per phase (average)
         const double mma_n = (double)n_blk * rows_per_stage * 3.0;          // MMAs per stage
         const double mma_clk = mma_n * (N / 2 > 32 ? N / 2 : 32);
         const double port_clk = mma_n * (4096.0 + 32.0 * N) / 128.0          // A and B operand reads
-                                + 2.0 * in_rows * in_cols * (64.0 + 16.0) / 128.0   // split (16 read + 32 written) + TMA write
+                                + quads * in_rows * in_cols * (64.0 + 16.0) / 128.0   // split (16 read + 32 written) + TMA write
                                 + 2.0 * wslab_f * 4.0 / 128.0;
-        const double split_issue = 2.0 * in_rows * in_cols * (d.in_stats ? 60.0 : 26.0) / 32.0 / 4.0;   // 8 warps on 4 schedulers
+        const double split_issue = quads * in_rows * in_cols * (d.in_stats ? 60.0 : 26.0) / 32.0 / 4.0;   // 8 warps on 4 schedulers
         double stage_clk = mma_clk > port_clk ? mma_clk : port_clk;
         if (split_issue > stage_clk) stage_clk = split_issue;
         const double fill = r >= 4 ? 0.0 : (r == 3 ? 40.0 : 700.0);        // exposed load latency per stage when the ring is shallow
@@ -774,6 +785,14 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
   ws_extent(d.KW, d.pad_w, d.stride, &a.smin_w, &a.KWe);
   const int cc_max = ws_cc_max(a.KWe);
   if (cc_max < 8) return DMVS_ERR_UNSUPPORTED;
+  // <= 4 input channels: a K = 8 MMA would multiply an all-zero channel quad.  Instead the second quad is the SAME staged
+  // plane one tile row further down (the A descriptor's leading-dimension offset is one row of positions instead of one
+  // plane), i.e. K = (kernel rows 2j, 2j+1) x 4 channels: ceil(KH/2) row-MMAs, one TMA box and half the split work per
+  // stage.  The weights come pair-packed (`w_ws_pair`, packing.pack_ws_pair).
+  a.pair = d.w_ws_pair != nullptr && aligned16(d.w_ws_pair) && a.S == 1 && d.C1 <= 4 && d.C2 == 0 && d.KH >= 2 &&
+           d.in_stats == nullptr;
+  a.KHm = a.pair ? (a.KHe + 1) / 2 : a.KHe;
+  if (a.pair) a.d.w_ws = d.w_ws_pair;
   int remaining = (d.Cout + 7) & ~7, co_base = 0;
   int64_t w_off = 0;
   int n_launch = 0;
@@ -781,7 +800,7 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
     const int CC = remaining < cc_max ? remaining : cc_max;
     const int N = (a.KWe * CC + 15) & ~15;
     TileCfg2 t;
-    choose_tile2(d, a.S, a.KHe, a.KWe, N, CC, a.cin_pad, t);
+    choose_tile2(d, a.S, a.KHe, a.KWe, N, CC, a.cin_pad, a.pair != 0, t);
     if (!t.TH) return DMVS_ERR_UNSUPPORTED;
     a.co_base = co_base;
     a.CC = CC;
@@ -791,19 +810,19 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
                  (d.bias == nullptr || a.vec_bias) && (d.res_mode == DMVS_RES_NONE || a.vec_res) && co_base + CC <= d.Cout;
     a.TH = t.TH;
     a.TW = t.TW;
-    a.in_rows = t.TH + a.KHe - 1;
+    a.in_rows = t.TH + (a.pair ? 2 * a.KHm : a.KHe) - 1;   // paired: the zero-weight half of the last pair reads real rows
     a.in_cols = t.in_cols;
     a.plane = t.plane;
     a.box_units = a.in_rows * a.in_cols;
     a.n_blk = t.n_blk;
     a.acc_cols = t.n_blk * N;
     a.R = t.R;
-    a.stage_f = 2 * t.plane * 4;
-    a.wslab_f = a.KHe * 2 * N * 4;
+    a.stage_f = (a.pair ? 1 : 2) * t.plane * 4;
+    a.wslab_f = a.KHm * 2 * N * 4;
     a.halo_f = t.halo_f;
     a.inv_in_cols = 1.0f / (float)t.in_cols;
     // packed slabs of this chunk: [hi | lo][KD][S*S phases][cin_pad/8][KHe][2][N][4]
-    const int64_t plane_w = (int64_t)d.KD * a.S * a.S * (a.cin_pad >> 3) * a.KHe * 2 * N * 4;
+    const int64_t plane_w = (int64_t)d.KD * a.S * a.S * (a.cin_pad >> 3) * a.KHm * 2 * N * 4;
     a.w_off = w_off;
     a.w_plane = plane_w;
     int cols = 32;

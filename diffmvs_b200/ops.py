@@ -282,6 +282,9 @@ class PackedConv:
     w_tc: Optional[Tensor] = None  # tcgen05 layout [2(hi,lo),KD,KH*KW,cin_pad8/4,cout_pad16,4]
     w_ws: Optional[Tensor] = None  # width-stacked tcgen05 slabs for stride 1 (packing.pack_ws)
     ws_strided: Optional[dict] = None   # (stride, pad_h, pad_w) -> slabs for strided use, built on first use
+    w_ws_pair: Optional[Tensor] = None  # <= 4 input channels: slabs with kernel rows paired along K (packing.pack_ws_pair)
+    w_host: Optional[Tensor] = None     # 8 -> 1 3x3x3 layers: [kd][kh][kw][ci] on the HOST (ops.conv3d_to1 launch parameters)
+    bias_host: float = 0.0
 
     def ws_slabs(self, stride: int, pad_h: int, pad_w: int) -> Optional[Tensor]:
         if stride == 1 or self.w_ws is None:
@@ -297,7 +300,7 @@ class PackedConv:
     def to(self, device) -> "PackedConv":
         mv = lambda t: None if t is None else t.to(device)
         return PackedConv(self.w.to(device), mv(self.bias), self.cin, self.cout, self.k, mv(self.w_t), mv(self.w_tc),
-                          mv(self.w_ws))
+                          mv(self.w_ws), None, mv(self.w_ws_pair), self.w_host, self.bias_host)
 
 
 @dataclass
@@ -357,6 +360,7 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         d.in_inv_count = 1.0 / float(D * H * W * (C1 // 4))
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
     d.w_t, d.w_tc, d.w_ws = _ptr(pc.w_t), _ptr(pc.w_tc), _ptr(pc.ws_slabs(stride, ph, pw))
+    d.w_ws_pair = _ptr(pc.w_ws_pair) if stride == 1 else None
     d.precision = _precision if pc.w_t is not None else PREC_FP32
     if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3) and pc.w_tc is None:
         d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3, PREC_WS2_TF32X3) else PREC_TF32
@@ -399,6 +403,22 @@ def deconv3d(x: Tensor, w: Tensor, bias: Tensor, skip: Tensor) -> Tensor:
     y = torch.empty_like(skip)
     check(_cabi.lib().dmvs_deconv3d_f32(_ptr(x), _ptr(w), _ptr(bias), _ptr(skip), _ptr(y), N, D, H, W, Cin, Cout,
                                         _stream()), "dmvs_deconv3d_f32")
+    return y
+
+
+@_profiled("conv3d_to1")
+def conv3d_to1(x: Tensor, pc: "PackedConv", sigmoid_max: bool = False) -> Tensor:
+    """Conv3d(8 -> 1, k=3, p=1) of a channels-last volume x [N,D,H,W,8] (a channel slice of a wider buffer is fine).
+    Returns the logits [N,D,H,W] or, with `sigmoid_max`, max_d sigmoid(logit) [N,H,W] (PixelViewWeight.forward,
+    module.py:459-463).  fp32 FFMA arithmetic whatever the precision mode."""
+    _req_cuda_f32(x, "x")
+    if x.dim() != 5 or pc.cin != 8 or pc.cout != 1 or tuple(pc.k) != (3, 3, 3) or pc.w_host is None:
+        raise ValueError("conv3d_to1: needs [N,D,H,W,8] input and a packed 8 -> 1 3x3x3 layer")
+    N, D, H, W, C = x.shape
+    ps = pixel_stride(x, "conv3d_to1 input")
+    y = torch.empty((N, H, W) if sigmoid_max else (N, D, H, W), device=x.device, dtype=torch.float32)
+    check(_cabi.lib().dmvs_conv3d_to1_f32(_ptr(x), ps, pc.w_host.data_ptr(), float(pc.bias_host), _ptr(y), N, D, H, W,
+                                          1 if sigmoid_max else 0, _stream()), "dmvs_conv3d_to1_f32")
     return y
 
 

@@ -56,7 +56,13 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None, pad_cin: i
     lo = rna_tf32(quad - hi)
     w_tc = torch.stack((hi, lo), 0).contiguous()
     w_ws = pack_ws(full.view(kd, kh, kw, ci8, co16), cout) if kw <= 8 else None   # stride-1 slabs
-    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc, w_ws)
+    w_pair = pack_ws_pair(full.view(kd, kh, kw, ci8, co16), cout) if (w_ws is not None and cin <= 4 and kh >= 2) else None
+    w_host, bias_host = None, 0.0
+    if cout == 1 and cin == 8 and (kd, kh, kw) == (3, 3, 3):     # ops.conv3d_to1: weights travel as launch parameters
+        w_host = w[0].permute(1, 2, 3, 0).contiguous()             # [kd][kh][kw][ci]
+        bias_host = 0.0 if b is None else float(b[0])
+    return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc, w_ws, None, w_pair,
+                      w_host, bias_host)
 
 
 def ws_cc_max(kw: int) -> int:
@@ -103,6 +109,32 @@ def pack_ws(full: torch.Tensor, cout: int, stride: int = 1, pad: Tuple[int, int]
                         # [kd][ci8][avail] -> [kd][chunk][quad][4][avail] -> [kd][chunk][quad][avail][4]
                         tap = full[:, th, tw, :, co_base:co_base + avail].reshape(kd, ci8 // 8, 2, 4, avail)
                         slab[:, pa * S + pb, :, khs, :, kws * cc:kws * cc + avail, :] = tap.permute(0, 1, 2, 4, 3)
+        hi = rna_tf32(slab)
+        lo = rna_tf32(slab - hi)
+        parts += [hi.reshape(-1), lo.reshape(-1)]
+        co_base += cc
+        remaining -= cc
+    return torch.cat(parts).contiguous()
+
+
+def pack_ws_pair(full: torch.Tensor, cout: int) -> torch.Tensor:
+    """Stride-1 slabs for layers with <= 4 input channels (`w_ws_pair`, include/diffmvs_b200.h): the K = 8 of one MMA
+    spans kernel rows (2j, 2j+1) x input channels 0..3 instead of 8 channels of one row.  Per output-channel chunk two
+    planes (hi, lo), each [KD][ceil(KH/2)][2][N][4], column kw*CC + c; the odd row past KH-1 is zero."""
+    kd, kh, kw, ci8, co16 = full.shape
+    assert float(full[:, :, :, 4:, :].abs().max()) == 0.0, "pair packing is for <= 4 input channels"
+    khp = (kh + 1) // 2
+    cc_max = ws_cc_max(kw)
+    remaining, co_base, parts = (cout + 7) & ~7, 0, []
+    while remaining > 0:
+        cc = min(remaining, cc_max)
+        n = (kw * cc + 15) & ~15
+        avail = min(cc, co16 - co_base)
+        slab = torch.zeros(kd, khp, 2, n, 4, dtype=torch.float32)
+        for r in range(kh):
+            for kws in range(kw):
+                # [kd][4][avail] -> [kd][avail][4]
+                slab[:, r // 2, r % 2, kws * cc:kws * cc + avail, :] = full[:, r, kws, :4, co_base:co_base + avail].permute(0, 2, 1)
         hi = rna_tf32(slab)
         lo = rna_tf32(slab - hi)
         parts += [hi.reshape(-1), lo.reshape(-1)]

@@ -193,8 +193,7 @@ class ViewWeightPlan:
 
     def __call__(self, cor: Tensor) -> Tensor:
         y = ops.conv(cor, self.c0, act=ACT_RELU)
-        logit = ops.conv(y, self.c1)                      # [N,D,H,W,1]
-        return ops.view_weight_max(logit.squeeze(-1))
+        return ops.conv3d_to1(y, self.c1, sigmoid_max=True)   # conv 8 -> 1, sigmoid, max over depth: one launch
 
 
 class CostRegPlan:
@@ -214,7 +213,7 @@ class CostRegPlan:
         x = ops.conv(ops.conv(c3, self.reg[4], stride=2, act=ACT_RELU), self.reg[5], act=ACT_RELU)
         x = ops.deconv3d(x, self.dc6[0], self.dc6[1], c3)
         x = ops.deconv3d(x, self.dc7[0], self.dc7[1], c1)
-        return ops.conv(x, self.prob).squeeze(-1)
+        return ops.conv3d_to1(x, self.prob)
 
 
 class InitialCostPlan:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DMVS_ABI_VERSION 3
+#define DMVS_ABI_VERSION 4
 
 #define DMVS_ERR_ARG (-1)      /* null pointer / non-positive size / unsupported combination */
 #define DMVS_ERR_ALIGN (-2)    /* pointer or stride not aligned as documented */
@@ -103,6 +103,11 @@ typedef struct dmvs_conv_desc {
                                channels, N = KWe*CC rounded up to 16) two planes (hi, lo), each
                                [KD][S*S][cin_pad8/8][KHe][2 channel quads][N][4] with column kw'*CC + c, zero where a
                                phase has no tap (packing.pack_ws); may be NULL */
+  const float* w_ws_pair;   /* optional, layers with <= 4 input channels and KH >= 2 (stride 1): the width-stacked layout with
+                               kernel rows PAIRED along the MMA's K dimension, per output-channel chunk two planes (hi, lo),
+                               each [KD][ceil(KH/2)][2][N][4]: quad q of pair j holds kernel row 2j+q (zero past KH-1) of
+                               input channels 0..3 (packing.pack_ws_pair).  The TMA-fed back end then issues ceil(KH/2)
+                               row-MMAs per stage instead of KH and stages one channel quad instead of two. */
   int32_t precision;        /* DMVS_PREC_* */
   const float* bias;        /* [Cout] or NULL */
   int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;
@@ -148,6 +153,16 @@ int dmvs_conv_ws2_timeline(int64_t* out, int32_t count);
  * x [N][D][H][W][Cin] -> y [N][2D][2H][2W][Cout]; w packed [27][Cin][Cout]; skip has y's shape. */
 int dmvs_deconv3d_f32(const float* x, const float* w, const float* bias, const float* skip, float* y,
                       int32_t N, int32_t D, int32_t H, int32_t W, int32_t Cin, int32_t Cout, void* stream);
+
+/* Conv3d(8 -> 1, k=3, s=1, p=1) marching along depth (conv3d_to1.cu): the output layer of PixelViewWeight
+ * (module.py:454-457) and CostRegNet_small.prob (module.py:439,447).  x [N][D][H][W][x_ps >= 8] (16-byte aligned
+ * pixels); w_host = the 216 weights [kd][kh][kw][ci] in HOST memory (they travel as launch parameters and become
+ * constant-bank operands; read before the call returns).
+ * mode 0: y [N][D][H][W] = conv + bias.
+ * mode 1: y [N][H][W] = max over depth of sigmoid(conv + bias) - PixelViewWeight.forward's tail (module.py:459-463)
+ *         fused, the logits never reach memory. */
+int dmvs_conv3d_to1_f32(const float* x, int32_t x_ps, const float* w_host, float bias, float* y, int32_t N, int32_t D,
+                        int32_t H, int32_t W, int32_t mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Homography warp + group-wise correlation (module.py:181-218, 514-548, 575-667).

@@ -176,6 +176,59 @@ def test_conv3d_matches_torch(cin, cout, stride, precision):
     _close(y.permute(0, 4, 1, 2, 3).cpu(), ref, tol=PREC_TOL[precision], what=f"conv3d {cin}->{cout} s{stride} [{precision}]")
 
 
+@pytest.mark.parametrize("cin,cout,k,dims", [
+    (3, 8, (1, 3, 3), (1, 100, 260)),      # RGB staged as 4 channels (FeatureNet conv0.0), multi-tile
+    (4, 16, (1, 5, 5), (1, 40, 72)),
+    (4, 8, (1, 7, 7), (1, 33, 50)),
+    (4, 8, (3, 3, 3), (6, 40, 70)),        # PixelViewWeight / CostRegNet first layers
+    (1, 8, (3, 3, 3), (5, 20, 33)),
+    (4, 72, (1, 3, 3), (1, 24, 40)),       # two output-channel chunks
+])
+def test_conv_paired_kernel_rows(cin, cout, k, dims):
+    """<= 4 input channels on the TMA-fed tcgen05 back end: kernel rows paired along K (`w_ws_pair`)."""
+    old = ops.get_precision()
+    ops.set_precision("ws2_tf32x3")
+    try:
+        N = 2
+        D, H, W = dims
+        three_d = k[0] > 1
+        x = _rand(N, cin, D, H, W, seed=11)
+        w = _rand(cout, cin, *k, seed=12) * (1.0 / math.sqrt(cin * k[0] * k[1] * k[2]))
+        b = _rand(cout, seed=13)
+        ref = F.relu(F.conv3d(x, w, b, padding=(k[0] // 2, k[1] // 2, k[2] // 2)))
+        cin_st = 4 if cin == 3 else cin                         # ws2 needs 16-byte pixel strides
+        xs = torch.zeros(N, D, H, W, cin_st)
+        xs[..., :cin] = x.permute(0, 2, 3, 4, 1)
+        pc = packing.pack_weight(w if three_d else w[:, :, 0], b, pad_cin=cin_st if cin_st != cin else 0).to(DEV)
+        assert pc.w_ws_pair is not None
+        xin = xs.to(DEV) if three_d else xs[:, 0].contiguous().to(DEV)
+        y = ops.conv(xin, pc, act=ops.ACT_RELU)
+        if cin_st % 4 == 0:
+            assert ops._LAST_CONV_BACKEND == ops.PREC_WS2_TF32X3
+        got = y.cpu() if three_d else y.cpu().unsqueeze(1)
+        _close(got.permute(0, 4, 1, 2, 3), ref, tol=PREC_TOL["ws2_tf32x3"], what=f"paired conv {cin}->{cout} k{k}")
+    finally:
+        ops.set_precision(old)
+
+
+@pytest.mark.parametrize("N,D,H,W,ps", [(2, 5, 13, 37, 8), (1, 9, 20, 70, 12), (3, 1, 8, 32, 8), (1, 48, 18, 50, 8)])
+def test_conv3d_to1_matches_torch(N, D, H, W, ps):
+    """Depth-marching Conv3d(8 -> 1): logits, and PixelViewWeight's sigmoid + max over depth (module.py:459-463)."""
+    x = _rand(N, 8, D, H, W, seed=21)
+    w, b = _rand(1, 8, 3, 3, 3, seed=22) * (1 / math.sqrt(27 * 8)), _rand(1, seed=23)
+    ref = F.conv3d(x, w, b, padding=1)[:, 0]
+    buf = torch.zeros(N, D, H, W, ps)
+    buf[..., :8] = x.permute(0, 2, 3, 4, 1)
+    xin = buf.to(DEV)[..., :8]                                   # a channel slice of a wider buffer when ps > 8
+    pc = packing.pack_weight(w, b).to(DEV)
+    y = ops.conv3d_to1(xin, pc)
+    _close(y.cpu(), ref, tol=2e-6, what="conv3d_to1 logits")
+    vw = ops.conv3d_to1(xin, pc, sigmoid_max=True)
+    _close(vw.cpu(), torch.sigmoid(ref).max(dim=1)[0], tol=2e-6, what="conv3d_to1 sigmoid-max")
+    pc0 = packing.pack_weight(w, None).to(DEV)                   # CostRegNet_small.prob has no bias
+    _close(ops.conv3d_to1(xin, pc0).cpu(), F.conv3d(x, w, None, padding=1)[:, 0], tol=2e-6, what="conv3d_to1 no bias")
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 16), (16, 8)])
 def test_deconv3d_matches_torch(cin, cout):
     N, D, H, W = 1, 3, 5, 7

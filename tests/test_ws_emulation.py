@@ -14,7 +14,7 @@ import torch.nn.functional as F
 
 from diffmvs_b200 import packing
 
-def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1):
+def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1, pair=False):
     """x [H,W,Cin] (numpy), pc PackedConv (2-D) -> y [Ho,Wo,Cout] via the kernel's data movement (stride S)."""
     H, W, Cin = x.shape
     KD, KH_real, KW_real = pc.k
@@ -31,22 +31,28 @@ def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1):
     N = (KW * CC + 15) & ~15
     # this launch's packed slabs: the chunks before co_base come first in w_ws (packing.pack_ws)
     w_ws = (pc.w_ws if S == 1 else packing.pack_ws_from_packed(pc.w, Cout, S, (pad_h, pad_w))).numpy()
+    # paired kernel rows (conv_ws2.cu, <= 4 input channels): KHm row-MMAs per stage, K = (rows 2j, 2j+1) x 4 channels
+    KHm = (KH + 1) // 2 if pair else KH
+    if pair:
+        assert S == 1 and Cin <= 4 and pc.w_ws_pair is not None
+        w_ws = pc.w_ws_pair.numpy()
     nchunks = cin_pad // 8
     nphase = S * S
     cc_max = packing.ws_cc_max(KW)
     w_off, rem, base = 0, (Cout + 7) & ~7, 0
     while base < co_base:
         cc = min(rem, cc_max)
-        w_off += 2 * KD * nphase * nchunks * KH * 2 * ((KW * cc + 15) & ~15) * 4
+        w_off += 2 * KD * nphase * nchunks * KHm * 2 * ((KW * cc + 15) & ~15) * 4
         base += cc
         rem -= cc
     assert base == co_base and CC == min(rem, cc_max), "test case must follow the kernel's channel chunking"
-    wslab_f = KH * 2 * N * 4
+    wslab_f = KHm * 2 * N * 4
     w_plane = KD * nphase * nchunks * wslab_f
-    in_rows, in_cols = TH + KH - 1, TW + KW - 1
+    KHg = 2 * KHm if pair else KH                              # staged rows beyond the tile height, + 1
+    in_rows, in_cols = TH + KHg - 1, TW + KW - 1
     m_total = TH * in_cols
     n_blk = -(-m_total // 128)
-    plane = (n_blk * 128 + (KH - 1) * in_cols + 8 + 7) & ~7
+    plane = (n_blk * 128 + (KHg - 1) * in_cols + 8 + 7) & ~7
     y = np.full((Ho, Wo, Cout), np.nan, dtype=np.float64)
     rng = np.random.default_rng(0)
     for ty0 in range(0, Ho, TH):
@@ -61,7 +67,7 @@ def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1):
                     iy = S * (ty0 + smin_h) + pa + S * row
                     for col in range(in_cols):
                         ix = S * (tx0 + smin_w) + pb + S * col
-                        for q in range(2):
+                        for q in range(1 if pair else 2):
                             ch = c0 + q * 4
                             ok = 0 <= iy < H and 0 <= ix < W and ch < Cin
                             v = np.zeros(4)
@@ -72,10 +78,16 @@ def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1):
                 # ---- weight slab [kh][quad][N][4] from the packed global layout ---------------------------
                 src = w_off + ((0 * nphase + phase) * nchunks + chunk) * wslab_f
                 slab = (w_ws[src:src + wslab_f] + w_ws[src + w_plane:src + w_plane + wslab_f]).astype(np.float64)  # hi + lo
-                slab = slab.reshape(KH, 2, N, 4)
+                slab = slab.reshape(KHm, 2, N, 4)
                 # ---- MMAs: per block and kernel row one instruction, N columns ---------------------------
                 for blk in range(n_blk):
-                    for kh in range(KH):
+                    for khp in range(KHm if pair else 0):
+                        # the A descriptor's leading-dimension offset is one tile row: K quad 1 = quad 0 one row down
+                        a_off = blk * 128 + 2 * khp * in_cols
+                        a_op = np.concatenate([A[0, a_off:a_off + 128], A[0, a_off + in_cols:a_off + in_cols + 128]], axis=1)
+                        b_op = np.concatenate([slab[khp, 0], slab[khp, 1]], axis=1)
+                        E[blk * 128:(blk + 1) * 128] += a_op @ b_op.T
+                    for kh in range(0 if pair else KH):
                         tap_row = S * (kh + smin_h) + pa + pad_h
                         if not 0 <= tap_row < KH_real:          # this phase has no kernel row behind shift kh
                             continue
@@ -185,4 +197,43 @@ def test_ws_stride2_phases_match_conv2d(cin, cout, k, H, W, TH, TW, CC):
     got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, TH, TW, CC, S=2)
     assert got.shape == ref.shape
     assert not np.isnan(got).any(), "some output was never written"
+    assert np.abs(got - ref).max() < 1e-6
+
+
+PAIR_CASES = [
+    # cin, cout, (kh,kw), H, W, TH, TW, CC
+    (3, 8, (3, 3), 21, 40, 8, 30, 8),
+    (4, 8, (3, 3), 16, 35, 16, 30, 8),
+    (4, 16, (5, 5), 18, 30, 4, 28, 16),
+    (1, 8, (3, 3), 12, 31, 4, 30, 8),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,H,W,TH,TW,CC", PAIR_CASES)
+def test_paired_rows_bookkeeping_matches_conv2d(cin, cout, k, H, W, TH, TW, CC):
+    """<= 4 input channels: kernel rows paired along K (`w_ws_pair`, one staged channel quad, A leading offset = one row)."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(1, cin, H, W, generator=g) - 0.5
+    w = (torch.rand(cout, cin, *k, generator=g) - 0.5) / math.sqrt(cin * k[0] * k[1])
+    pc = packing.pack_weight(w, None)
+    assert pc.w_ws_pair is not None
+    pad = (k[0] // 2, k[1] // 2)
+    ref = F.conv2d(x.double(), w.double(), padding=pad)[0].permute(1, 2, 0).numpy()
+    got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, TH, TW, CC, pair=True)
+    assert not np.isnan(got).any(), "some output was never written"
+    assert np.abs(got - ref).max() < 1e-6
+
+
+def test_paired_rows_two_channel_chunks():
+    """Cout = 72 runs as two launches (64 + 8 channels) over consecutive `w_ws_pair` chunks."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 4, 9, 33, generator=g) - 0.5
+    w = (torch.rand(72, 4, 3, 3, generator=g) - 0.5) / 6.0
+    pc = packing.pack_weight(w, None)
+    ref = F.conv2d(x.double(), w.double(), padding=1)[0].permute(1, 2, 0).numpy()
+    xin = x[0].permute(1, 2, 0).double().numpy()
+    a = emulate_ws_conv(xin, pc, 4, 30, 64, co_base=0, pair=True)
+    b = emulate_ws_conv(xin, pc, 4, 30, 8, co_base=64, pair=True)
+    got = np.where(np.isnan(a), b, a)
+    assert not np.isnan(got).any()
     assert np.abs(got - ref).max() < 1e-6

@@ -28,11 +28,15 @@ for name, N, cin, cout, k, s, dims in LAYERS:
         continue
     g = torch.Generator().manual_seed(0)
     three_d = k[0] > 1 or dims[0] > 1
-    shape = (N, *dims, cin) if three_d else (N, dims[1], dims[2], cin)
-    x = torch.rand(*shape, generator=g).cuda()
+    cin_st = 4 if cin == 3 else cin        # RGB images are staged with a zero fourth channel (pipeline.py)
+    shape = (N, *dims, cin_st) if three_d else (N, dims[1], dims[2], cin_st)
+    x = torch.rand(*shape, generator=g)
+    if cin_st != cin:
+        x[..., cin:] = 0
+    x = x.cuda()
     wshape = (cout, cin, *k) if three_d else (cout, cin, k[1], k[2])
     w = (torch.rand(*wshape, generator=g) - 0.5) / math.sqrt(cin * k[0] * k[1] * k[2])
-    pc = packing.pack_weight(w, torch.zeros(cout)).to("cuda")
+    pc = packing.pack_weight(w, torch.zeros(cout), pad_cin=cin_st if cin_st != cin else 0).to("cuda")
     ops.set_precision("ws2_tf32x3")
     y = ops.conv(x, pc, stride=s, act=ops.ACT_RELU)
     ops.conv(x, pc, stride=s, act=ops.ACT_RELU, out=y)
