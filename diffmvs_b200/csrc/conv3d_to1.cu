@@ -25,6 +25,7 @@ struct To1Args {
   int x_ps;
   int N, D, H, W;
   int mode;            // 0: y = conv + bias   1: y = max_d sigmoid(conv + bias)
+  int segs, seg_len;   // mode 0: the depth range is cut into `segs` segments of `seg_len` output slices (more CTAs for small N)
   float bias;
   float w[27 * kCin];  // [kd][kh][kw][ci]
 };
@@ -40,32 +41,47 @@ __global__ void __launch_bounds__(kTW * kTH) conv3d_to1_kernel(const __grid_cons
   __shared__ __align__(16) float tile[2][2][kTilePx][4];
   const int tid = threadIdx.x;
   const int lx = tid & 31, ly = tid >> 5;
-  const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, n = blockIdx.z;
+  const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH;
+  const int n = blockIdx.z / a.segs, seg = blockIdx.z - n * a.segs;
+  const int d0 = seg * a.seg_len, d1 = min(d0 + a.seg_len, a.D);          // output slices of this CTA
+  const int zs = max(d0 - 1, 0), ze = min(d1 + 1, a.D);                    // input slices it walks
   const int ox = x0 + lx, oy = y0 + ly;
   const bool valid = ox < a.W && oy < a.H;
   pdl_sync();
 
+  // the (quad, pixel) units this thread stages are the same for every slice: offsets and bounds once
+  constexpr int kUnits = (2 * kTilePx + kTW * kTH - 1) / (kTW * kTH);   // 3
+  int src_off[kUnits], dst_off[kUnits];
+#pragma unroll
+  for (int i = 0; i < kUnits; ++i) {
+    const int u = tid + i * kTW * kTH;
+    const int q = u / kTilePx, p = u - q * kTilePx;
+    const int r = p / kIW, c = p - r * kIW;
+    const int iy = y0 - 1 + r, ix = x0 - 1 + c;
+    const bool ok = u < 2 * kTilePx && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+    src_off[i] = ok ? (iy * a.W + ix) * a.x_ps + q * 4 : -1;          // one slice is < 2^31 floats (host-checked)
+    dst_off[i] = u < 2 * kTilePx ? (q * kTilePx + p) * 4 : -1;
+  }
+  const int64_t slice_in = (int64_t)a.H * a.W * a.x_ps;
   auto stage = [&](int z, int buf) {
-    const float* slice = a.x + ((int64_t)(n * a.D + z) * a.H) * a.W * a.x_ps;
-    for (int u = tid; u < 2 * kTilePx; u += kTW * kTH) {
-      const int q = u / kTilePx, p = u - q * kTilePx;
-      const int r = p / kIW, c = p - r * kIW;
-      const int iy = y0 - 1 + r, ix = x0 - 1 + c;
-      const bool ok = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-      const float* src = ok ? slice + ((int64_t)iy * a.W + ix) * a.x_ps + q * 4 : a.x;
-      cp_async16_zfill(&tile[buf][q][p][0], src, ok);
+    const float* slice = a.x + (int64_t)(n * a.D + z) * slice_in;
+#pragma unroll
+    for (int i = 0; i < kUnits; ++i) {
+      if (dst_off[i] < 0) continue;
+      const bool ok = src_off[i] >= 0;
+      cp_async16_zfill(&tile[buf][0][0][0] + dst_off[i], ok ? slice + src_off[i] : a.x, ok);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
 
-  stage(0, 0);
+  stage(zs, 0);
   float p0 = 0.f, p1 = 0.f;          // partial sums of output slices z-1 (taps kd = 0, 1 done) and z (tap kd = 0 done)
   float best = 0.f;                   // mode 1: sigmoid > 0, so 0 is below every candidate
   float* yout = a.y + ((int64_t)n * (a.mode == 0 ? a.D : 1) * a.H + oy) * a.W + ox;
   const int64_t slice_out = (int64_t)a.H * a.W;
-  for (int z = 0; z < a.D; ++z) {
-    const int buf = z & 1;
-    if (z + 1 < a.D) {
+  for (int z = zs; z < ze; ++z) {
+    const int buf = (z - zs) & 1;
+    if (z + 1 < ze) {
       stage(z + 1, buf ^ 1);
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
     } else {
@@ -91,7 +107,7 @@ __global__ void __launch_bounds__(kTW * kTH) conv3d_to1_kernel(const __grid_cons
       }
     }
     __syncthreads();                 // the buffer is refilled by the next iteration's prefetch
-    if (z >= 1) {                    // output slice z-1 is complete: taps kd = 0, 1 (earlier slices) + kd = 2 (this one)
+    if (z - 1 >= d0) {               // output slice z-1 is complete: taps kd = 0, 1 (earlier slices) + kd = 2 (this one)
       const float o = (p0 + t2) + a.bias;
       if (a.mode == 0) {
         if (valid) yout[(int64_t)(z - 1) * slice_out] = o;
@@ -102,15 +118,15 @@ __global__ void __launch_bounds__(kTW * kTH) conv3d_to1_kernel(const __grid_cons
     p0 = p1 + t1;
     p1 = t0;
   }
-  {                                  // last output slice: its kd = 2 tap reads the zero padding
+  if (d1 == a.D) {                   // last output slice of the volume: its kd = 2 tap reads the zero padding
     const float o = p0 + a.bias;
     if (a.mode == 0) {
       if (valid) yout[(int64_t)(a.D - 1) * slice_out] = o;
     } else {
       best = fmaxf(best, sigmoidf_(o));
-      if (valid) *yout = best;
     }
   }
+  if (a.mode == 1 && valid) *yout = best;
 }
 
 }  // namespace
@@ -123,7 +139,7 @@ extern "C" int dmvs_conv3d_to1_f32(const float* x, int32_t x_ps, const float* w_
   if (!x || !w_host || !y) return DMVS_ERR_ARG;
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || x_ps < kCin || (mode != 0 && mode != 1)) return DMVS_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0 || (x_ps % 4) != 0) return DMVS_ERR_ALIGN;
-  if (N > 65535 || ceil_div(H, kTH) > 65535) return DMVS_ERR_UNSUPPORTED;
+  if (N > 65535 || ceil_div(H, kTH) > 65535 || (int64_t)H * W * x_ps > 0x7fffffffLL) return DMVS_ERR_UNSUPPORTED;
   To1Args a;
   a.x = x;
   a.y = y;
@@ -132,7 +148,19 @@ extern "C" int dmvs_conv3d_to1_f32(const float* x, int32_t x_ps, const float* w_
   a.mode = mode;
   a.bias = bias;
   for (int i = 0; i < 27 * kCin; ++i) a.w[i] = w_host[i];
-  const dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), N);
+  // small batches: cut the depth range so that about four CTAs per SM exist (each segment re-reads two halo slices);
+  // the fused maximum over depth keeps one CTA per pixel column
+  const int ctas = ceil_div(W, kTW) * ceil_div(H, kTH) * N;
+  int segs = 1;
+  if (mode == 0) {
+    segs = ceil_div(4 * kNumSMs, ctas);
+    if (segs > D / 8) segs = D / 8;
+    if (segs < 1) segs = 1;
+  }
+  a.seg_len = ceil_div(D, segs);
+  a.segs = ceil_div(D, a.seg_len);
+  if ((int64_t)N * a.segs > 65535) return DMVS_ERR_UNSUPPORTED;
+  const dim3 grid(ceil_div(W, kTW), ceil_div(H, kTH), N * a.segs);
   launch_pdl(conv3d_to1_kernel, grid, dim3(kTW * kTH), 0, static_cast<cudaStream_t>(stream), a);
   return launch_status();
 }

@@ -211,7 +211,7 @@ def test_conv_paired_kernel_rows(cin, cout, k, dims):
         ops.set_precision(old)
 
 
-@pytest.mark.parametrize("N,D,H,W,ps", [(2, 5, 13, 37, 8), (1, 9, 20, 70, 12), (3, 1, 8, 32, 8), (1, 48, 18, 50, 8)])
+@pytest.mark.parametrize("N,D,H,W,ps", [(2, 5, 13, 37, 8), (1, 9, 20, 70, 12), (3, 1, 8, 32, 8), (1, 48, 18, 50, 8), (1, 20, 9, 33, 8)])
 def test_conv3d_to1_matches_torch(N, D, H, W, ps):
     """Depth-marching Conv3d(8 -> 1): logits, and PixelViewWeight's sigmoid + max over depth (module.py:459-463)."""
     x = _rand(N, 8, D, H, W, seed=21)
