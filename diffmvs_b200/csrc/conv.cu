@@ -443,6 +443,106 @@ __global__ void __launch_bounds__(128) deconv3d_kernel(const float* __restrict__
   }
 }
 
+// Parity form of the same operator for the two shapes CostRegNet_small uses (32 -> 16 and 16 -> 8 channels).
+// An output voxel (2z+pz, 2y+py, 2x+px) reads kernel tap 1 of input index i along a dimension of even parity and taps
+// 0 (input i+1) and 2 (input i) along a dimension of odd parity: 1, 2, 4 or 8 taps depending on the parity class.  A
+// warp owns one parity class of 32 consecutive input columns, so its tap list is warp-uniform (no divergence), the
+// weights are 128-bit shared-memory broadcasts feeding four FFMAs each, and the four warps of a CTA take class lists of
+// 8, 7, 6 and 6 taps: together they write the complete 2 x 2 x 2 output octets of their 32 input voxels.  Persistent
+// CTAs load the 27 x Cin x Cout weights once.  Summation order = the gather kernel above (results are bit-identical).
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128) deconv3d_parity_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias,
+                                                              const float* __restrict__ skip, float* __restrict__ y,
+                                                              int N, int D, int H, int W) {
+  extern __shared__ __align__(16) float ws[];  // [27][CIN][COUT]
+  // the weights never change after packing: staged before the dependency wait, overlapping the producer's tail
+  for (int i = threadIdx.x * 4; i < 27 * CIN * COUT; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(ws + i) = ldg4(w + i);
+  pdl_sync();
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // parity classes (bit 2: depth, bit 1: row, bit 0: column) per warp, 0xF terminated: 8 | 4+2+1 | 4+2 | 4+2 taps
+  const unsigned my_list = warp == 0 ? 0xFFF7u : warp == 1 ? 0xF046u : warp == 2 ? 0xFF25u : 0xFF13u;
+  const int xchunks = ceil_div(W, 32);
+  const int64_t items = (int64_t)N * D * H * xchunks;
+  const int Ho = 2 * H, Wo = 2 * W;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int xc = (int)(item % xchunks);
+    int64_t t = item / xchunks;
+    const int iy = (int)(t % H);
+    t /= H;
+    const int iz = (int)(t % D);
+    const int n = (int)(t / D);
+    const int ix = xc * 32 + lane;
+    for (unsigned list = my_list; (list & 0xFu) != 0xFu; list >>= 4) {
+      const int pz = (list >> 2) & 1, py = (list >> 1) & 1, px = list & 1;
+      float acc[COUT];
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+      for (int a = 0; a <= pz; ++a) {                       // odd parity: tap 0 reads input i+1, then tap 2 reads input i
+        const int kd = pz ? 2 * a : 1, sz = iz + (pz && a == 0 ? 1 : 0);
+        if (sz >= D) continue;
+        for (int b = 0; b <= py; ++b) {
+          const int kh = py ? 2 * b : 1, sy = iy + (py && b == 0 ? 1 : 0);
+          if (sy >= H) continue;
+          for (int c = 0; c <= px; ++c) {
+            const int kw = px ? 2 * c : 1, sx = ix + (px && c == 0 ? 1 : 0);
+            const bool ok = sx < W;
+            const float* xp = x + ((((int64_t)n * D + sz) * H + sy) * W + (ok ? sx : 0)) * CIN;
+            const float* wp = ws + ((kd * 3 + kh) * 3 + kw) * CIN * COUT;
+#pragma unroll 2
+            for (int c4 = 0; c4 < CIN; c4 += 4) {
+              float4 v = ldg4(xp + c4);
+              if (!ok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j4 = 0; j4 < COUT; j4 += 4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wp + (c4 + k) * COUT + j4);
+                  acc[j4 + 0] = fmaf(e[k], w4.x, acc[j4 + 0]);
+                  acc[j4 + 1] = fmaf(e[k], w4.y, acc[j4 + 1]);
+                  acc[j4 + 2] = fmaf(e[k], w4.z, acc[j4 + 2]);
+                  acc[j4 + 3] = fmaf(e[k], w4.w, acc[j4 + 3]);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (ix < W) {
+        const int64_t o = (((int64_t)n * 2 * D + 2 * iz + pz) * Ho + 2 * iy + py) * Wo + 2 * ix + px;
+        float* yp = y + o * COUT;
+        const float* sp = skip + o * COUT;
+#pragma unroll
+        for (int j4 = 0; j4 < COUT; j4 += 4) {
+          const float4 s = ldg4(sp + j4), b4 = ldg4(bias + j4);
+          float4 r;
+          r.x = fmaxf(acc[j4 + 0] + b4.x, 0.f) + s.x;
+          r.y = fmaxf(acc[j4 + 1] + b4.y, 0.f) + s.y;
+          r.z = fmaxf(acc[j4 + 2] + b4.z, 0.f) + s.z;
+          r.w = fmaxf(acc[j4 + 3] + b4.w, 0.f) + s.w;
+          *reinterpret_cast<float4*>(yp + j4) = r;
+        }
+      }
+    }
+  }
+}
+
+template <int CIN, int COUT>
+int launch_deconv3d_parity(const float* x, const float* w, const float* bias, const float* skip, float* y, int N, int D,
+                           int H, int W, cudaStream_t st) {
+  static SmemOptIn opt_in;
+  const size_t smem = (size_t)27 * CIN * COUT * 4;
+  opt_in.ensure(deconv3d_parity_kernel<CIN, COUT>, 100 * 1024);
+  const int64_t items = (int64_t)N * D * H * ceil_div(W, 32);
+  const int per_sm = smem > 40 * 1024 ? 3 : 8;
+  const int blocks = (int)(items < (int64_t)kNumSMs * per_sm ? items : (int64_t)kNumSMs * per_sm);
+  launch_pdl(deconv3d_parity_kernel<CIN, COUT>, dim3(blocks), dim3(128), smem, st, x, w, bias, skip, y, N, D, H, W);
+  return launch_status();
+}
+
 }  // namespace
 }  // namespace dmvs
 
@@ -452,10 +552,14 @@ extern "C" int dmvs_deconv3d_f32(const float* x, const float* w, const float* bi
   if (N <= 0 || D <= 0 || H <= 0 || W <= 0 || Cin <= 0 || (Cin % 4) != 0) return DMVS_ERR_ARG;
   if (Cout != 8 && Cout != 16) return DMVS_ERR_UNSUPPORTED;
   if (!aligned16(x) || !aligned16(skip) || !aligned16(y)) return DMVS_ERR_ALIGN;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (aligned16(w) && aligned16(bias)) {
+    if (Cin == 32 && Cout == 16) return launch_deconv3d_parity<32, 16>(x, w, bias, skip, y, N, D, H, W, st);
+    if (Cin == 16 && Cout == 8) return launch_deconv3d_parity<16, 8>(x, w, bias, skip, y, N, D, H, W, st);
+  }
   const size_t smem = (size_t)27 * Cin * Cout * 4;
   const int64_t total = (int64_t)N * 8 * D * H * W;
   int blocks = (int)(ceil_div64(total, 128) < (int64_t)kNumSMs * 16 ? ceil_div64(total, 128) : (int64_t)kNumSMs * 16);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (Cout == 8) {
     static SmemOptIn opt_in;
     opt_in.ensure(deconv3d_kernel<8>, 100 * 1024);
