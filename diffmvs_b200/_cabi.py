@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
         ("y", f32p), ("Do", i32), ("Ho", i32), ("Wo", i32), ("Cout", i32), ("y_ps", i32),
         ("act", i32), ("act_c0", i32), ("res_mode", i32), ("res", f32p), ("res_ps", i32), ("res_up2", i32),
         ("epi", i32), ("aux1", f32p), ("aux2", f32p), ("aux1_ps", i32), ("aux2_ps", i32), ("gru_hidden", i32),
+        ("explicit_extent", i32), ("y_row_stride", i32), ("res_row_stride", i32),
         ("out_stats", C.c_void_p),
     ]
 
@@ -52,6 +53,7 @@ SIGNATURES = {
     "dmvs_conv_ws2_timeline": (C.c_int, [C.POINTER(C.c_int64), i32]),
     "dmvs_deconv3d_f32": (C.c_int, [f32p, f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_conv3d_to1_f32": (C.c_int, [f32p, i32, C.c_void_p, C.c_float, f32p, i32, i32, i32, i32, i32, C.c_void_p]),
+    "dmvs_border_bias_add": (C.c_int, [f32p, i32, f32p, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_compose_homographies": (C.c_int, [f32p, f32p, i32, i32, C.c_void_p]),
     "dmvs_warp_volume": (C.c_int, [f32p, i32, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "dmvs_plane_sweep_corr": (C.c_int, [f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]),

@@ -224,11 +224,19 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
   if ((d.in_up2 || d.res_up2) && (d.D != 1 || d.KD != 1)) return DMVS_ERR_UNSUPPORTED;
   if (d.in_up2 && ((d.H | d.W) & 1)) return DMVS_ERR_ARG;
   if (d.res_up2 && ((d.Ho | d.Wo) & 1)) return DMVS_ERR_ARG;
-  // the output size must be what the geometry implies
-  if ((d.H + 2 * d.pad_h - d.KH) / d.stride + 1 != d.Ho || (d.W + 2 * d.pad_w - d.KW) / d.stride + 1 != d.Wo ||
-      (d.D + 2 * d.pad_d - d.KD) / d.stride + 1 != d.Do)
+  const bool phase_launch = d.explicit_extent != 0 || d.y_row_stride != 0 || d.res_row_stride != 0;
+  // the output size must be what the geometry implies (phase launches state it themselves)
+  if (!d.explicit_extent &&
+      ((d.H + 2 * d.pad_h - d.KH) / d.stride + 1 != d.Ho || (d.W + 2 * d.pad_w - d.KW) / d.stride + 1 != d.Wo ||
+       (d.D + 2 * d.pad_d - d.KD) / d.stride + 1 != d.Do))
     return DMVS_ERR_ARG;
   if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
+  if (phase_launch) {   // one-sided padding / strided output rows: the TMA-fed tcgen05 kernel only
+    if (d.precision != DMVS_PREC_AUTO && d.precision != DMVS_PREC_WS2_TF32X3) return DMVS_ERR_UNSUPPORTED;
+    if (d.res_up2 || d.pad_d < 0 || d.pad_h < 0 || d.pad_w < 0) return DMVS_ERR_ARG;
+    if (!conv_ws2_supported(d)) return DMVS_ERR_UNSUPPORTED;
+    return dispatch_conv_ws2(d, static_cast<cudaStream_t>(stream));
+  }
   if (d.precision == DMVS_PREC_AUTO) {
     // fp32-class arithmetic, back end chosen per layer without measuring (the host-side autotuner measures instead,
     // ops._tune): the TMA-fed tcgen05 kernel for every layer it supports with at least 0.25 GMAC of work and 8 input
@@ -366,6 +374,8 @@ extern "C" int dmvs_conv_ws2_timeline(int64_t* out, int32_t count) {
 extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
   if (dp == nullptr) return DMVS_ERR_ARG;
   const dmvs_conv_desc& d = *dp;
+  if (d.explicit_extent != 0 || d.y_row_stride != 0 || d.res_row_stride != 0)   // phase launches (ops.conv_up2)
+    return conv_ws2_supported(d) ? 16 : 0;
   int mask = 1;                                        // bit 0: FFMA kernel (always)
 #ifdef DMVS_LEGACY_BACKENDS
   if (d.w_t) mask |= 2;                                // bit 1: legacy mma.sync kernel

@@ -71,6 +71,7 @@ struct alignas(64) Ws2Args {
   int pair;              // 1: <= 4 input channels, kernel rows paired along K (see dispatch_conv_ws2): one quad plane per
                          //    stage, the MMA's second K quad is the same plane one tile row further down
   int KHm;               // row-MMAs per (block, stage): KHe, or ceil(KHe / 2) when paired
+  int y_rs, res_rs;      // floats between consecutive output / residual rows (dense: Wo * pixel stride)
   float inv_in_cols;
   int64_t w_off;         // offset (floats) of this launch's hi slabs inside w_ws
   int64_t w_plane;       // distance (floats) from a hi slab to its lo twin
@@ -477,9 +478,8 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
             }
             const bool relu = d.act == DMVS_ACT_RELU;
             if (d.res_mode != DMVS_RES_NONE) {
-              int64_t rpix = opix;
-              if (d.res_up2) rpix = ((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1);
-              const float* rp = d.res + rpix * d.res_ps + c0;
+              const float* rp = d.res + (img_base + oy) * a.res_rs + (int64_t)ox * d.res_ps + c0;
+              if (d.res_up2) rp = d.res + (((int64_t)n * (d.Ho >> 1) + (oy >> 1)) * (d.Wo >> 1) + (ox >> 1)) * d.res_ps + c0;
               const bool pre_act = d.res_mode == DMVS_RES_PRE_ACT;
 #pragma unroll
               for (int j = 0; j < NCH; j += 4) {
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
 #pragma unroll
               for (int k = 0; k < NCH; ++k) acc[k] = fmaxf(acc[k], 0.0f);
             }
-            float* yp = d.y + opix * d.y_ps + c0;
+            float* yp = d.y + (img_base + oy) * a.y_rs + (int64_t)ox * d.y_ps + c0;
 #pragma unroll
             for (int j = 0; j < NCH; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             if (d.out_stats != nullptr) {
@@ -808,6 +808,10 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
     // straight-line epilogue: standard bias / residual / ReLU-on-all-channels arithmetic on whole 128-bit vectors
     a.fast_epi = d.epi == DMVS_EPI_STD && (d.act == DMVS_ACT_NONE || (d.act == DMVS_ACT_RELU && d.act_c0 <= 0)) && a.vec_y &&
                  (d.bias == nullptr || a.vec_bias) && (d.res_mode == DMVS_RES_NONE || a.vec_res) && co_base + CC <= d.Cout;
+    const bool phase_launch = d.y_row_stride != 0 || d.res_row_stride != 0;
+    if (phase_launch && !a.fast_epi) return DMVS_ERR_UNSUPPORTED;   // strided rows exist on the straight-line epilogue only
+    a.y_rs = d.y_row_stride != 0 ? d.y_row_stride : d.Wo * d.y_ps;
+    a.res_rs = d.res_row_stride != 0 ? d.res_row_stride : d.Wo * d.res_ps;
     a.TH = t.TH;
     a.TW = t.TW;
     a.in_rows = t.TH + (a.pair ? 2 * a.KHm : a.KHe) - 1;   // paired: the zero-weight half of the last pair reads real rows

@@ -151,6 +151,31 @@ __global__ void upsample_nearest_kernel(const float* __restrict__ x, int x_ps, f
   y[o] = __ldg(x + (((int64_t)b * H + oy / f) * W + ox / f) * x_ps);
 }
 
+// y[n][oy][ox][:] += table[ry][rx][:] on the one-pixel frame of every image (ry, rx = 0 first / 1 interior / 2 last row
+// or column): the position-dependent part of a bias that went through a zero-padded 3x3 convolution (see
+// pipeline.FeatureNetPlan: inner2's bias seen through out3).  One thread per (frame pixel, channel quad).
+__global__ void border_bias_add_kernel(float* __restrict__ y, int y_ps, const float* __restrict__ table, int N, int H, int W,
+                                       int C4) {
+  pdl_sync();
+  const int frame = 2 * W + 2 * (H - 2);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * frame * C4) return;
+  const int c4 = (int)(i % C4);
+  int64_t t = i / C4;
+  const int f = (int)(t % frame);
+  const int n = (int)(t / frame);
+  int oy, ox;
+  if (f < W) { oy = 0; ox = f; }
+  else if (f < 2 * W) { oy = H - 1; ox = f - W; }
+  else { const int g = f - 2 * W; oy = 1 + (g >> 1); ox = (g & 1) ? W - 1 : 0; }
+  const int ry = oy == 0 ? 0 : (oy == H - 1 ? 2 : 1), rx = ox == 0 ? 0 : (ox == W - 1 ? 2 : 1);
+  const float4 b = ldg4(table + ((ry * 3 + rx) * C4 + c4) * 4);
+  float4* p = reinterpret_cast<float4*>(y + (((int64_t)n * H + oy) * W + ox) * y_ps + c4 * 4);
+  float4 v = *p;
+  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  *p = v;
+}
+
 // [N][C][HW] -> [N][HW][C] through a 32x32 shared tile (both sides coalesced)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, float* __restrict__ y, int y_ps, int C, int HW) {
   pdl_sync();
@@ -306,6 +331,17 @@ extern "C" int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int
   const int64_t total = (int64_t)B * H * W * factor * factor;
   launch_pdl(upsample_nearest_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, x_ps, y, B, H,
                                                                                                          W, factor);
+  return launch_status();
+}
+
+extern "C" int dmvs_border_bias_add(float* y, int32_t y_ps, const float* table, int32_t N, int32_t H, int32_t W, int32_t C,
+                                    void* stream) {
+  if (!y || !table || N <= 0 || H < 2 || W < 2 || C <= 0 || (C % 4) != 0 || y_ps < C) return DMVS_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(y) & 15u) != 0 || (reinterpret_cast<uintptr_t>(table) & 15u) != 0 || (y_ps % 4) != 0)
+    return DMVS_ERR_ALIGN;
+  const int64_t total = (int64_t)N * (2 * W + 2 * (H - 2)) * (C / 4);
+  launch_pdl(border_bias_add_kernel, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+             y, y_ps, table, N, H, W, C / 4);
   return launch_status();
 }
 

@@ -303,6 +303,16 @@ class PackedConv:
                           mv(self.w_ws), None, mv(self.w_ws_pair), self.w_host, self.bias_host)
 
 
+def _row_strided(t: Tensor, name: str) -> Tuple[int, int]:
+    """(pixel stride, row stride) of a channels-last [N,H,W,C] view whose rows may be strided (phase launches)."""
+    _req_cuda_f32(t, name)
+    if t.dim() != 4 or t.stride(-1) != 1 or (t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1)):
+        raise ValueError(f"{name}: expected a [N,H,W,C] view with uniformly strided rows, got strides {t.stride()}")
+    if t.stride(2) < t.shape[3] or t.stride(1) < t.shape[2] * t.stride(2):
+        raise ValueError(f"{name}: overlapping pixels / rows (strides {t.stride()})")
+    return t.stride(2), t.stride(1)
+
+
 @dataclass
 class GroupNormIn:
     """GroupNorm(4)+affine+SiLU of the producer, applied while the consumer stages its input."""
@@ -317,8 +327,10 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
          res: Optional[Tensor] = None, res_mode: int = RES_NONE, res_up2: bool = False, in_up2: bool = False,
          in_gn: Optional[GroupNormIn] = None, out: Optional[Tensor] = None, out_stats: Optional[Tensor] = None,
          epi: int = EPI_STD, aux1: Optional[Tensor] = None, aux2: Optional[Tensor] = None,
-         gru_hidden: int = 0) -> Tensor:
-    """2-D (x: [N,H,W,C]) or 3-D (x: [N,D,H,W,C]) convolution with fused prologue/epilogue."""
+         gru_hidden: int = 0, explicit_out: Optional[Tuple[int, int]] = None) -> Tensor:
+    """2-D (x: [N,H,W,C]) or 3-D (x: [N,D,H,W,C]) convolution with fused prologue/epilogue.
+    `explicit_out` = (Ho, Wo) marks a phase launch (see `conv_up2`): one-sided padding, `out` / `res` may be views whose
+    rows are strided (every other row of a larger tensor); TMA-fed tcgen05 back end only."""
     three_d = x.dim() == 5
     x_ps = pixel_stride(x, "conv input")
     if three_d:
@@ -344,12 +356,20 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     Do = (D + 2 * pd - KD) // stride + 1
     Ho = (H + 2 * ph - KH) // stride + 1
     Wo = (W + 2 * pw - KW) // stride + 1
+    if explicit_out is not None:
+        if three_d or out is None or stride != 1 or res_up2 or in_up2:
+            raise ValueError("conv: a phase launch is a 2-D stride-1 convolution into a given output view")
+        Ho, Wo = explicit_out
     oshape = (N, Do, Ho, Wo, pc.cout) if three_d else (N, Ho, Wo, pc.cout)
     if out is None:
         out = torch.empty(oshape, device=x.device, dtype=torch.float32)
     elif tuple(out.shape) != oshape:
         raise ValueError(f"conv: out has shape {tuple(out.shape)}, expected {oshape}")
-    y_ps = pixel_stride(out, "conv output")
+    y_rs = res_rs = 0
+    if explicit_out is not None:
+        y_ps, y_rs = _row_strided(out, "conv output")
+    else:
+        y_ps = pixel_stride(out, "conv output")
 
     d = ConvDesc()
     d.x, d.x2 = _ptr(x), _ptr(x2)
@@ -368,12 +388,21 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
     d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps
     d.act, d.act_c0, d.res_mode = act, act_c0, res_mode
-    if res is not None:
+    if res is not None and explicit_out is not None:
+        d.res_ps, res_rs = _row_strided(res, "conv residual")
+        d.res = _ptr(res)
+        if tuple(res.shape) != tuple(out.shape):
+            raise ValueError("conv: phase-launch residual must have the output view's shape")
+    elif res is not None:
         d.res, d.res_ps, d.res_up2 = _ptr(res), pixel_stride(res, "conv residual"), int(res_up2)
         want = (N, Ho // 2, Wo // 2) if res_up2 else tuple(oshape[:-1])
         if tuple(res.shape[:-1]) != want or res.shape[-1] < pc.cout:
             raise ValueError(f"conv: residual shape {tuple(res.shape)} incompatible with output {oshape}")
     d.epi, d.gru_hidden = epi, gru_hidden
+    if explicit_out is not None:
+        d.explicit_extent, d.y_row_stride, d.res_row_stride = 1, y_rs, res_rs
+        if d.precision not in (PREC_AUTO, PREC_WS2_TF32X3):
+            d.precision = PREC_WS2_TF32X3        # the only back end with strided rows; same fp32-class arithmetic
     if aux1 is not None:
         d.aux1, d.aux1_ps = _ptr(aux1), pixel_stride(aux1, "conv aux1")
     if aux2 is not None:
@@ -381,6 +410,8 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     if out_stats is not None and out_stats.dtype != torch.int64:
         raise ValueError("conv: out_stats must be a zero-initialised int64 [N,4,2] tensor (fixed-point accumulators)")
     d.out_stats = _ptr(out_stats)
+    if d.precision == PREC_AUTO and explicit_out is not None:
+        d.precision = PREC_WS2_TF32X3
     if d.precision == PREC_AUTO and _AUTOTUNE:
         key = (N, D, H, W, C1, C2, pc.cout, KD, KH, KW, stride, pd, ph, pw, int(in_up2), in_gn is not None, epi,
                res_mode, int(res_up2), x_ps, x2_ps, y_ps)
@@ -403,6 +434,41 @@ def deconv3d(x: Tensor, w: Tensor, bias: Tensor, skip: Tensor) -> Tensor:
     y = torch.empty_like(skip)
     check(_cabi.lib().dmvs_deconv3d_f32(_ptr(x), _ptr(w), _ptr(bias), _ptr(skip), _ptr(y), N, D, H, W, Cin, Cout,
                                         _stream()), "dmvs_deconv3d_f32")
+    return y
+
+
+def conv_up2(x: Tensor, pcu: Tuple[PackedConv, PackedConv], *, out: Optional[Tensor] = None,
+             accumulate: bool = False) -> Tensor:
+    """conv3x3(pad 1)(nearest_x2(x)) for x [N,H,W,C] -> [N,2H,2W,Cout] WITHOUT forming the upsampled map: output row
+    parity py and column parity px select which of the 3x3 taps fall on the same low-resolution pixel, so each parity
+    class is a 2x2 convolution of x with summed taps (packing.pack_up2_phases).  Two launches (py = 0, 1), each a
+    KH=2 x KW=3 convolution producing both column parities as 2*Cout channels = two adjacent output pixels: 4/9 of the
+    multiply-adds of the direct form and a quarter of its input traffic.  `accumulate` adds to `out` in place."""
+    N, H, W, C = x.shape
+    cout = pcu[0].cout // 2
+    if out is None:
+        if accumulate:
+            raise ValueError("conv_up2: accumulate needs `out`")
+        out = torch.empty((N, 2 * H, 2 * W, cout), device=x.device, dtype=torch.float32)
+    if tuple(out.shape) != (N, 2 * H, 2 * W, cout) or not out.is_contiguous():
+        raise ValueError(f"conv_up2: out must be a dense [N,2H,2W,{cout}] tensor")
+    rows = out.view(N, H, 2, W, 2 * cout)
+    for py in (0, 1):
+        view = rows[:, :, py]                                  # [N,H,W,2*cout]: every other output row, pixel pairs
+        conv(x, pcu[py], pad=(0, 1 - py, 1), out=view, explicit_out=(H, W),
+             res=view if accumulate else None, res_mode=RES_PRE_ACT if accumulate else RES_NONE)
+    return out
+
+
+@_profiled("border_bias_add")
+def border_bias_add(y: Tensor, table: Tensor) -> Tensor:
+    """y [N,H,W,C] += table[3,3,C] on the one-pixel frame of every image (in place)."""
+    ps = pixel_stride(y, "border_bias_add")
+    N, H, W, Cc = y.shape
+    if tuple(table.shape) != (3, 3, Cc) or not table.is_contiguous():
+        raise ValueError(f"border_bias_add: table must be a dense [3,3,{Cc}] tensor")
+    _req_cuda_f32(table, "table")
+    check(_cabi.lib().dmvs_border_bias_add(_ptr(y), ps, _ptr(table), N, H, W, Cc, _stream()), "dmvs_border_bias_add")
     return y
 
 

@@ -143,6 +143,51 @@ def pack_ws_pair(full: torch.Tensor, cout: int) -> torch.Tensor:
     return torch.cat(parts).contiguous()
 
 
+def pack_up2_phases(w3: torch.Tensor) -> Tuple[PackedConv, PackedConv]:
+    """Phase-collapsed weights of conv3x3(pad 1)(nearest_x2(.)) for ops.conv_up2.  w3 [Cout,C,3,3] -> two PackedConv
+    (output-row parity py = 0, 1), each [2*Cout, C, 2, 3]: channel px*Cout + o is output column parity px.
+    Row taps: py = 0 reads low-res rows (y-1, y) with kernel rows ({0}, {1,2}) summed; py = 1 reads (y, y+1) with
+    ({0,1}, {2}).  Column taps over (x-1, x, x+1): px = 0 uses ({0}, {1,2}, {}), px = 1 uses ({}, {0,1}, {2})."""
+    w = w3.detach().double().cpu()
+    cout, c = w.shape[:2]
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    cols = {0: ([0], [1, 2], []), 1: ([], [0, 1], [2])}
+    out = []
+    for py in (0, 1):
+        wp = torch.zeros(2 * cout, c, 2, 3, dtype=torch.float64)
+        for px in (0, 1):
+            for a, khs in enumerate(rows[py]):
+                for b, kws in enumerate(cols[px]):
+                    for kh in khs:
+                        for kw in kws:
+                            wp[px * cout:(px + 1) * cout, :, a, b] += w[:, :, kh, kw]
+        out.append(pack_weight(wp.float(), None))
+    return out[0], out[1]
+
+
+def compose_1x1_into_3x3(w3: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.Tensor]):
+    """conv3x3_{w3}(conv1x1_{w1,b1}(x)), zero padding 1, as ONE 3x3 convolution of x plus a frame correction:
+    returns (w [Cout,Cin,3,3], interior bias [Cout], table [3,3,Cout]).  The bias b1 reaches an output pixel through the
+    taps that fall inside the image only, so on the one-pixel frame the interior bias overshoots by the out-of-image
+    taps' share: table[ry][rx] (ry, rx = 0 first, 1 interior, 2 last row / column) is that correction (zero at [1][1]),
+    applied by ops.border_bias_add.  Composed in float64."""
+    w3d, w1d = w3.detach().double().cpu(), w1.detach().double().cpu().reshape(w1.shape[0], w1.shape[1])
+    w = torch.einsum("omhw,mc->ochw", w3d, w1d)
+    cout = w3.shape[0]
+    s = torch.zeros(3, 3, cout, dtype=torch.float64)          # s[kh][kw][o] = sum_m w3[o,m,kh,kw] * b1[m]
+    if b1 is not None:
+        s = torch.einsum("omhw,m->hwo", w3d, b1.detach().double().cpu())
+    table = torch.zeros(3, 3, cout, dtype=torch.float64)
+    oob = {0: [0], 1: [], 2: [2]}
+    for ry in range(3):
+        for rx in range(3):
+            for kh in range(3):
+                for kw in range(3):
+                    if kh in oob[ry] or kw in oob[rx]:
+                        table[ry, rx] -= s[kh, kw]
+    return w.float(), s.sum(dim=(0, 1)).float(), table.float().contiguous()
+
+
 def pack_ws_from_packed(w: torch.Tensor, cout: int, stride: int, pad: Tuple[int, int]) -> torch.Tensor:
     """Width-stacked slabs for a given stride / padding from the FFMA layout `PackedConv.w`
     ([KD,KH,KW,cin_pad4,cout_pad4]); built on first use of a strided layer (ops.conv) and cached."""

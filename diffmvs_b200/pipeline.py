@@ -7,6 +7,7 @@ into channel slices of the consumer's input buffer.  Reference lines are cited p
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -104,6 +105,21 @@ class FeatureNetPlan:
         if cas:
             self.inner2 = up(packing.pack_conv(sd, "inner2"))
             self.out3 = up(packing.pack_conv(sd, "out3"))
+            # out3(nearest_x2(intra) + inner2(conv1)) without the 64-channel half-resolution intermediate
+            # (module.py:415-417): the convolution is linear, so
+            #   out3 = [out3 o inner2](conv1)  +  out3(nearest_x2(intra))  +  inner2's bias seen through out3.
+            # The first term is one 16 -> 16 3x3 convolution with composed weights, the second runs as phase-collapsed
+            # 2x2 convolutions of the quarter-resolution map (ops.conv_up2: 4/9 of the multiply-adds, no upsampled
+            # tensor), the third is a constant except on the one-pixel frame (ops.border_bias_add).  Saves the 0.83 GB
+            # write + read of `intra` at cfg3 and about half of the two layers' time; DMVS_FPN_COMPOSE=0 runs the
+            # layers one by one.
+            self.compose = os.environ.get("DMVS_FPN_COMPOSE", "1") != "0"
+            if self.compose:
+                w, b, table = packing.compose_1x1_into_3x3(sd["out3.weight"].float(), sd["inner2.weight"].float(),
+                                                           sd.get("inner2.bias"))
+                self.out3_c1 = up(packing.pack_weight(w, b))
+                self.out3_up = tuple(up(pc) for pc in packing.pack_up2_phases(sd["out3.weight"].float()))
+                self.out3_frame = table.to(device) if float(table.abs().max()) > 0.0 else None
 
     def __call__(self, x: Tensor) -> Dict[str, Tensor]:
         """x [N,H,W,3] (or [N,H,W,4] with a zero fourth channel) -> {"stage1": [N,H/8,W/8,48],
@@ -120,7 +136,13 @@ class FeatureNetPlan:
         out = {"stage1": ops.conv(c3, self.out1)}
         intra = ops.conv(c2, self.inner1, res=c3, res_mode=RES_PRE_ACT, res_up2=True)
         out["stage2"] = ops.conv(intra, self.out2)
-        if self.cas:
+        if self.cas and self.compose and intra.shape[1] >= 2 and intra.shape[2] >= 2:
+            y = ops.conv(c1, self.out3_c1)
+            ops.conv_up2(intra, self.out3_up, out=y, accumulate=True)
+            if self.out3_frame is not None:
+                ops.border_bias_add(y, self.out3_frame)
+            out["stage3"] = y
+        elif self.cas:
             intra = ops.conv(c1, self.inner2, res=intra, res_mode=RES_PRE_ACT, res_up2=True)
             out["stage3"] = ops.conv(intra, self.out3)
         return out

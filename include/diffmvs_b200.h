@@ -124,6 +124,14 @@ typedef struct dmvs_conv_desc {
   const float* aux1;
   const float* aux2;
   int32_t aux1_ps, aux2_ps, gru_hidden;
+  /* Phase launches of "3x3 convolution of a nearest x2 upsampled map" (ops.conv_up2): the output rows of one launch are
+   * every other row of the real tensor and the padding is one-sided.  Only the TMA-fed width-stacked back end accepts
+   * these (dmvs_conv_backends reports bit 4 alone); 0 everywhere else. */
+  int32_t explicit_extent;  /* 1: (Do, Ho, Wo) are taken as given - output o reads inputs o*stride - pad + k, zero outside
+                               the input - instead of being checked against the symmetric-padding formula */
+  int32_t y_row_stride;     /* floats between consecutive output rows (image n / slice d start at (n*Do + d)*Ho rows);
+                               0 = dense (Wo * y_ps) */
+  int32_t res_row_stride;   /* same for `res` (not with res_up2) */
   int64_t* out_stats;       /* optional [N][4][2] sum / sumsq of the written values per GroupNorm group, accumulated as
                                64-bit fixed point (2^-20 units; integer adds: the result is independent of the order in
                                which CTAs arrive, runs are bit-reproducible); must be zeroed by the caller */
@@ -247,6 +255,13 @@ int dmvs_ddim_step(float* img, const float* delta, const float* noise, float k_r
  * (diffusion.py:205-207,274-278). */
 int dmvs_upsample_nearest(const float* x, int32_t x_ps, float* y, int32_t B, int32_t H, int32_t W, int32_t factor,
                           void* stream);
+
+/* y [N][H][W][y_ps >= C] += table[ry][rx][C] on the one-pixel frame of every image, (ry, rx) in {0 first, 1 interior,
+ * 2 last} row / column (the interior is untouched): the position-dependent remainder of a per-channel bias that passed
+ * through a zero-padded 3x3 convolution.  Used where FeatureNet's `inner2` bias is folded through `out3`
+ * (module.py:395-396,415-417; pipeline.FeatureNetPlan).  C % 4 == 0, H, W >= 2. */
+int dmvs_border_bias_add(float* y, int32_t y_ps, const float* table, int32_t N, int32_t H, int32_t W, int32_t C,
+                         void* stream);
 
 /* Input images (datasets/mvs.py:93-97: [N][3][H][W], RGB in [0,1]) -> channels-last [N][HW][4] with a zero
  * fourth channel, the layout the first convolutions (module.py:332,364) stage with 128-bit copies. */

@@ -229,6 +229,36 @@ def test_conv3d_to1_matches_torch(N, D, H, W, ps):
     _close(ops.conv3d_to1(xin, pc0).cpu(), F.conv3d(x, w, None, padding=1)[:, 0], tol=2e-6, what="conv3d_to1 no bias")
 
 
+@pytest.mark.parametrize("C,Cout,H,W", [(64, 16, 36, 50), (16, 8, 17, 33), (32, 32, 8, 70)])
+def test_conv_up2_matches_conv_of_upsampled_map(C, Cout, H, W):
+    """ops.conv_up2: conv3x3(nearest_x2(x)) as two phase launches (one-sided padding, every other output row)."""
+    N = 2
+    x = _rand(N, C, H, W, seed=31)
+    w3 = _rand(Cout, C, 3, 3, seed=32) * (1.0 / math.sqrt(9 * C))
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w3, padding=1)
+    pcu = tuple(pc.to(DEV) for pc in packing.pack_up2_phases(w3))
+    y = ops.conv_up2(_nhwc(x), pcu)
+    _close(_nchw(y), ref, tol=2e-5, what="conv_up2")
+    base = _rand(N, Cout, 2 * H, 2 * W, seed=33)
+    y2 = _nhwc(base).contiguous()
+    ops.conv_up2(_nhwc(x), pcu, out=y2, accumulate=True)
+    _close(_nchw(y2), ref + base, tol=2e-5, what="conv_up2 accumulate")
+
+
+def test_fpn_last_level_composed_matches_layerwise():
+    """out3(nearest_x2(intra) + inner2(conv1)) (module.py:415-417): composed / phase-collapsed form vs the layers."""
+    N, H, W = 2, 20, 34                                       # quarter-resolution size; conv1 is [N,16,2H,2W]
+    intra, c1 = _rand(N, 64, H, W, seed=41), _rand(N, 16, 2 * H, 2 * W, seed=42)
+    wi, bi = _rand(64, 16, 1, 1, seed=43) * 0.25, _rand(64, seed=44)
+    w3 = _rand(16, 64, 3, 3, seed=45) * (1.0 / 24.0)
+    ref = F.conv2d(F.interpolate(intra, scale_factor=2, mode="nearest") + F.conv2d(c1, wi, bi), w3, padding=1)
+    w, b, table = packing.compose_1x1_into_3x3(w3, wi, bi)
+    y = ops.conv(_nhwc(c1), packing.pack_weight(w, b).to(DEV))
+    ops.conv_up2(_nhwc(intra), tuple(pc.to(DEV) for pc in packing.pack_up2_phases(w3)), out=y, accumulate=True)
+    ops.border_bias_add(y, table.to(DEV))
+    _close(_nchw(y), ref, tol=2e-5, what="composed FPN level")
+
+
 @pytest.mark.parametrize("cin,cout", [(32, 16), (16, 8)])
 def test_deconv3d_matches_torch(cin, cout):
     N, D, H, W = 1, 3, 5, 7
