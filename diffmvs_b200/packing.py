@@ -143,7 +143,7 @@ def pack_ws_pair(full: torch.Tensor, cout: int) -> torch.Tensor:
     return torch.cat(parts).contiguous()
 
 
-def pack_up2_phases(w3: torch.Tensor) -> Tuple[PackedConv, PackedConv]:
+def pack_up2_phases(w3: torch.Tensor, bias: Optional[torch.Tensor] = None) -> Tuple[PackedConv, PackedConv]:
     """Phase-collapsed weights of conv3x3(pad 1)(nearest_x2(.)) for ops.conv_up2.  w3 [Cout,C,3,3] -> two PackedConv
     (output-row parity py = 0, 1), each [2*Cout, C, 2, 3]: channel px*Cout + o is output column parity px.
     Row taps: py = 0 reads low-res rows (y-1, y) with kernel rows ({0}, {1,2}) summed; py = 1 reads (y, y+1) with
@@ -161,7 +161,7 @@ def pack_up2_phases(w3: torch.Tensor) -> Tuple[PackedConv, PackedConv]:
                     for kh in khs:
                         for kw in kws:
                             wp[px * cout:(px + 1) * cout, :, a, b] += w[:, :, kh, kw]
-        out.append(pack_weight(wp.float(), None))
+        out.append(pack_weight(wp.float(), None if bias is None else torch.cat((bias.float(), bias.float()))))
     return out[0], out[1]
 
 

@@ -317,6 +317,9 @@ class UnetPlan:
         self.up_rb = [ResnetBlockPlan(sd, f"ups.{i}.0", device, temb) for i in range(L)]
         self.up = [up(packing.pack_conv(sd, f"ups.{i}.1.1")) if i < L - 1
                    else up(packing.pack_conv(sd, f"ups.{i}.1")) for i in range(L)]
+        # Upsample = nearest x2 + 3x3 convolution (update.py:38-42): as phase-collapsed 2x2 convolutions (ops.conv_up2)
+        self.up2 = [tuple(up(pc) for pc in packing.pack_up2_phases(sd[f"ups.{i}.1.1.weight"], sd.get(f"ups.{i}.1.1.bias")))
+                    if i < L - 1 and os.environ.get("DMVS_UNET_UP2", "1") != "0" else None for i in range(L)]
         self.final = ResnetBlockPlan(sd, "final_res_block", device, temb)
         # final_conv (delta) and conf share one 1x1 launch: channel 0 = delta, channel 1 = sigmoid(conf)
         w = torch.cat((sd["final_conv.weight"].float(), sd["conf.weight"].float()), 0)
@@ -343,7 +346,10 @@ class UnetPlan:
         x = self.mid(hidden, arena)
         for i in range(L):
             x = self.up_rb[i](x, arena, x2=skips.pop())
-            x = ops.conv(x, self.up[i], in_up2=(i < L - 1))
+            if self.up2[i] is not None:
+                x = ops.conv_up2(x, self.up2[i])
+            else:
+                x = ops.conv(x, self.up[i], in_up2=(i < L - 1))
         x = self.final(x, arena, x2=r)
         head = ops.conv(x, self.head, act=ACT_SIGMOID, act_c0=1)
         return hidden, head
