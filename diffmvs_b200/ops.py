@@ -72,27 +72,65 @@ def set_autotune(enabled: bool, use_ws: Optional[bool] = None) -> None:
     _TUNED.clear()
 
 
+# The table is keyed by (device index, signature); entries loaded from a file apply to every device (index -1).  A
+# signature is the 24-tuple built in `conv`: shapes, kernel, stride, padding, prologue / epilogue kinds, pixel strides,
+# activation and bias presence.
+_SIG_LEN = 24
+DEFAULT_TUNED_TABLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuned", "b200_default.json")
+_default_table_state = {"checked": False}
+
+
+def _tuned_lookup(dev: int, sig: tuple):
+    hit = _TUNED.get((dev,) + sig)
+    return hit if hit is not None else _TUNED.get((-1,) + sig)
+
+
 def save_tuned(path: str) -> None:
-    """Write the autotuning table as JSON (signature -> chosen back end and the measured times)."""
+    """Write the autotuning table as JSON (signature -> chosen back end and the measured times), device independent."""
     import json
     names = {v: k for k, v in PRECISIONS.items()}
-    rows = [{"sig": [int(x) for x in k], "choice": names[c], "ms": {names[m]: t for m, t in ts.items()}}
-            for k, (c, ts) in _TUNED.items()]
+    rows, seen = [], set()
+    for k, (c, ts) in _TUNED.items():
+        sig = k[1:]
+        if sig in seen:
+            continue
+        seen.add(sig)
+        rows.append({"sig": [int(x) for x in sig], "choice": names[c], "ms": {names[m]: t for m, t in ts.items()}})
     with open(path, "w") as f:
         json.dump(rows, f, indent=0)
 
 
 def load_tuned(path: str) -> int:
-    """Preload the autotuning table written by `save_tuned` (e.g. so that a run under a profiler, whose timings are
-    distorted, uses the back ends a normal run chose).  Returns the number of entries."""
+    """Preload an autotuning table written by `save_tuned`: its signatures use the recorded back end on every device
+    instead of being timed (reproducible back-end choice across processes and ranks; also what a run under a profiler,
+    whose timings are distorted, needs).  Entries of another signature format are skipped.  Returns the number loaded."""
     import json
     with open(path) as f:
         rows = json.load(f)
+    n = 0
     for r in rows:
         sig = r["sig"]
-        key = tuple(sig[:15]) + (bool(sig[15]),) + tuple(sig[16:])
-        _TUNED[key] = (PRECISIONS[r["choice"]], {PRECISIONS[m]: t for m, t in r.get("ms", {}).items()})
-    return len(rows)
+        if len(sig) != _SIG_LEN or r["choice"] not in PRECISIONS:
+            continue
+        key = (-1,) + tuple(sig[:15]) + (bool(sig[15]),) + tuple(sig[16:22]) + (int(sig[22]), bool(sig[23]))
+        _TUNED[key] = (PRECISIONS[r["choice"]], {PRECISIONS[m]: t for m, t in r.get("ms", {}).items() if m in PRECISIONS})
+        n += 1
+    return n
+
+
+def _load_default_table_once(dev: int) -> None:
+    """First tuned convolution of the process: preload the table shipped for this GPU model (B200) so that the layers of
+    the known workloads run on recorded back ends - no timing noise decides them, every process and rank agrees, and
+    results are bit-reproducible across runs.  DMVS_TUNED_TABLE=<path> selects another table, DMVS_TUNED_TABLE=0 none."""
+    if _default_table_state["checked"]:
+        return
+    _default_table_state["checked"] = True
+    path = os.environ.get("DMVS_TUNED_TABLE", DEFAULT_TUNED_TABLE)
+    if path in ("0", "", "none") or not os.path.exists(path):
+        return
+    if path == DEFAULT_TUNED_TABLE and "B200" not in torch.cuda.get_device_name(dev):
+        return
+    load_tuned(path)
 
 
 def tuned_table() -> dict:
@@ -100,12 +138,50 @@ def tuned_table() -> dict:
     return dict(_TUNED)
 
 
-def _tune(d: "ConvDesc", key) -> int:
+_capture_misses: set = set()
+
+
+def _span(t: Optional[Tensor]):
+    """[first byte, last byte + 1) of the memory a strided view can touch."""
+    if t is None or t.numel() == 0:
+        return None
+    last = sum((n - 1) * st for n, st in zip(t.shape, t.stride()))
+    return t.data_ptr(), t.data_ptr() + (last + 1) * t.element_size()
+
+
+def _disjoint(out: Tensor, *others: Optional[Tensor]) -> bool:
+    """True when `out` shares no byte with any of `others`.  Spans are compared, except for the layout this package uses
+    all the time: two channel slices of one channels-last buffer (same strides, offsets within one pixel record)."""
+    a = _span(out)
+    for o in others:
+        b = _span(o)
+        if a is None or b is None or not (a[0] < b[1] and b[0] < a[1]):
+            continue
+        if (out.dim() == o.dim() and out.stride() == o.stride() and tuple(out.shape[:-1]) == tuple(o.shape[:-1])
+                and out.stride(-1) == 1 and out.dim() >= 2):
+            delta = (o.data_ptr() - out.data_ptr()) // out.element_size()       # channel offset of o relative to out
+            ps = out.stride(-2)
+            if abs(delta) < ps and (delta >= out.shape[-1] or -delta >= o.shape[-1]):
+                continue
+        return False
+    return True
+
+
+def _tune(d: "ConvDesc", key, safe: bool = True) -> int:
     lib = _cabi.lib()
     mask = lib.dmvs_conv_backends(C.byref(d))
     cands = [code for bit, code in _BACKEND_BITS if mask & bit and (code != PREC_WS_TF32X3 or _AUTOTUNE_WS)]
-    if torch.cuda.is_current_stream_capturing() or len(cands) < 2:
-        return PREC_AUTO if len(cands) >= 2 else cands[0]
+    if len(cands) < 2:
+        return cands[0]
+    if torch.cuda.is_current_stream_capturing():
+        if key not in _capture_misses:
+            _capture_misses.add(key)
+            import warnings
+            warnings.warn("diffmvs_b200: a convolution signature was first seen during CUDA-graph capture; it runs on the "
+                          "static back-end rule and is not tuned (run one eager forward first)", RuntimeWarning)
+        return PREC_AUTO
+    if not safe:      # the output overlaps an input: trial launches would change what later launches read
+        return PREC_AUTO
     stream = _stream()
     stats, d.out_stats = d.out_stats, None        # accumulating statistics must not see the trial runs
     times = {}
@@ -413,10 +489,12 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     if d.precision == PREC_AUTO and explicit_out is not None:
         d.precision = PREC_WS2_TF32X3
     if d.precision == PREC_AUTO and _AUTOTUNE:
-        key = (N, D, H, W, C1, C2, pc.cout, KD, KH, KW, stride, pd, ph, pw, int(in_up2), in_gn is not None, epi,
-               res_mode, int(res_up2), x_ps, x2_ps, y_ps)
-        hit = _TUNED.get(key)
-        d.precision = hit[0] if hit is not None else _tune(d, key)
+        dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+        _load_default_table_once(dev)
+        sig = (N, D, H, W, C1, C2, pc.cout, KD, KH, KW, stride, pd, ph, pw, int(in_up2), in_gn is not None, epi,
+               res_mode, int(res_up2), x_ps, x2_ps, y_ps, int(act), pc.bias is not None)
+        hit = _tuned_lookup(dev, sig)
+        d.precision = hit[0] if hit is not None else _tune(d, (dev,) + sig, _disjoint(out, x, x2, res, aux1, aux2))
     global _LAST_CONV_BACKEND
     _LAST_CONV_BACKEND = PREC_WS_TF32X3 if (d.precision == PREC_WS2_TF32X3 and in_up2) else d.precision
     check(_cabi.lib().dmvs_conv_f32(C.byref(d), _stream()), "dmvs_conv_f32")

@@ -74,13 +74,28 @@ def test_unsupported_layers_are_refused():
 
 def test_autotune_table_round_trip(tmp_path):
     ops._TUNED.clear()
-    key = (7, 1, 576, 800, 64, 0, 16, 1, 3, 3, 1, 0, 1, 1, 0, False, 0, 0, 0, 64, 0, 16)
-    ops._TUNED[key] = (ops.PREC_WS_TF32X3, {ops.PREC_FP32: 1.39, ops.PREC_WS_TF32X3: 0.61})
+    sig = (7, 1, 576, 800, 64, 0, 16, 1, 3, 3, 1, 0, 1, 1, 0, False, 0, 0, 0, 64, 0, 16, 1, True)
+    assert len(sig) == ops._SIG_LEN
+    ops._TUNED[(3,) + sig] = (ops.PREC_WS_TF32X3, {ops.PREC_FP32: 1.39, ops.PREC_WS_TF32X3: 0.61})   # tuned on cuda:3
     path = tmp_path / "tuned.json"
     ops.save_tuned(str(path))
     rows = json.load(open(path))
     assert rows[0]["choice"] == "ws_tf32x3"
     ops._TUNED.clear()
     assert ops.load_tuned(str(path)) == 1
-    assert ops._TUNED[key][0] == ops.PREC_WS_TF32X3
+    assert ops._tuned_lookup(0, sig)[0] == ops.PREC_WS_TF32X3      # a loaded table applies to every device
+    assert ops._tuned_lookup(5, sig)[0] == ops.PREC_WS_TF32X3
     ops._TUNED.clear()
+    json.dump([{"sig": list(sig[:22]), "choice": "ws_tf32x3", "ms": {}}], open(path, "w"))   # round-1 format: skipped
+    assert ops.load_tuned(str(path)) == 0
+
+
+def test_span_overlap_detection():
+    import torch
+    buf = torch.zeros(4, 6, 8)
+    a, b = buf[..., :4], buf[..., 4:]                     # channel slices of one buffer: spans overlap, bytes do not
+    assert ops._disjoint(a, b) and ops._disjoint(b, a)
+    assert not ops._disjoint(buf[..., :5], buf[..., 4:])
+    assert not ops._disjoint(buf, a)
+    assert ops._disjoint(buf[:2], buf[2:])
+    assert ops._disjoint(buf, None, torch.zeros(3))
