@@ -1,0 +1,8 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 1200 python tools/make_default_tuned.py 2>&1 | tail -3
+cp diffmvs_b200/tuned/b200_default.json gpurun_out/b200_default.json
+bash tools/gpu_bench_only.sh
+grep '^{"metric' gpurun_out/bench.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('batched', d['batched'])"
