@@ -2,26 +2,30 @@
 // layouts of conv_ws.cu (kernel-row taps stacked along N, 3xTF32, shift-add epilogue - see the header of that file)
 // behind a fully asynchronous, role-specialised pipeline:
 //
-//   warp 20     TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
+//   warp 27     TMA producer   cp.async.bulk.tensor boxes of the raw fp32 halo tile (one 4-channel quad plane per copy,
 //                              hardware zero fill = the convolution's padding) + cp.async.bulk of the stage's weight
 //                              slabs, all completing on tma_full[slot] (mbarrier transaction count)
-//   warps 12-19 split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
+//   warps 20-26 split workers  raw -> (hi, lo) TF32 pair in place (+ GroupNorm+SiLU of the producer layer), then
 //                              fence.proxy.async and one arrival per warp on op_full[slot]
 //   warps 0-3   MMA issuers    FOUR issuing threads, one per scheduler, M blocks dealt round-robin: measured on B200
-//                              (profiles/r2_pipe_probe*.txt) a single thread sustains one tcgen05.mma per ~70-100 clk
-//                              of its own descriptor arithmetic, while an M128 x N48 x K8 TF32 MMA occupies the tensor
-//                              pipe for 24 clk - one issuer starves it.  Each issuer commits to empty[slot] (ring slot
-//                              free) and, after a tile's last stage, to acc_full[set] (accumulators complete)
-//   warps 4-11  epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
-//                              t+1 fill the other set; acc_empty[set] hands the set back.  Two warps per TMEM lane
-//                              quadrant and a specialised straight-line path for the common bias/ReLU/residual case:
-//                              a single warp executes its ~150-400 dependent instructions per 32x16 output block at
-//                              ~6 clk each (ncu: stall_wait / short_scoreboard), so the epilogue - not the tensor pipe
-//                              - bounds the layers with few input channels unless it is both short and parallel
+//                              (profiles/r2_pipe_probe*.txt, r2_mma_issue_experiments.txt) a single thread sustains one
+//                              tcgen05.mma per ~100 clk whatever N is, four sustain one per ~70 clk in aggregate, while
+//                              an M128 x N48 x K8 TF32 MMA needs 24 clk of math - the NUMBER of MMAs bounds the layers
+//                              with many input channels.  Each issuer commits to empty[slot] (ring slot free) and,
+//                              after a tile's last stage, to acc_full[set] (accumulators complete)
+//   warps 4-19  epilogue       shift-add + fused epilogue of tile t out of accumulator set t&1 while the MMAs of tile
+//                              t+1 fill the other set; acc_empty[set] hands the set back.  Four warps per TMEM lane
+//                              quadrant, 8 output channels per work item, and a specialised straight-line path for the
+//                              common bias/ReLU/residual case; when the staged tile is exactly 32 positions wide a lane
+//                              quadrant is one tile row and no halo exchange between quadrants is needed.  The epilogue
+//                              - not the tensor pipe - bounds the layers with <= 8 input channels.
 //
-// One persistent CTA per SM; the ring is R = 2..4 stages deep, a stage = (tile, depth tap, stride phase, 8 input
-// channels).  Compared with conv_ws.cu nothing in a CTA waits for global-memory latency any more: the producer runs up
-// to R-1 stages ahead, the split of stage s+1 overlaps the MMAs of stage s, and the epilogue overlaps the next tile.
+// Variants selected on the host (dispatch_conv_ws2): kernel rows paired along K for <= 4 input channels (`pair`), phase
+// launches with one-sided padding and strided output rows (ops.conv_up2).  One persistent CTA per SM; the ring is
+// R = 2..4 stages deep, a stage = (tile, depth tap, stride phase, 8 input channels).  Compared with conv_ws.cu nothing in
+// a CTA waits for global-memory latency any more: the producer runs up to R-1 stages ahead, the split of stage s+1
+// overlaps the MMAs of stage s, and the epilogue overlaps the next tile.  Every launch is a programmatic dependent launch:
+// barrier set-up, TMEM allocation and descriptor prefetch run before griddepcontrol.wait.
 #include <cstdlib>
 #include <type_traits>
 
