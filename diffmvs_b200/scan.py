@@ -9,9 +9,12 @@ so FeatureNet runs only on images it has not seen; depth maps are unchanged (`te
 """
 from __future__ import annotations
 
+import os
+import time
 from collections import OrderedDict
-from typing import Dict, Hashable, List, Optional, Sequence
+from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 Tensor = torch.Tensor
@@ -64,3 +67,63 @@ class ScanRunner:
             self.cache.put(image_ids[v], out["features"][v])
         out.pop("features", None)
         return out
+
+
+def scan_metas(testpath: str, scans: Sequence[str], dataset: str = "dtu") -> List[Tuple[str, int, List[int]]]:
+    """(scan, reference view, source views) of every reference view the evaluation loader would visit, in its order
+    (`MVSDataset.build_metas`, datasets/mvs.py:41-77)."""
+    from . import scene_io
+    if dataset == "general":
+        return [("", r, s) for r, s in scene_io.read_pairs_for_inference(os.path.join(testpath, "pair.txt"), 0.01)]
+    metas = []
+    for scan in scans:
+        metas += [(scan, r, s) for r, s in scene_io.read_pairs_for_inference(os.path.join(testpath, scan, "pair.txt"), 0.1)]
+    return metas
+
+
+def save_scene_depth(model, testpath: str, scans: Sequence[str], outdir: str, num_view: int = 5, numdepth: int = 384,
+                     dataset: str = "dtu", max_h: int = 4800, max_w: int = 6400, rank: int = 0, world: int = 1,
+                     cache_views: int = 0, device=None, verbose: bool = False) -> float:
+    """The per-scene loop of the reference's evaluation script (`save_scene_depth`, test.py:91-205) around an already
+    built model: for every reference view of `scans` read the images / cameras (`scene_io.load_sample` = one
+    `MVSDataset` item), run `model(imgs, proj_matrices, depth_values)` at batch 1 and write
+    `<outdir>/<scan>/{depth_est,cams,images,conf<i>}/<id>.*` exactly as test.py:142-200 does, i.e. the directory
+    `filter.py` / `fusion.filter_depth` reads.  Returns the average forward time per reference view in seconds (the
+    value test.py prints).
+
+    `rank` / `world`: this process handles its contiguous block of the reference views (`sharding.shard_views`); no
+    exchange is needed, every rank writes its own files.  `cache_views` > 0 keeps that many FeatureNet pyramids on the
+    device and re-encodes only images not seen before (`ScanRunner`; same depth maps)."""
+    from . import scene_io, sharding
+    if device is None:
+        device = next(model.parameters()).device
+    metas = scan_metas(testpath, scans, dataset)
+    mine = sharding.shard_views(len(metas), rank, world)
+    runner = ScanRunner(model, capacity=cache_views) if cache_views > 0 else None
+    time_sum, n_done = 0.0, 0
+    with torch.no_grad():
+        for idx in mine:
+            scan, ref_view, src_views = metas[idx]
+            sample = scene_io.load_sample(testpath, scan, ref_view, src_views, num_view, dataset, numdepth, max_w, max_h)
+            imgs = [torch.from_numpy(np.ascontiguousarray(i))[None].to(device) for i in sample["imgs"]]
+            proj = {k: torch.from_numpy(v)[None].to(device) for k, v in sample["proj_matrices"].items()}
+            dv = torch.from_numpy(sample["depth_values"])[None].to(device)
+            depth_max = 1.0 / float(sample["depth_values"][0])          # test.py:116-117
+            depth_min = 1.0 / float(sample["depth_values"][-1])
+            torch.cuda.synchronize(device)
+            t0 = time.time()
+            if runner is not None:
+                ids = [(scan, v) for v in ([ref_view] + list(src_views)[:num_view - 1])]
+                out = runner(ids, imgs, proj, dv)
+            else:
+                out = model(imgs, proj, dv)
+            torch.cuda.synchronize(device)
+            time_sum += time.time() - t0
+            n_done += 1
+            depth = out["depth"][-1][0].cpu().numpy()
+            confs = [c[0].cpu().numpy() for c in out["photometric_confidence"]]
+            cam = sample["proj_matrices"]["stage4"][0]                   # reference camera (test.py:147,155)
+            scene_io.save_outputs(outdir, sample["filename"], depth, confs, cam, depth_max, depth_min, img=sample["imgs"][0])
+            if verbose:
+                print(f"Iter {n_done}/{len(mine)}, Time:{time.time() - t0:.4f} Res:{tuple(depth.shape)}")
+    return time_sum / max(n_done, 1)

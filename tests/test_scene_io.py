@@ -143,3 +143,12 @@ def test_ply_round_trip(tmp_path):
     assert np.array_equal(p2, pts) and np.array_equal(c2, col)
     with pytest.raises(ValueError):
         data_io.write_ply(path, pts, col[:-1])
+
+
+def test_scan_metas_equal_the_reference_loader_order():
+    """`scan.scan_metas` = `MVSDataset.build_metas` (mvs.py:41-77), recorded by oracle/make_io_golden.py."""
+    import json
+    from diffmvs_b200 import scan
+    meta = json.load(open(os.path.join(G, "meta.json")))
+    assert [[r, s] for _, r, s in scan.scan_metas(os.path.join(G, "general"), [""], "general")] == meta["general_metas"]
+    assert [[r, s] for _, r, s in scan.scan_metas(os.path.join(G, "bench"), ["scan1"], "dtu")] == meta["dtu_metas"]
