@@ -16,7 +16,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_SILU = 0, 1, 2, 3, 4
 RES_NONE, RES_PRE_ACT, RES_POST_ACT = 0, 1, 2
 EPI_STD, EPI_GRU_ZR, EPI_GRU_Q = 0, 1, 2
 PREC_FP32, PREC_TF32X3, PREC_TF32, PREC_TC_TF32X3, PREC_TC_TF32, PREC_AUTO = 0, 1, 2, 3, 4, 5
-PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3 = 6, 7, 8
+PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3, PREC_WS2_TF32_F16C = 6, 7, 8, 9
 
 ABI_VERSION = 4   # DMVS_ABI_VERSION of include/diffmvs_b200.h
 
@@ -31,7 +31,7 @@ class ConvDesc(C.Structure):
         ("N", i32), ("D", i32), ("H", i32), ("W", i32),
         ("C1", i32), ("C2", i32), ("x_ps", i32), ("x2_ps", i32), ("in_up2", i32),
         ("in_stats", C.c_void_p), ("in_g1", f32p), ("in_g0", f32p), ("in_inv_count", C.c_float),
-        ("w", f32p), ("w_t", f32p), ("w_tc", f32p), ("w_ws", f32p), ("w_ws_pair", f32p), ("precision", i32), ("bias", f32p),
+        ("w", f32p), ("w_t", f32p), ("w_tc", f32p), ("w_ws", f32p), ("w_ws_pair", f32p), ("w_ws16", f32p), ("precision", i32), ("bias", f32p),
         ("KD", i32), ("KH", i32), ("KW", i32), ("stride", i32), ("pad_d", i32), ("pad_h", i32), ("pad_w", i32),
         ("y", f32p), ("Do", i32), ("Ho", i32), ("Wo", i32), ("Cout", i32), ("y_ps", i32),
         ("act", i32), ("act_c0", i32), ("res_mode", i32), ("res", f32p), ("res_ps", i32), ("res_up2", i32),

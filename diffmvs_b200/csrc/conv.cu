@@ -232,7 +232,8 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
     return DMVS_ERR_ARG;
   if (!aligned16(d.w)) return DMVS_ERR_ALIGN;
   if (phase_launch) {   // one-sided padding / strided output rows: the TMA-fed tcgen05 kernel only
-    if (d.precision != DMVS_PREC_AUTO && d.precision != DMVS_PREC_WS2_TF32X3) return DMVS_ERR_UNSUPPORTED;
+    if (d.precision != DMVS_PREC_AUTO && d.precision != DMVS_PREC_WS2_TF32X3 && d.precision != DMVS_PREC_WS2_TF32_F16C)
+      return DMVS_ERR_UNSUPPORTED;
     if (d.res_up2 || d.pad_d < 0 || d.pad_h < 0 || d.pad_w < 0) return DMVS_ERR_ARG;
     if (!conv_ws2_supported(d)) return DMVS_ERR_UNSUPPORTED;
     return dispatch_conv_ws2(d, static_cast<cudaStream_t>(stream));
@@ -250,7 +251,7 @@ extern "C" int dmvs_conv_f32(const dmvs_conv_desc* dp, void* stream) {
         return dispatch_conv_ws(alt, static_cast<cudaStream_t>(stream));
       }
     }
-  } else if (d.precision == DMVS_PREC_WS2_TF32X3) {
+  } else if (d.precision == DMVS_PREC_WS2_TF32X3 || d.precision == DMVS_PREC_WS2_TF32_F16C) {
     // TMA-fed width-stacked kernel where it applies, the first-generation one for nearest-upsampled inputs, FFMA elsewhere
     if (conv_ws2_supported(d)) return dispatch_conv_ws2(d, static_cast<cudaStream_t>(stream));
     if (conv_ws_supported(d)) {
@@ -383,6 +384,8 @@ extern "C" int dmvs_conv_backends(const dmvs_conv_desc* dp) {
 #endif
   if (conv_ws_supported(d)) mask |= 8;       // bit 3: tcgen05 kernel, kernel-row taps stacked along N
   if (conv_ws2_supported(d)) mask |= 16;     // bit 4: the same arithmetic behind the TMA-fed pipeline (conv_ws2.cu)
+  if ((mask & 16) && d.w_ws16 != nullptr && !(d.w_ws_pair != nullptr && d.C1 <= 4 && d.C2 == 0 && d.stride == 1 && d.KH >= 2))
+    mask |= 32;                              // bit 5: ... with the fp16 correction MMA (DMVS_PREC_WS2_TF32_F16C)
   return mask;
 }
 

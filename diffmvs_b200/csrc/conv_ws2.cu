@@ -76,6 +76,8 @@ struct alignas(64) Ws2Args {
                          //    stage, the MMA's second K quad is the same plane one tile row further down
   int KHm;               // row-MMAs per (block, stage): KHe, or ceil(KHe / 2) when paired
   int y_rs, res_rs;      // floats between consecutive output / residual rows (dense: Wo * pixel stride)
+  int corr16;            // 1: two MMAs per kernel row instead of three - A_hi*B_hi in TF32 plus ONE kind::f16 MMA (K = 16)
+                         //    computing A_lo*B_hi + A_hi*B_lo from fp16 copies of the correction operands (see dispatch)
   float inv_in_cols;
   int64_t w_off;         // offset (floats) of this launch's hi slabs inside w_ws
   int64_t w_plane;       // distance (floats) from a hi slab to its lo twin
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
     // warp w issues the MMAs of M blocks w, w + 4, ...; the descriptors' upper words are constant, the lower words
     // (start address field) advance by plain 32-bit adds, so one kernel row costs a handful of scalar instructions
     const bool leader = elect_one();
-    const uint32_t idesc = idesc_tf32_m128(N);
+    const uint32_t idesc = idesc_tf32_m128(N), idesc16 = idesc_f16_m128(N);
     // paired rows: K quad 1 of the A operand is quad 0 one tile row further down (kernel row 2*khp + 1)
     const uint32_t lbo_a = (uint32_t)(a.pair ? a.in_cols : a.plane) * 16u, lbo_b = (uint32_t)N * 16u;
     const uint32_t a_step = (uint32_t)(a.pair ? 2 * a.in_cols : a.in_cols);
@@ -246,9 +248,14 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
 #pragma unroll 1
           for (int khe = 0; khe < a.KHm; ++khe, a_off += a_step, b_off += b_step, r >>= 1) {
             if (!(r & 1u)) continue;
-            umma_tf32_w(d_tmem, al + a_off, a_hiword, bh + b_off, b_hiword, idesc, accum);
-            umma_tf32_w(d_tmem, ah + a_off, a_hiword, bl + b_off, b_hiword, idesc, 1u);
-            umma_tf32_w(d_tmem, ah + a_off, a_hiword, bh + b_off, b_hiword, idesc, 1u);
+            if (a.corr16) {
+              umma_tf32_w(d_tmem, ah + a_off, a_hiword, bh + b_off, b_hiword, idesc, accum);
+              umma_f16_w(d_tmem, al + a_off, a_hiword, bl + b_off, b_hiword, idesc16, 1u);   // [A_lo | A_hi] x [B_hi ; B_lo]
+            } else {
+              umma_tf32_w(d_tmem, al + a_off, a_hiword, bh + b_off, b_hiword, idesc, accum);
+              umma_tf32_w(d_tmem, ah + a_off, a_hiword, bl + b_off, b_hiword, idesc, 1u);
+              umma_tf32_w(d_tmem, ah + a_off, a_hiword, bh + b_off, b_hiword, idesc, 1u);
+            }
             accum = 1u;
           }
         }
@@ -283,6 +290,54 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
       float* hi = hi0 + slot * a.stage_f;
       float* lo = lo0 + slot * a.stage_f;
       const int iy0 = cur.ty0 + a.smin_h, ix0 = cur.tx0 + a.smin_w;   // GN layers are stride 1
+      if (a.corr16) {
+        // fp16 correction operands: a thread owns a position's 8 channels.  hi (TF32-rounded fp32) stays in place; the
+        // "lo" planes receive 16-byte units of 8 halves: plane 0 = fp16(x - hi) (exact residual, rounded once),
+        // plane 1 = fp16(hi) saturated - the K = 16 operand row [A_lo | A_hi] of the kind::f16 MMA
+        float4 g1a = make_float4(0.f, 0.f, 0.f, 0.f), g0a = g1a, g1b = g1a, g0b = g1a;
+        bool oka = false, okb = false;
+        if (GN) {
+          const int ch = cur.chunk * 8;
+          oka = ch < d.C1;
+          okb = ch + 4 < d.C1;
+          if (oka) { g1a = *reinterpret_cast<const float4*>(gn_s + ch); g0a = *reinterpret_cast<const float4*>(gn_s + d.C1 + ch); }
+          if (okb) { g1b = *reinterpret_cast<const float4*>(gn_s + ch + 4); g0b = *reinterpret_cast<const float4*>(gn_s + d.C1 + ch + 4); }
+        }
+        float4* ph0 = reinterpret_cast<float4*>(hi);
+        float4* ph1 = reinterpret_cast<float4*>(hi + a.plane * 4);
+        uint4* pc0 = reinterpret_cast<uint4*>(lo);
+        uint4* pc1 = reinterpret_cast<uint4*>(lo + a.plane * 4);
+#pragma unroll 2
+        for (int u = wtid; u < a.box_units; u += kSplitThreads) {
+          float4 va = ph0[u], vb = ph1[u];
+          if (GN) {
+            const int row = (int)(((float)u + 0.5f) * a.inv_in_cols);
+            const int col = u - row * a.in_cols;
+            const int iy = iy0 + row, ix = ix0 + col;
+            const bool inside = iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;   // padding stays zero
+            if (oka && inside) {
+              va.x = siluf_(fmaf(va.x, g1a.x, g0a.x)); va.y = siluf_(fmaf(va.y, g1a.y, g0a.y));
+              va.z = siluf_(fmaf(va.z, g1a.z, g0a.z)); va.w = siluf_(fmaf(va.w, g1a.w, g0a.w));
+            } else {
+              va = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (okb && inside) {
+              vb.x = siluf_(fmaf(vb.x, g1b.x, g0b.x)); vb.y = siluf_(fmaf(vb.y, g1b.y, g0b.y));
+              vb.z = siluf_(fmaf(vb.z, g1b.z, g0b.z)); vb.w = siluf_(fmaf(vb.w, g1b.w, g0b.w));
+            } else {
+              vb = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          float4 ha, hb, la, lb;
+          split_tf32(va.x, ha.x, la.x); split_tf32(va.y, ha.y, la.y); split_tf32(va.z, ha.z, la.z); split_tf32(va.w, ha.w, la.w);
+          split_tf32(vb.x, hb.x, lb.x); split_tf32(vb.y, hb.y, lb.y); split_tf32(vb.z, hb.z, lb.z); split_tf32(vb.w, hb.w, lb.w);
+          ph0[u] = ha;
+          ph1[u] = hb;
+          pc0[u] = make_uint4(pack_f16x2(va.x - ha.x, va.y - ha.y), pack_f16x2(va.z - ha.z, va.w - ha.w),
+                              pack_f16x2(vb.x - hb.x, vb.y - hb.y), pack_f16x2(vb.z - hb.z, vb.w - hb.w));
+          pc1[u] = make_uint4(pack_f16x2(ha.x, ha.y), pack_f16x2(ha.z, ha.w), pack_f16x2(hb.x, hb.y), pack_f16x2(hb.z, hb.w));
+        }
+      } else {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (q == 1 && a.pair) break;
@@ -322,6 +377,7 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
           ph[u] = h;
           pl[u] = l;
         }
+      }
       }
       fence_async_smem();
       __syncwarp();                                          // one arrival per warp: the lanes' writes are ordered before it
@@ -797,6 +853,15 @@ int dispatch_conv_ws2(const dmvs_conv_desc& d, cudaStream_t st, int32_t* plan_ou
            d.in_stats == nullptr;
   a.KHm = a.pair ? (a.KHe + 1) / 2 : a.KHe;
   if (a.pair) a.d.w_ws = d.w_ws_pair;
+  // DMVS_PREC_WS2_TF32_F16C: the two correction products of the 3xTF32 scheme, A_lo*B_hi + A_hi*B_lo, come from ONE
+  // kind::f16 MMA (K = 16: operand rows [A_lo | A_hi] and [B_hi ; B_lo] as fp16, 11 significant bits - the same as the
+  // TF32 copies they replace; A_hi saturates at 65504, where only the correction term degrades).  Two MMAs per kernel
+  // row instead of three.  Needs the slabs packed with fp16 correction planes (`w_ws16`).
+  a.corr16 = (d.precision == DMVS_PREC_WS2_TF32_F16C && d.w_ws16 != nullptr && !a.pair) ? 1 : 0;
+  if (a.corr16) {
+    if (!aligned16(d.w_ws16)) return DMVS_ERR_ALIGN;
+    a.d.w_ws = d.w_ws16;
+  }
   int remaining = (d.Cout + 7) & ~7, co_base = 0;
   int64_t w_off = 0;
   int n_launch = 0;

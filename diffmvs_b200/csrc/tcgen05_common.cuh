@@ -25,6 +25,11 @@ __device__ __forceinline__ uint32_t idesc_tf32_m128(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// instruction descriptor of kind::f16 with fp16 operands (format 0), D = f32, both K-major, K = 16 per instruction
+__device__ __forceinline__ uint32_t idesc_f16_m128(int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
@@ -42,6 +47,23 @@ __device__ __forceinline__ void umma_tf32_w(uint32_t d_tmem, uint32_t a_lo, uint
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n}\n" ::"r"(d_tmem),
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// kind::f16 twin of umma_tf32_w (K = 16 halves = the same 32 bytes per operand row)
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %2};\nmov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// two floats -> packed fp16 pair (first argument in the LOW half), round to nearest, saturating at +-65504
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
 }
 
 // arrives on `bar` once every MMA issued so far by this thread has retired (implies tcgen05.fence::before_thread_sync)

@@ -17,13 +17,15 @@ import os
 
 from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU_Q, EPI_GRU_ZR, EPI_STD,  # noqa: F401
                     PREC_AUTO, PREC_FP32, PREC_TC_TF32, PREC_TC_TF32X3, PREC_TF32, PREC_TF32X3, PREC_WS_TF32, PREC_WS_TF32X3,
-                    PREC_WS2_TF32X3,
+                    PREC_WS2_TF32X3, PREC_WS2_TF32_F16C,
                     RES_NONE, RES_POST_ACT, RES_PRE_ACT, ConvDesc, check)
 
 # Arithmetic of the convolutions (storage is always fp32).  fp32-class modes (parity-safe, <= 5e-6 depth rel-L1):
 #   "auto"  (default)  per layer the fastest of the back ends below, measured on first use (like cudnn.benchmark)
 #   "fp32"             CUDA-core kernel everywhere (packed fp32x2 FMAs)
 #   "ws2_tf32x3"       TMA-fed width-stacked tcgen05/TMEM kernel (conv_ws2.cu) wherever it applies, 3xTF32 operand split
+#   "ws2_f16c"         as "ws2_tf32x3" with the two correction products from one fp16 MMA (2 MMAs per kernel row instead
+#                      of 3, the same 11 significant bits per factor)
 #   "ws_tf32x3"        the first-generation width-stacked tcgen05 kernel (conv_ws.cu; still used for upsampled inputs)
 # Plain-TF32 mode (NOT parity-safe on the synthetic weights: 1e-3..3e-3 depth rel-L1, 2-6 % index flips):
 #   "ws_tf32"          operands rounded to TF32 - the numerics cuDNN uses under torch defaults
@@ -31,7 +33,7 @@ from ._cabi import (ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_SILU, ACT_TANH, EPI_GRU
 # library built with DMVS_BUILD_LEGACY=1 (`legacy_backends()`); no shipped configuration uses them.
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32, "tc_tf32x3": PREC_TC_TF32X3,
               "tc_tf32": PREC_TC_TF32, "auto": PREC_AUTO, "ws_tf32x3": PREC_WS_TF32X3, "ws_tf32": PREC_WS_TF32,
-              "ws2_tf32x3": PREC_WS2_TF32X3}
+              "ws2_tf32x3": PREC_WS2_TF32X3, "ws2_f16c": PREC_WS2_TF32_F16C}
 _precision = PRECISIONS[os.environ.get("DMVS_PRECISION", "auto")]
 
 
@@ -61,7 +63,8 @@ def set_precision(name: str) -> None:
 _AUTOTUNE = os.environ.get("DMVS_AUTOTUNE", "1") != "0"
 _AUTOTUNE_WS = os.environ.get("DMVS_AUTO_WS", "1") != "0"
 _TUNED: dict = {}
-_BACKEND_BITS = ((1, PREC_FP32), (4, PREC_TC_TF32X3), (8, PREC_WS_TF32X3), (16, PREC_WS2_TF32X3))
+_AUTOTUNE_F16C = os.environ.get("DMVS_AUTO_F16C", "1") != "0"     # let `auto` consider the fp16-correction variant
+_BACKEND_BITS = ((1, PREC_FP32), (4, PREC_TC_TF32X3), (8, PREC_WS_TF32X3), (16, PREC_WS2_TF32X3), (32, PREC_WS2_TF32_F16C))
 
 
 def set_autotune(enabled: bool, use_ws: Optional[bool] = None) -> None:
@@ -170,7 +173,8 @@ def _disjoint(out: Tensor, *others: Optional[Tensor]) -> bool:
 def _tune(d: "ConvDesc", key, safe: bool = True) -> int:
     lib = _cabi.lib()
     mask = lib.dmvs_conv_backends(C.byref(d))
-    cands = [code for bit, code in _BACKEND_BITS if mask & bit and (code != PREC_WS_TF32X3 or _AUTOTUNE_WS)]
+    cands = [code for bit, code in _BACKEND_BITS if mask & bit and (code != PREC_WS_TF32X3 or _AUTOTUNE_WS)
+             and (code != PREC_WS2_TF32_F16C or _AUTOTUNE_F16C)]
     if len(cands) < 2:
         return cands[0]
     if torch.cuda.is_current_stream_capturing():
@@ -253,7 +257,8 @@ _LAST_CONV_BACKEND = PREC_FP32
 # C kernel behind each back-end code (what `cuobjdump` / ncu list for that launch)
 KERNEL_OF_BACKEND = {PREC_FP32: "conv_kernel", PREC_TF32X3: "conv_mma_kernel", PREC_TF32: "conv_mma_kernel",
                      PREC_TC_TF32X3: "conv_tc_kernel", PREC_TC_TF32: "conv_tc_kernel", PREC_WS_TF32X3: "conv_ws_kernel",
-                     PREC_WS_TF32: "conv_ws_kernel", PREC_WS2_TF32X3: "conv_ws2_kernel", PREC_AUTO: "conv_kernel|conv_tc_kernel"}
+                     PREC_WS_TF32: "conv_ws_kernel", PREC_WS2_TF32X3: "conv_ws2_kernel",
+                     PREC_WS2_TF32_F16C: "conv_ws2_kernel", PREC_AUTO: "conv_kernel|conv_tc_kernel"}
 
 
 def set_profiler(p: Optional[Profiler]) -> None:
@@ -359,24 +364,26 @@ class PackedConv:
     w_ws: Optional[Tensor] = None  # width-stacked tcgen05 slabs for stride 1 (packing.pack_ws)
     ws_strided: Optional[dict] = None   # (stride, pad_h, pad_w) -> slabs for strided use, built on first use
     w_ws_pair: Optional[Tensor] = None  # <= 4 input channels: slabs with kernel rows paired along K (packing.pack_ws_pair)
+    w_ws16: Optional[Tensor] = None     # `w_ws` with fp16 correction planes (packing.pack_ws(..., corr16=True)), stride 1
     w_host: Optional[Tensor] = None     # 8 -> 1 3x3x3 layers: [kd][kh][kw][ci] on the HOST (ops.conv3d_to1 launch parameters)
     bias_host: float = 0.0
 
-    def ws_slabs(self, stride: int, pad_h: int, pad_w: int) -> Optional[Tensor]:
+    def ws_slabs(self, stride: int, pad_h: int, pad_w: int, corr16: bool = False) -> Optional[Tensor]:
         if stride == 1 or self.w_ws is None:
-            return self.w_ws
+            return self.w_ws16 if corr16 else self.w_ws
         if self.ws_strided is None:
             self.ws_strided = {}
-        key = (stride, pad_h, pad_w)
+        key = (stride, pad_h, pad_w, corr16)
         if key not in self.ws_strided:
             from . import packing
-            self.ws_strided[key] = packing.pack_ws_from_packed(self.w, self.cout, stride, (pad_h, pad_w)).to(self.w.device)
+            self.ws_strided[key] = packing.pack_ws_from_packed(self.w, self.cout, stride, (pad_h, pad_w),
+                                                               corr16=corr16).to(self.w.device)
         return self.ws_strided[key]
 
     def to(self, device) -> "PackedConv":
         mv = lambda t: None if t is None else t.to(device)
         return PackedConv(self.w.to(device), mv(self.bias), self.cin, self.cout, self.k, mv(self.w_t), mv(self.w_tc),
-                          mv(self.w_ws), None, mv(self.w_ws_pair), self.w_host, self.bias_host)
+                          mv(self.w_ws), None, mv(self.w_ws_pair), mv(self.w_ws16), self.w_host, self.bias_host)
 
 
 def _row_strided(t: Tensor, name: str) -> Tuple[int, int]:
@@ -457,9 +464,12 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     d.w, d.bias = _ptr(pc.w), _ptr(pc.bias)
     d.w_t, d.w_tc, d.w_ws = _ptr(pc.w_t), _ptr(pc.w_tc), _ptr(pc.ws_slabs(stride, ph, pw))
     d.w_ws_pair = _ptr(pc.w_ws_pair) if stride == 1 else None
+    d.w_ws16 = _ptr(pc.ws_slabs(stride, ph, pw, corr16=True)) if pc.w_ws16 is not None else None
     d.precision = _precision if pc.w_t is not None else PREC_FP32
-    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3) and pc.w_tc is None:
-        d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3, PREC_WS2_TF32X3) else PREC_TF32
+    if d.precision in (PREC_TC_TF32X3, PREC_TC_TF32, PREC_WS_TF32X3, PREC_WS_TF32, PREC_WS2_TF32X3,
+                       PREC_WS2_TF32_F16C) and pc.w_tc is None:
+        d.precision = PREC_TF32X3 if d.precision in (PREC_TC_TF32X3, PREC_WS_TF32X3, PREC_WS2_TF32X3,
+                                                     PREC_WS2_TF32_F16C) else PREC_TF32
     d.KD, d.KH, d.KW, d.stride = KD, KH, KW, stride
     d.pad_d, d.pad_h, d.pad_w = pd, ph, pw
     d.y, d.Do, d.Ho, d.Wo, d.Cout, d.y_ps = _ptr(out), Do, Ho, Wo, pc.cout, y_ps
@@ -477,7 +487,7 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
     d.epi, d.gru_hidden = epi, gru_hidden
     if explicit_out is not None:
         d.explicit_extent, d.y_row_stride, d.res_row_stride = 1, y_rs, res_rs
-        if d.precision not in (PREC_AUTO, PREC_WS2_TF32X3):
+        if d.precision not in (PREC_AUTO, PREC_WS2_TF32X3, PREC_WS2_TF32_F16C):
             d.precision = PREC_WS2_TF32X3        # the only back end with strided rows; same fp32-class arithmetic
     if aux1 is not None:
         d.aux1, d.aux1_ps = _ptr(aux1), pixel_stride(aux1, "conv aux1")
@@ -487,7 +497,7 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         raise ValueError("conv: out_stats must be a zero-initialised int64 [N,4,2] tensor (fixed-point accumulators)")
     d.out_stats = _ptr(out_stats)
     if d.precision == PREC_AUTO and explicit_out is not None:
-        d.precision = PREC_WS2_TF32X3
+        d.precision = PREC_WS2_TF32_F16C if (_AUTOTUNE_F16C and pc.w_ws16 is not None) else PREC_WS2_TF32X3
     if d.precision == PREC_AUTO and _AUTOTUNE:
         dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
         _load_default_table_once(dev)
@@ -496,7 +506,7 @@ def conv(x: Tensor, pc: PackedConv, *, x2: Optional[Tensor] = None, stride: int 
         hit = _tuned_lookup(dev, sig)
         d.precision = hit[0] if hit is not None else _tune(d, (dev,) + sig, _disjoint(out, x, x2, res, aux1, aux2))
     global _LAST_CONV_BACKEND
-    _LAST_CONV_BACKEND = PREC_WS_TF32X3 if (d.precision == PREC_WS2_TF32X3 and in_up2) else d.precision
+    _LAST_CONV_BACKEND = PREC_WS_TF32X3 if (d.precision in (PREC_WS2_TF32X3, PREC_WS2_TF32_F16C) and in_up2) else d.precision
     check(_cabi.lib().dmvs_conv_f32(C.byref(d), _stream()), "dmvs_conv_f32")
     return out
 

@@ -56,13 +56,14 @@ def pack_weight(w: torch.Tensor, bias: Optional[torch.Tensor] = None, pad_cin: i
     lo = rna_tf32(quad - hi)
     w_tc = torch.stack((hi, lo), 0).contiguous()
     w_ws = pack_ws(full.view(kd, kh, kw, ci8, co16), cout) if kw <= 8 else None   # stride-1 slabs
+    w_ws16 = pack_ws(full.view(kd, kh, kw, ci8, co16), cout, corr16=True) if kw <= 8 else None
     w_pair = pack_ws_pair(full.view(kd, kh, kw, ci8, co16), cout) if (w_ws is not None and cin <= 4 and kh >= 2) else None
     w_host, bias_host = None, 0.0
     if cout == 1 and cin == 8 and (kd, kh, kw) == (3, 3, 3):     # ops.conv3d_to1: weights travel as launch parameters
         w_host = w[0].permute(1, 2, 3, 0).contiguous()             # [kd][kh][kw][ci]
         bias_host = 0.0 if b is None else float(b[0])
     return PackedConv(packed.contiguous(), b, cin, cout, (kd, kh, kw), w_t.contiguous(), w_tc, w_ws, None, w_pair,
-                      w_host, bias_host)
+                      w_ws16, w_host, bias_host)
 
 
 def ws_cc_max(kw: int) -> int:
@@ -77,7 +78,7 @@ def ws_extent(k: int, pad: int, stride: int) -> Tuple[int, int]:
     return smin, (k - 1 - pad) // stride - smin + 1
 
 
-def pack_ws(full: torch.Tensor, cout: int, stride: int = 1, pad: Tuple[int, int] = (0, 0)) -> torch.Tensor:
+def pack_ws(full: torch.Tensor, cout: int, stride: int = 1, pad: Tuple[int, int] = (0, 0), corr16: bool = False) -> torch.Tensor:
     """full [KD,KH,KW,cin_pad8,cout_pad16] -> flat width-stacked slabs (include/diffmvs_b200.h, `w_ws`).  A stride-S
     convolution is S*S stride-1 phases over decimated input planes; with (KHe, KWe) the kernel extent in phase-plane
     shifts, every output-channel chunk (CC channels, N = KWe*CC rounded up to 16) stores the planes
@@ -110,7 +111,16 @@ def pack_ws(full: torch.Tensor, cout: int, stride: int = 1, pad: Tuple[int, int]
                         tap = full[:, th, tw, :, co_base:co_base + avail].reshape(kd, ci8 // 8, 2, 4, avail)
                         slab[:, pa * S + pb, :, khs, :, kws * cc:kws * cc + avail, :] = tap.permute(0, 1, 2, 4, 3)
         hi = rna_tf32(slab)
-        lo = rna_tf32(slab - hi)
+        if corr16:
+            # `w_ws16`: the lo plane holds the fp16 correction operand of DMVS_PREC_WS2_TF32_F16C - per (kernel row, n) two
+            # 16-byte units of 8 halves: unit 0 = fp16(hi) of the chunk's input channels 0..7, unit 1 = fp16(w - hi)
+            res = slab - hi                                   # exact in fp32
+            c16 = torch.zeros(kd, S * S, ci8 // 8, khe, 2, n, 8, dtype=torch.float16)
+            c16[..., 0, :, 0:4], c16[..., 0, :, 4:8] = hi[..., 0, :, :].half(), hi[..., 1, :, :].half()
+            c16[..., 1, :, 0:4], c16[..., 1, :, 4:8] = res[..., 0, :, :].half(), res[..., 1, :, :].half()
+            lo = c16.contiguous().view(torch.float32)         # [..., 2, n, 4]: the same bytes as a lo plane
+        else:
+            lo = rna_tf32(slab - hi)
         parts += [hi.reshape(-1), lo.reshape(-1)]
         co_base += cc
         remaining -= cc
@@ -188,14 +198,14 @@ def compose_1x1_into_3x3(w3: torch.Tensor, w1: torch.Tensor, b1: Optional[torch.
     return w.float(), s.sum(dim=(0, 1)).float(), table.float().contiguous()
 
 
-def pack_ws_from_packed(w: torch.Tensor, cout: int, stride: int, pad: Tuple[int, int]) -> torch.Tensor:
+def pack_ws_from_packed(w: torch.Tensor, cout: int, stride: int, pad: Tuple[int, int], corr16: bool = False) -> torch.Tensor:
     """Width-stacked slabs for a given stride / padding from the FFMA layout `PackedConv.w`
     ([KD,KH,KW,cin_pad4,cout_pad4]); built on first use of a strided layer (ops.conv) and cached."""
     w = w.detach().float().cpu()
     kd, kh, kw, ci4, co4 = w.shape
     full = torch.zeros(kd, kh, kw, (ci4 + 7) & ~7, (cout + 15) & ~15, dtype=torch.float32)
     full[..., :ci4, :min(co4, full.shape[-1])] = w[..., :min(co4, full.shape[-1])]
-    return pack_ws(full, cout, stride, pad)
+    return pack_ws(full, cout, stride, pad, corr16=corr16)
 
 
 def bn_scale_shift(sd: SD, p: str) -> Tuple[torch.Tensor, torch.Tensor]:

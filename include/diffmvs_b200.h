@@ -56,6 +56,11 @@ extern "C" {
                                   persistent CTA per SM, cp.async.bulk.tensor producer, split / MMA / epilogue warps, two
                                   TMEM accumulator sets; conv_ws.cu for nearest-upsampled inputs, FFMA elsewhere */
 
+#define DMVS_PREC_WS2_TF32_F16C 9 /* as WS2_TF32X3 with the two correction products A_lo*B_hi + A_hi*B_lo computed by one
+                                     kind::f16 MMA (K = 16) from fp16 copies of the correction operands: two MMAs per kernel
+                                     row instead of three, the same 11 significant bits in every factor (`w_ws16` required;
+                                     layers it does not cover - <= 4 input channels, no `w_ws16` - run as WS2_TF32X3) */
+
 /* epilogue kinds */
 #define DMVS_EPI_STD 0
 #define DMVS_EPI_GRU_ZR 1 /* c<hid: z=sigmoid(v); c>=hid: r*h = sigmoid(v)*aux1[c-hid]   module.py:166-168 */
@@ -108,6 +113,10 @@ typedef struct dmvs_conv_desc {
                                each [KD][ceil(KH/2)][2][N][4]: quad q of pair j holds kernel row 2j+q (zero past KH-1) of
                                input channels 0..3 (packing.pack_ws_pair).  The TMA-fed back end then issues ceil(KH/2)
                                row-MMAs per stage instead of KH and stages one channel quad instead of two. */
+  const float* w_ws16;      /* optional: the `w_ws` layout with the lo plane of every slab replaced by fp16 correction
+                               operands for DMVS_PREC_WS2_TF32_F16C - per (kernel row, column n) two 16-byte units of 8
+                               halves: unit 0 = fp16(hi) of input channels 0..7 of the chunk, unit 1 = fp16(w - hi)
+                               (packing.pack_ws(..., corr16=True)); packed for THIS stride and padding like `w_ws` */
   int32_t precision;        /* DMVS_PREC_* */
   const float* bias;        /* [Cout] or NULL */
   int32_t KD, KH, KW, stride, pad_d, pad_h, pad_w;

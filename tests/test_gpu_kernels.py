@@ -33,11 +33,11 @@ def _nchw(y):  # GPU [N,H,W,C] -> CPU NCHW
 
 
 PREC_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "tf32": 3e-3, "tc_tf32x3": 2e-5, "tc_tf32": 3e-3, "auto": 2e-5,
-            "ws_tf32x3": 2e-5, "ws_tf32": 3e-3, "ws2_tf32x3": 2e-5}   # max-abs error relative to the output scale
+            "ws_tf32x3": 2e-5, "ws_tf32": 3e-3, "ws2_tf32x3": 2e-5, "ws2_f16c": 2e-5}   # max-abs error relative to the output scale
 
 
 def _modes():
-    modes = ["fp32", "auto", "ws_tf32x3", "ws_tf32", "ws2_tf32x3"]
+    modes = ["fp32", "auto", "ws_tf32x3", "ws_tf32", "ws2_tf32x3", "ws2_f16c"]
     try:                       # the round-1 back ends only exist in a DMVS_BUILD_LEGACY=1 library
         if ops.legacy_backends():
             modes += list(ops.LEGACY_MODES)

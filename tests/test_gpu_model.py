@@ -224,7 +224,8 @@ def test_full_size_against_cpu_fp32_oracle(workload, monkeypatch):
         assert (c.cpu() - r).abs().mean().item() < 1e-4, (workload, "conf", i)
 
 
-@pytest.mark.parametrize("mode,tol", [("ws_tf32x3", DEPTH_TOL), ("ws2_tf32x3", DEPTH_TOL), ("fp32", DEPTH_TOL), ("ws_tf32", 1e-2)])
+@pytest.mark.parametrize("mode,tol", [("ws_tf32x3", DEPTH_TOL), ("ws2_tf32x3", DEPTH_TOL), ("ws2_f16c", DEPTH_TOL),
+                                      ("fp32", DEPTH_TOL), ("ws_tf32", 1e-2)])
 @pytest.mark.parametrize("workload", ["cas_small", "cfg2"])
 def test_tensor_core_modes_meet_the_parity_bar(workload, mode, tol, monkeypatch):
     """The convolution modes against the CPU oracle.  The 3xTF32 modes (operand split) and the FFMA mode must stay in the

@@ -37,7 +37,7 @@ for name, N, cin, cout, k, s, dims in LAYERS:
     wshape = (cout, cin, *k) if three_d else (cout, cin, k[1], k[2])
     w = (torch.rand(*wshape, generator=g) - 0.5) / math.sqrt(cin * k[0] * k[1] * k[2])
     pc = packing.pack_weight(w, torch.zeros(cout), pad_cin=cin_st if cin_st != cin else 0).to("cuda")
-    ops.set_precision("ws2_tf32x3")
+    ops.set_precision(os.environ.get("DMVS_TIMELINE_MODE", "ws2_tf32x3"))
     y = ops.conv(x, pc, stride=s, act=ops.ACT_RELU)
     ops.conv(x, pc, stride=s, act=ops.ACT_RELU, out=y)
     torch.cuda.synchronize()
