@@ -328,11 +328,15 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
               vb = make_float4(0.f, 0.f, 0.f, 0.f);
             }
           }
-          float4 ha, hb, la, lb;
-          split_tf32(va.x, ha.x, la.x); split_tf32(va.y, ha.y, la.y); split_tf32(va.z, ha.z, la.z); split_tf32(va.w, ha.w, la.w);
-          split_tf32(vb.x, hb.x, lb.x); split_tf32(vb.y, hb.y, lb.y); split_tf32(vb.z, hb.z, lb.z); split_tf32(vb.w, hb.w, lb.w);
-          ph0[u] = ha;
-          ph1[u] = hb;
+          // The TF32 operand is read raw: the tensor core ignores the 13 low mantissa bits (truncation, verified on B200),
+          // so "hi" = the truncated value needs no store and the exact residual x - trunc(x) goes to the fp16 plane
+          float4 ha, hb;
+          ha.x = trunc_tf32(va.x); ha.y = trunc_tf32(va.y); ha.z = trunc_tf32(va.z); ha.w = trunc_tf32(va.w);
+          hb.x = trunc_tf32(vb.x); hb.y = trunc_tf32(vb.y); hb.z = trunc_tf32(vb.z); hb.w = trunc_tf32(vb.w);
+          if (GN) {            // the prologue changed the values: the raw operand has to be written back
+            ph0[u] = va;
+            ph1[u] = vb;
+          }
           pc0[u] = make_uint4(pack_f16x2(va.x - ha.x, va.y - ha.y), pack_f16x2(va.z - ha.z, va.w - ha.w),
                               pack_f16x2(vb.x - hb.x, vb.y - hb.y), pack_f16x2(vb.z - hb.z, vb.w - hb.w));
           pc1[u] = make_uint4(pack_f16x2(ha.x, ha.y), pack_f16x2(ha.z, ha.w), pack_f16x2(hb.x, hb.y), pack_f16x2(hb.z, hb.w));

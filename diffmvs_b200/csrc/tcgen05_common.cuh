@@ -146,6 +146,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
 }
 
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
 // ---- TMEM -> registers: NCH consecutive fp32 columns of this thread's lane (32x32b shape); no wait inside -----------
 template <int NCH>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NCH]);
