@@ -8,7 +8,8 @@
  *
  * Conventions
  *   - all tensors are fp32, device memory, channels-last: 2-D maps are [N][H][W][C], volumes are
- *     [N][D][H][W][C].  A "pixel stride" (`*_ps`) is the distance in floats between consecutive
+ *     [N][D][H][W][C] (exceptions are stated per function: uint8 images, the float64 camera matrices
+ *     and integer masks of the fusion entry points, the host-side weight block of dmvs_conv3d_to1_f32).  A "pixel stride" (`*_ps`) is the distance in floats between consecutive
  *     pixels, so a channel slice of a wider buffer is addressed with ptr+offset and the wide stride
  *     (this is how every `torch.cat`/`torch.split` of the reference is made free).
  *   - every function only enqueues work on `stream` (a cudaStream_t passed as void*); it never
