@@ -337,9 +337,13 @@ __global__ void __launch_bounds__(kWs2Threads, 1) conv_ws2_kernel(const __grid_c
             ph0[u] = va;
             ph1[u] = vb;
           }
-          pc0[u] = make_uint4(pack_f16x2(va.x - ha.x, va.y - ha.y), pack_f16x2(va.z - ha.z, va.w - ha.w),
-                              pack_f16x2(vb.x - hb.x, vb.y - hb.y), pack_f16x2(vb.z - hb.z, vb.w - hb.w));
-          pc1[u] = make_uint4(pack_f16x2(ha.x, ha.y), pack_f16x2(ha.z, ha.w), pack_f16x2(hb.x, hb.y), pack_f16x2(hb.z, hb.w));
+          // the two correction products are balanced by powers of two (exact): A_lo * 16 meets B_hi / 16 and A_hi / 16 meets
+          // B_lo * 16 (packing.pack_ws), which keeps the small residuals out of fp16's subnormal range
+          constexpr float kUp = 16.0f, kDn = 0.0625f;
+          pc0[u] = make_uint4(pack_f16x2((va.x - ha.x) * kUp, (va.y - ha.y) * kUp), pack_f16x2((va.z - ha.z) * kUp, (va.w - ha.w) * kUp),
+                              pack_f16x2((vb.x - hb.x) * kUp, (vb.y - hb.y) * kUp), pack_f16x2((vb.z - hb.z) * kUp, (vb.w - hb.w) * kUp));
+          pc1[u] = make_uint4(pack_f16x2(ha.x * kDn, ha.y * kDn), pack_f16x2(ha.z * kDn, ha.w * kDn),
+                              pack_f16x2(hb.x * kDn, hb.y * kDn), pack_f16x2(hb.z * kDn, hb.w * kDn));
         }
       } else {
 #pragma unroll

@@ -116,8 +116,10 @@ def pack_ws(full: torch.Tensor, cout: int, stride: int = 1, pad: Tuple[int, int]
             # 16-byte units of 8 halves: unit 0 = fp16(hi) of the chunk's input channels 0..7, unit 1 = fp16(w - hi)
             res = slab - hi                                   # exact in fp32
             c16 = torch.zeros(kd, S * S, ci8 // 8, khe, 2, n, 8, dtype=torch.float16)
-            c16[..., 0, :, 0:4], c16[..., 0, :, 4:8] = hi[..., 0, :, :].half(), hi[..., 1, :, :].half()
-            c16[..., 1, :, 0:4], c16[..., 1, :, 4:8] = res[..., 0, :, :].half(), res[..., 1, :, :].half()
+            # balanced by exact powers of two against the activation side (conv_ws2.cu: A_lo * 16, A_hi / 16), so that the
+            # tiny residual w - hi stays out of fp16's subnormal range
+            c16[..., 0, :, 0:4], c16[..., 0, :, 4:8] = (hi[..., 0, :, :] / 16).half(), (hi[..., 1, :, :] / 16).half()
+            c16[..., 1, :, 0:4], c16[..., 1, :, 4:8] = (res[..., 0, :, :] * 16).half(), (res[..., 1, :, :] * 16).half()
             lo = c16.contiguous().view(torch.float32)         # [..., 2, n, 4]: the same bytes as a lo plane
         else:
             lo = rna_tf32(slab - hi)

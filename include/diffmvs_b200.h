@@ -116,7 +116,7 @@ typedef struct dmvs_conv_desc {
                                row-MMAs per stage instead of KH and stages one channel quad instead of two. */
   const float* w_ws16;      /* optional: the `w_ws` layout with the lo plane of every slab replaced by fp16 correction
                                operands for DMVS_PREC_WS2_TF32_F16C - per (kernel row, column n) two 16-byte units of 8
-                               halves: unit 0 = fp16(hi) of input channels 0..7 of the chunk, unit 1 = fp16(w - hi)
+                               halves: unit 0 = fp16(hi / 16) of input channels 0..7 of the chunk, unit 1 = fp16(16 (w - hi))
                                (packing.pack_ws(..., corr16=True)); packed for THIS stride and padding like `w_ws` */
   int32_t precision;        /* DMVS_PREC_* */
   const float* bias;        /* [Cout] or NULL */

@@ -237,3 +237,47 @@ def test_paired_rows_two_channel_chunks():
     got = np.where(np.isnan(a), b, a)
     assert not np.isnan(got).any()
     assert np.abs(got - ref).max() < 1e-6
+
+
+def test_fp16_correction_planes_hold_hi_and_residual():
+    """`w_ws16` (DMVS_PREC_WS2_TF32_F16C): same hi plane as `w_ws`; the lo plane holds, per (kernel row, column n), two
+    16-byte units of 8 halves - unit 0 = fp16(hi) of the chunk's input channels 0..7, unit 1 = fp16(w - hi)."""
+    g = torch.Generator().manual_seed(5)
+    cin, cout, kh, kw = 16, 16, 3, 3
+    w = (torch.rand(cout, cin, kh, kw, generator=g) - 0.5) / 12.0
+    pc = packing.pack_weight(w, None)
+    a, b = pc.w_ws.numpy(), pc.w_ws16
+    n_half = a.size // 2
+    assert np.array_equal(a[:n_half], b[:n_half].numpy())                 # identical hi planes
+    N = (kw * cout + 15) & ~15
+    hi = a[:n_half].reshape(1, 1, cin // 8, kh, 2, N, 4)                  # [kd][phase][chunk][kh][quad][n][4]
+    c16 = b[n_half:].contiguous().view(torch.float16).numpy().astype(np.float64).reshape(1, 1, cin // 8, kh, 2, N, 8)
+    hi8 = np.concatenate([hi[..., 0, :, :], hi[..., 1, :, :]], axis=-1)   # channels 0..7 of the chunk per (kh, n)
+    assert np.abs(c16[..., 0, :, :] * 16 - hi8).max() <= 16 * 3.0e-8       # fp16(hi / 16): exact but for subnormal weights
+    full = hi8 + c16[..., 1, :, :] / 16           # hi + fp16(16 (w - hi)) / 16 reproduces w to 2^-21 |w| (or 2^-29 absolute)
+    ref = np.zeros_like(full)
+    for chunk in range(cin // 8):
+        for r in range(kh):
+            for t in range(kw):
+                ref[0, 0, chunk, r, t * cout:(t + 1) * cout, :] = w[:, chunk * 8:(chunk + 1) * 8, r, t].numpy()
+    assert np.abs(full - ref).max() <= np.abs(ref).max() * 2.0 ** -21 + 2.0 ** -25
+
+
+def test_fp16_correction_product_error_bound():
+    """x*w ~ trunc_tf32(x)*rna_tf32(w) [TF32 MMA] + fp16(x - trunc)*fp16(w_hi) + fp16(trunc)*fp16(w - w_hi) [one fp16 MMA]:
+    every factor keeps 11 significant bits, the dropped lo*lo term is 2^-21 relative - the 3xTF32 class."""
+    g = torch.Generator().manual_seed(6)
+    x = (torch.rand(200000, generator=g) - 0.5) * 8.0
+    w = (torch.rand(200000, generator=g) - 0.5) * 0.5
+    x_hi = (x.view(torch.int32) & -8192).view(torch.float32)               # 0xffffe000: what the tensor core reads
+    w_hi = packing.rna_tf32(w)
+    main = x_hi.double() * w_hi.double()
+    corr = ((x - x_hi) * 16).half().double() * (w_hi / 16).half().double() + (x_hi / 16).half().double() * ((w - w_hi) * 16).half().double()
+    exact = x.double() * w.double()
+    err = (main + corr - exact).abs() / (exact.abs() + 1e-30)
+    # relative to the SCALE of the products (what a sum of them sees) the worst case is 2^-21; the mean relative error
+    # per product is 2^-23.8 (the two products are balanced by 16 / (1/16) to stay clear of fp16's subnormal range)
+    assert float((main + corr - exact).abs().max()) < 2.0 ** -21 * float(exact.abs().max())
+    assert float(err.mean()) < 2.0 ** -23
+    plain = (x_hi.double() * w_hi.double() - x.double() * w.double()).abs() / (x.double().abs() * w.double().abs() + 1e-30)
+    assert float(plain.mean()) > 50 * float(err.mean())                   # what one TF32 pass alone would give
