@@ -2,6 +2,7 @@
 (`dmvs_conv_ws_plan`), the back-end query and the save / load round trip of the autotuning table."""
 import ctypes as C
 import json
+import os
 
 import pytest
 
@@ -99,3 +100,16 @@ def test_span_overlap_detection():
     assert not ops._disjoint(buf, a)
     assert ops._disjoint(buf[:2], buf[2:])
     assert ops._disjoint(buf, None, torch.zeros(3))
+
+
+def test_shipped_tuned_table_loads():
+    """The per-layer back-end table shipped for B200 matches the current signature format and names known modes."""
+    ops._TUNED.clear()
+    assert os.path.exists(ops.DEFAULT_TUNED_TABLE)
+    rows = json.load(open(ops.DEFAULT_TUNED_TABLE))
+    assert len(rows) > 100 and all(len(r["sig"]) == ops._SIG_LEN and r["choice"] in ops.PRECISIONS for r in rows)
+    assert ops.load_tuned(ops.DEFAULT_TUNED_TABLE) == len(rows)
+    # the headline layer 16 -> 16 3x3 at 576 x 800 x 7 views (FeatureNet conv1.1) has an entry, on a tcgen05 back end
+    hits = [v for k, v in ops._TUNED.items() if k[1:8] == (7, 1, 576, 800, 16, 0, 16) and k[8:11] == (1, 3, 3)]
+    assert hits and all(c in (ops.PREC_WS2_TF32X3, ops.PREC_WS2_TF32_F16C, ops.PREC_WS_TF32X3) for c, _ in hits)
+    ops._TUNED.clear()
