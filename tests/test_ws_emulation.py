@@ -14,14 +14,16 @@ import torch.nn.functional as F
 
 from diffmvs_b200 import packing
 
-def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1, pair=False):
+def emulate_ws_conv(x, pc, TH, TW, CC, co_base=0, S=1, pair=False, pad=None, out_hw=None):
     """x [H,W,Cin] (numpy), pc PackedConv (2-D) -> y [Ho,Wo,Cout] via the kernel's data movement (stride S)."""
     H, W, Cin = x.shape
     KD, KH_real, KW_real = pc.k
     assert KD == 1
     Cout = pc.cout
-    pad_h, pad_w = KH_real // 2, KW_real // 2
+    pad_h, pad_w = (KH_real // 2, KW_real // 2) if pad is None else pad
     Ho, Wo = (H + 2 * pad_h - KH_real) // S + 1, (W + 2 * pad_w - KW_real) // S + 1
+    if out_hw is not None:       # phase launch (`explicit_extent`): the output size is given, padding is one-sided
+        Ho, Wo = out_hw
     smin_h, KH = packing.ws_extent(KH_real, pad_h, S)      # below, KH / KW are the extents in phase-plane shifts
     smin_w, KW = packing.ws_extent(KW_real, pad_w, S)
     cin_pad = (Cin + 7) & ~7
@@ -281,3 +283,19 @@ def test_fp16_correction_product_error_bound():
     assert float(err.mean()) < 2.0 ** -23
     plain = (x_hi.double() * w_hi.double() - x.double() * w.double()).abs() / (x.double().abs() * w.double().abs() + 1e-30)
     assert float(plain.mean()) > 50 * float(err.mean())                   # what one TF32 pass alone would give
+
+
+@pytest.mark.parametrize("py", [0, 1])
+def test_phase_launch_bookkeeping(py):
+    """ops.conv_up2's launches: KH = 2 x KW = 3 kernel, padding (1 - py, 1), output height = input height (the row
+    below the image is the TMA's zero fill).  The emulation's tile loader already zero-fills everything outside."""
+    g = torch.Generator().manual_seed(7)
+    C, Cout, H, W = 8, 8, 9, 33
+    x = torch.rand(1, C, H, W, generator=g) - 0.5
+    w3 = torch.rand(Cout, C, 3, 3, generator=g) - 0.5
+    pc = packing.pack_up2_phases(w3)[py]
+    wp = pc.w[0].permute(3, 2, 0, 1)[:pc.cout, :pc.cin].contiguous()          # [2*Cout, C, 2, 3]
+    ref = F.conv2d(F.pad(x.double(), (1, 1, 1 - py, py)), wp.double())[0].permute(1, 2, 0).numpy()
+    got = emulate_ws_conv(x[0].permute(1, 2, 0).double().numpy(), pc, 4, 30, 16, pad=(1 - py, 1), out_hw=(H, W))
+    assert got.shape == ref.shape and not np.isnan(got).any()
+    assert np.abs(got - ref).max() < 1e-6
